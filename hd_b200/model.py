@@ -1,0 +1,88 @@
+"""Host-side mirror of hd's exported data model (reference model.go:18-130, 222-315).
+
+Field names, meaning and mutability follow the Go structs one to one so that a test
+written against hd reads the same against this package:
+
+    Model{Points, Beams[]BeamProp{N,A,J,E}, Pins, Supports}          model.go:18-77
+    LoadCase{LoadNodes, PointDisplacementGlobal, BeamForces, Reactions,
+             AmountLinearBuckling, LinearBucklingResult}              model.go:80-130
+    LoadNode{N, Forces}                                               model.go:304-315
+    ModalCase{ModalMasses, Result}, ModalMass{N, Mass}                model.go:222-228, 294-301
+    ModalResult{Hz, ModalDisplacement}                                model.go:258-272
+    BucklingResult{Factor, PointDisplacementGlobal}                   model.go:275-291
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+Gravity = 9.80665  # model.go:713
+
+
+@dataclass
+class BeamProp:
+    N: List[int]
+    A: float
+    J: float
+    E: float
+
+
+@dataclass
+class Model:
+    Points: List[List[float]] = field(default_factory=list)
+    Beams: List[BeamProp] = field(default_factory=list)
+    Pins: List[List[bool]] = field(default_factory=list)
+    Supports: List[List[bool]] = field(default_factory=list)
+
+    def clone(self) -> "Model":
+        return copy.deepcopy(self)
+
+
+@dataclass
+class LoadNode:
+    N: int
+    Forces: List[float]
+
+
+@dataclass
+class BucklingResult:
+    Factor: float = 0.0
+    PointDisplacementGlobal: Optional[list] = None
+
+
+@dataclass
+class LoadCase:
+    LoadNodes: List[LoadNode] = field(default_factory=list)
+    PointDisplacementGlobal: Optional[list] = None
+    BeamForces: Optional[list] = None
+    Reactions: Optional[list] = None
+    AmountLinearBuckling: int = 0
+    LinearBucklingResult: Optional[list] = None
+
+    def reset(self) -> None:  # model.go:214-219
+        self.PointDisplacementGlobal = None
+        self.BeamForces = None
+        self.Reactions = None
+        self.LinearBucklingResult = None
+
+
+@dataclass
+class ModalMass:
+    N: int
+    Mass: float
+
+
+@dataclass
+class ModalResult:
+    Hz: float = 0.0
+    ModalDisplacement: Optional[list] = None
+
+
+@dataclass
+class ModalCase:
+    ModalMasses: List[ModalMass] = field(default_factory=list)
+    Result: Optional[list] = None
+
+    def reset(self) -> None:  # model.go:231-233
+        self.Result = None
