@@ -1,0 +1,798 @@
+// capi.cu — implementation of the C ABI declared in include/hdb200.h.
+//
+// Host side of the batched LinearStatic / Modal path: the topology handle (symbolic phase +
+// device copies of its schedules), workspace management, the chunked host<->device pipeline
+// for callers that pass host memory, and CUDA-event timing of every kernel.  No torch types,
+// no CPU compute path: without a device the compute entries return HDB_ERR_NO_DEVICE.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "device_topo.hpp"
+#include "hdb_internal.hpp"
+#include "modal.hpp"
+
+namespace hdb {
+
+static thread_local std::string g_detail;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error_detail(const std::string &s) { g_detail = s; }
+void count_launch(int n) { g_launches += n; }
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            char buf__[512];                                                                  \
+            std::snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,  \
+                          cudaGetErrorString(e__));                                           \
+            set_error_detail(buf__);                                                          \
+            return (e__ == cudaErrorMemoryAllocation) ? HDB_ERR_NOMEM : HDB_ERR_CUDA;          \
+        }                                                                                     \
+    } while (0)
+
+struct HostChunk {
+    double *sec = nullptr, *loads = nullptr, *disp = nullptr, *forces = nullptr, *react = nullptr;
+    int32_t *status = nullptr, *fail = nullptr;
+    cudaEvent_t evIn = nullptr, evK = nullptr, evOut = nullptr;
+    size_t bytes = 0;
+    void *base = nullptr;
+};
+constexpr int NBUF = 3;
+
+} // namespace hdb
+
+using namespace hdb;
+
+struct hdb_topology {
+    Symbolic S;
+    int device = 0;
+    bool devReady = false;
+    int smemOptin = 0, smCount = 0;
+    DevTopo D{};
+    std::vector<void *> devAllocs;
+    // workspace of the device path
+    double *W = nullptr, *Ksf = nullptr, *keScratch = nullptr;
+    size_t wsModels = 0;
+    int subBatch = 4096;
+    // host path
+    HostChunk chunk[NBUF];
+    cudaStream_t sIn = nullptr, sK = nullptr, sOut = nullptr; // copy-in, compute, copy-out
+    int chunkModels = 0, chunkLC = 0;
+    // profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
+    std::vector<int> evKind; // kernel kind of interval [2i, 2i+1]
+    int lastKinds = 0;
+    // modal
+    ModalState *modal = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(hdb_topology *t, const std::vector<T> &v, const T **out)
+{
+    void *p = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    t->devAllocs.push_back(p);
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T *)p;
+    return HDB_OK;
+}
+
+static int ensure_device(hdb_topology *t)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        set_error_detail("no CUDA device visible: libhdb200 has no CPU path");
+        return HDB_ERR_NO_DEVICE;
+    }
+    if (t->device < 0 || t->device >= n) {
+        set_error_detail("device ordinal out of range");
+        return HDB_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(t->device));
+    if (t->devReady) return HDB_OK;
+    CUDA_TRY(cudaDeviceGetAttribute(&t->smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, t->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&t->smCount, cudaDevAttrMultiProcessorCount, t->device));
+    const Symbolic &S = t->S;
+    DevTopo &D = t->D;
+    D.nP = S.nP; D.nB = S.nB; D.dof = S.dof; D.nFree = S.nFree; D.nnzL = S.nnzL; D.nSlots = S.nSlots;
+    D.nSup = S.nSup; D.nnzR = S.nnzR; D.nnzK = S.nnzK; D.maxColCount = S.maxColCount;
+    // gather codes -> padded shared-memory indices
+    auto pad = [](const std::vector<int32_t> &src) {
+        std::vector<int32_t> o(src.size());
+        for (size_t i = 0; i < src.size(); i++) o[i] = (src[i] / 36) * KE_LD + (src[i] % 36);
+        return o;
+    };
+    std::vector<uint8_t> dropped((size_t)S.nB * 36, 0);
+    { // scatter is in triplet order (p1,p2,r1,r2); dropped[] is indexed by beam*36 + local row-major
+        size_t q = 0;
+        for (int b = 0; b < S.nB; b++)
+            for (int p1 = 0; p1 < 2; p1++)
+                for (int p2 = 0; p2 < 2; p2++)
+                    for (int r1 = 0; r1 < 3; r1++)
+                        for (int r2 = 0; r2 < 3; r2++, q++)
+                            if (S.scatter[q] < 0) dropped[(size_t)b * 36 + (p1 * 3 + r1) * 6 + (p2 * 3 + r2)] = 1;
+    }
+    int rc;
+#define UP(vec, field)                                  \
+    if ((rc = upload(t, vec, &D.field)) != HDB_OK) return rc
+    UP(S.points, points);
+    UP(S.beamN32, beamN);
+    UP(S.pinMask, pinMask);
+    UP(dropped, dropped);
+    UP(S.gptr, gptr);
+    UP(pad(S.gsrc), gsrc);
+    UP(S.rgptr, rgptr);
+    UP(pad(S.rgsrc), rgsrc);
+    UP(S.kptr, kptr);
+    UP(pad(S.ksrc), ksrc);
+    UP(S.Lp, Lp);
+    UP(S.Li, Li);
+    UP(S.uptr, uptr);
+    UP(S.utgt, utgt);
+    UP(S.rLp, rLp);
+    UP(S.rLcol, rLcol);
+    UP(S.rLslot, rLslot);
+    UP(S.xrow, xrow);
+    UP(S.beamRows, beamRows);
+    UP(S.supIndex, supIndex);
+    UP(S.rptr, rptr);
+    UP(S.rcol, rcol);
+#undef UP
+    if (const char *e = std::getenv("HDB_SUB_BATCH")) {
+        int v = std::atoi(e);
+        if (v >= 32) t->subBatch = v;
+    }
+    t->devReady = true;
+    return HDB_OK;
+}
+
+static int ensure_workspace(hdb_topology *t, size_t models)
+{
+    if (models <= t->wsModels) return HDB_OK;
+    if (t->W) cudaFree(t->W);
+    if (t->Ksf) cudaFree(t->Ksf);
+    if (t->keScratch) cudaFree(t->keScratch);
+    t->W = t->Ksf = t->keScratch = nullptr;
+    t->wsModels = 0;
+    const size_t ld = (models + 31) / 32 * 32;
+    CUDA_TRY(cudaMalloc(&t->W, (size_t)t->S.nSlots * ld * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&t->Ksf, std::max<size_t>(1, models * (size_t)t->S.nnzR) * sizeof(double)));
+    if (!assemble_fits_smem(t->D, t->smemOptin))
+        CUDA_TRY(cudaMalloc(&t->keScratch, models * (size_t)t->S.nB * KE_LD * sizeof(double)));
+    t->wsModels = ld;
+    return HDB_OK;
+}
+
+static bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+enum { KIND_ASSEMBLE = 0, KIND_FACTOR = 1, KIND_SOLVE = 2, KIND_MODAL0 = 3 };
+
+static void prof_reset(hdb_topology *t)
+{
+    t->evKind.clear();
+}
+
+static cudaEvent_t prof_event(hdb_topology *t, size_t i)
+{
+    while (t->events.size() <= i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        t->events.push_back(e);
+    }
+    return t->events[i];
+}
+
+struct ProfScope {
+    hdb_topology *t;
+    cudaStream_t st;
+    size_t slot;
+    bool on;
+    ProfScope(hdb_topology *t_, int kind, cudaStream_t s) : t(t_), st(s), slot(0), on(t_->profiling)
+    {
+        if (!on) return;
+        slot = t->evKind.size();
+        t->evKind.push_back(kind);
+        cudaEventRecord(prof_event(t, 2 * slot), st);
+    }
+    ~ProfScope()
+    {
+        if (on) cudaEventRecord(prof_event(t, 2 * slot + 1), st);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: topology
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int hdb_version(void) { return HDB_VERSION; }
+
+const char *hdb_error_string(int code)
+{
+    switch (code) {
+    case HDB_OK: return "ok";
+    case HDB_ERR_ARG: return "invalid argument";
+    case HDB_ERR_NO_DEVICE: return "no CUDA device (libhdb200 has no CPU path)";
+    case HDB_ERR_CUDA: return "CUDA runtime error";
+    case HDB_ERR_NOMEM: return "out of memory";
+    case HDB_ERR_UNSUPPORTED: return "model too large for the shared-memory resident kernels";
+    case HDB_ERR_INPUT: return "input data rejected";
+    case HDB_ERR_SMALL_BUFFER: return "output buffer too small";
+    default: return "unknown error";
+    }
+}
+
+const char *hdb_last_error_detail(void) { return g_detail.c_str(); }
+
+int64_t hdb_launch_count(void) { return g_launches.load(); }
+
+int hdb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int hdb_topology_create(int32_t nP, const double *points, int32_t nB, const hdb_beam *beams, const uint8_t *pins,
+                        const uint8_t *supports, const hdb_options *opts, hdb_topology **out)
+{
+    if (!out) return HDB_ERR_ARG;
+    *out = nullptr;
+    hdb_topology *t = new (std::nothrow) hdb_topology();
+    if (!t) return HDB_ERR_NOMEM;
+    std::string detail;
+    int rc = build_symbolic(nP, points, nB, beams, pins, supports, opts ? opts->ordering : 0, t->S, detail);
+    if (rc != HDB_OK) {
+        set_error_detail(detail);
+        delete t;
+        return rc;
+    }
+    t->device = (opts && opts->device >= 0) ? opts->device : -1;
+    if (t->device < 0) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) {
+            (void)cudaGetLastError();
+            cur = 0;
+        }
+        t->device = cur;
+    }
+    *out = t;
+    return HDB_OK;
+}
+
+void hdb_topology_destroy(hdb_topology *t)
+{
+    if (!t) return;
+    if (t->devReady) {
+        cudaSetDevice(t->device);
+        cudaDeviceSynchronize();
+        for (void *p : t->devAllocs) cudaFree(p);
+        if (t->W) cudaFree(t->W);
+        if (t->Ksf) cudaFree(t->Ksf);
+        if (t->keScratch) cudaFree(t->keScratch);
+        for (auto &c : t->chunk) {
+            if (c.base) cudaFree(c.base);
+            if (c.evIn) cudaEventDestroy(c.evIn);
+            if (c.evK) cudaEventDestroy(c.evK);
+            if (c.evOut) cudaEventDestroy(c.evOut);
+        }
+        for (cudaStream_t st : {t->sIn, t->sK, t->sOut})
+            if (st) cudaStreamDestroy(st);
+        for (cudaEvent_t e : t->events) cudaEventDestroy(e);
+        modal_state_free(t->modal);
+    }
+    delete t;
+}
+
+int hdb_topology_get_info(const hdb_topology *t, hdb_topology_info *info)
+{
+    if (!t || !info) return HDB_ERR_ARG;
+    std::memset(info, 0, sizeof(*info));
+    const Symbolic &S = t->S;
+    info->nP = S.nP; info->nB = S.nB; info->dof = S.dof; info->nFree = S.nFree;
+    info->nElim = (int32_t)S.elim.size(); info->nIgnore = (int32_t)S.ignore.size(); info->nSupported = S.nSup;
+    info->nnzK = S.nnzK; info->nnzKff = S.nnzKff; info->nnzL = S.nnzL; info->nnzR = S.nnzR;
+    info->nUpdates = (int32_t)S.nUpdates; info->device = t->device;
+    return HDB_OK;
+}
+
+int64_t hdb_topology_query(const hdb_topology *t, int32_t which, void *buf, int64_t capacity)
+{
+    if (!t) return HDB_ERR_ARG;
+    const std::vector<int32_t> *v = nullptr;
+    const Symbolic &S = t->S;
+    switch (which) {
+    case HDB_Q_ELIMINATED: v = &S.elim; break;
+    case HDB_Q_IGNORE: v = &S.ignore; break;
+    case HDB_Q_CSR_ROWPTR: v = &S.rowptr; break;
+    case HDB_Q_CSR_COLIND: v = &S.colind; break;
+    case HDB_Q_SCATTER: v = &S.scatter; break;
+    case HDB_Q_FREE_INDEX: v = &S.freeIndex; break;
+    case HDB_Q_PERM: v = &S.perm; break;
+    case HDB_Q_L_COLPTR: v = &S.Lp; break;
+    case HDB_Q_L_ROWIND: v = &S.Li; break;
+    default: return HDB_ERR_ARG;
+    }
+    const int64_t bytes = (int64_t)v->size() * (int64_t)sizeof(int32_t);
+    if (buf) {
+        if (capacity < bytes) return HDB_ERR_SMALL_BUFFER;
+        if (bytes) std::memcpy(buf, v->data(), (size_t)bytes);
+    }
+    return (int64_t)v->size();
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: validation helpers (check.go) and assemblyNodeLoad
+// ------------------------------------------------------------------------------------------------
+static void copy_msg(const std::string &s, char *msg, int32_t len)
+{
+    if (!msg || len <= 0) return;
+    const size_t n = std::min<size_t>(s.size(), (size_t)len - 1);
+    std::memcpy(msg, s.data(), n);
+    msg[n] = 0;
+}
+
+int hdb_check_model(int32_t nP, const double *points, int32_t nB, const hdb_beam *beams, int32_t nPins,
+                    const uint8_t *pins, int32_t nSupports, const uint8_t *supports, char *msg, int32_t msgLen)
+{
+    if (nP < 0 || nB < 0 || nPins < 0 || nSupports < 0 || (nP > 0 && !points) || (nB > 0 && !beams)) return HDB_ERR_ARG;
+    std::string m;
+    int rc = check_model_impl(nP, points, nB, beams, nPins, pins, nSupports, supports, m);
+    copy_msg(m, msg, msgLen);
+    return rc;
+}
+
+int hdb_check_loads(int32_t nP, int32_t nLoads, const hdb_load_node *loads, char *msg, int32_t msgLen)
+{
+    if (nLoads < 0 || (nLoads > 0 && !loads)) return HDB_ERR_ARG;
+    std::string m;
+    bool err = false;
+    for (int j = 0; j < nLoads; j++) { // check.go:131-155
+        if (loads[j].n < 0 || loads[j].n >= nP) {
+            m += "Error in load case, load position " + std::to_string(j) + " : outside index of point\n";
+            err = true;
+        }
+        for (int k = 0; k < 3; k++)
+            if (std::isnan(loads[j].forces[k]) || std::isinf(loads[j].forces[k])) {
+                m += "Error in load case, load position " + std::to_string(j) + " : not finite force\n";
+                err = true;
+            }
+    }
+    copy_msg(m, msg, msgLen);
+    return err ? HDB_ERR_INPUT : HDB_OK;
+}
+
+int hdb_check_modal(int32_t nP, int32_t nSupports, const uint8_t *supports, int32_t nMasses,
+                    const hdb_modal_mass *masses, char *msg, int32_t msgLen)
+{
+    if (nMasses < 0 || (nMasses > 0 && !masses)) return HDB_ERR_ARG;
+    std::string m;
+    bool err = false;
+    for (int j = 0; j < nMasses; j++) { // check.go:413-447
+        const int64_t n = masses[j].n;
+        const double v = masses[j].mass;
+        if (n < 0 || n >= nP) {
+            m += "Error in modal case, mass position " + std::to_string(j) + " : outside index of point\n";
+            err = true;
+        }
+        if (std::isnan(v) || std::isinf(v) || v < 0 || v == 0) {
+            m += "Error in modal case, mass position " + std::to_string(j) + " : not valid mass\n";
+            err = true;
+        }
+        if (supports && n >= 0 && n < nSupports && (supports[3 * n] || supports[3 * n + 1] || supports[3 * n + 2])) {
+            m += "Error in modal case, mass position " + std::to_string(j) + " : Modal mass on support\n";
+            err = true;
+        }
+    }
+    copy_msg(m, msg, msgLen);
+    return err ? HDB_ERR_INPUT : HDB_OK;
+}
+
+int hdb_assemble_node_loads(int32_t nP, int32_t nLoads, const hdb_load_node *loads, double *p)
+{
+    if (nP < 0 || nLoads < 0 || !p || (nLoads > 0 && !loads)) return HDB_ERR_ARG;
+    for (int i = 0; i < 3 * nP; i++) p[i] = 0.0;
+    for (int j = 0; j < nLoads; j++) { // model.go:687-691
+        if (loads[j].n < 0 || loads[j].n >= nP) return HDB_ERR_INPUT;
+        for (int i = 0; i < 3; i++) p[loads[j].n * 3 + i] += loads[j].forces[i];
+    }
+    return HDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: pinned memory, profiling
+// ------------------------------------------------------------------------------------------------
+int hdb_host_alloc(void **ptr, int64_t bytes)
+{
+    if (!ptr || bytes < 0) return HDB_ERR_ARG;
+    if (hdb_device_count() <= 0) {
+        set_error_detail("hdb_host_alloc: no CUDA device");
+        return HDB_ERR_NO_DEVICE;
+    }
+    CUDA_TRY(cudaHostAlloc(ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    return HDB_OK;
+}
+
+int hdb_host_free(void *ptr)
+{
+    if (!ptr) return HDB_OK;
+    CUDA_TRY(cudaFreeHost(ptr));
+    return HDB_OK;
+}
+
+int hdb_set_profiling(hdb_topology *t, int32_t on)
+{
+    if (!t) return HDB_ERR_ARG;
+    t->profiling = on != 0;
+    return HDB_OK;
+}
+
+int hdb_last_kernel_ms(hdb_topology *t, float *ms, int32_t capacity)
+{
+    if (!t || !ms || capacity <= 0) return HDB_ERR_ARG;
+    int kinds = 0;
+    for (int k : t->evKind) kinds = std::max(kinds, k + 1);
+    kinds = std::min<int>(kinds, capacity);
+    for (int i = 0; i < kinds; i++) ms[i] = 0.f;
+    for (size_t i = 0; i < t->evKind.size(); i++) {
+        float v = 0.f;
+        if (cudaEventSynchronize(t->events[2 * i + 1]) != cudaSuccess) return HDB_ERR_CUDA;
+        if (cudaEventElapsedTime(&v, t->events[2 * i], t->events[2 * i + 1]) != cudaSuccess) return HDB_ERR_CUDA;
+        if (t->evKind[i] < kinds) ms[t->evKind[i]] += v;
+    }
+    return kinds;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: LinearStatic batch
+// ------------------------------------------------------------------------------------------------
+static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
+                          double *disp, double *forces, double *react, int32_t *status, int32_t *failCase,
+                          double *kval, cudaStream_t st, bool solve)
+{
+    const Symbolic &S = t->S;
+    int cp;
+    size_t smem;
+    if (solve && !solve_config(t->D, nLC, t->smemOptin, cp, smem)) {
+        set_error_detail("model does not fit the shared-memory resident solve kernel");
+        return HDB_ERR_UNSUPPORTED;
+    }
+    const int sb = std::min<int>(nModels, t->subBatch);
+    int rc = ensure_workspace(t, (size_t)sb);
+    if (rc != HDB_OK) return rc;
+    for (int m0 = 0; m0 < nModels; m0 += sb) {
+        const int nm = std::min(sb, nModels - m0);
+        StaticLaunch L{};
+        L.nModels = nm;
+        L.nLC = nLC;
+        L.ld = (int)t->wsModels;
+        L.sections = sections + (size_t)m0 * S.nB * 3;
+        L.loads = loads ? loads + (size_t)m0 * nLC * S.dof : nullptr;
+        L.disp = disp ? disp + (size_t)m0 * nLC * S.dof : nullptr;
+        L.forces = forces ? forces + (size_t)m0 * nLC * S.nB * 6 : nullptr;
+        L.react = react ? react + (size_t)m0 * nLC * S.dof : nullptr;
+        L.status = status + m0;
+        L.failCase = failCase ? failCase + m0 : nullptr;
+        L.W = t->W;
+        L.Ksf = t->Ksf;
+        L.kval = kval ? kval + (size_t)m0 * S.nnzK : nullptr;
+        L.keScratch = t->keScratch;
+        {
+            ProfScope ps(t, KIND_ASSEMBLE, st);
+            CUDA_TRY(launch_assemble(t->D, L, st));
+        }
+        count_launch(1);
+        if (!solve) continue;
+        {
+            ProfScope ps(t, KIND_FACTOR, st);
+            CUDA_TRY(launch_factor(t->D, L, st));
+        }
+        {
+            ProfScope ps(t, KIND_SOLVE, st);
+            CUDA_TRY(launch_solve_recover(t->D, L, st));
+        }
+        count_launch(2);
+    }
+    return HDB_OK;
+}
+
+int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
+                         double *disp, double *forces, double *react, int32_t *status, int32_t *failCase, void *stream)
+{
+    if (!t || nModels < 0 || nLC < 0 || !sections || !status || (nLC > 0 && !loads)) return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    if (nModels == 0) return HDB_OK;
+    prof_reset(t);
+    return static_enqueue(t, nModels, sections, nLC, loads, disp, forces, react, status, failCase, nullptr,
+                          (cudaStream_t)stream, true);
+}
+
+static int ensure_chunks(hdb_topology *t, int chunkModels, int nLC)
+{
+    if (t->chunkModels >= chunkModels && t->chunkLC >= nLC && t->chunk[0].base) return HDB_OK;
+    const Symbolic &S = t->S;
+    for (auto &c : t->chunk) {
+        if (c.base) cudaFree(c.base);
+        c.base = nullptr;
+    }
+    const size_t m = (size_t)chunkModels;
+    const size_t nSec = m * S.nB * 3, nLoad = m * nLC * S.dof, nForce = m * nLC * S.nB * 6;
+    const size_t doubles = nSec + 3 * nLoad + nForce;
+    const size_t bytes = doubles * sizeof(double) + 2 * m * sizeof(int32_t) + 256;
+    for (auto &c : t->chunk) {
+        CUDA_TRY(cudaMalloc(&c.base, bytes));
+        double *p = (double *)c.base;
+        c.sec = p; p += nSec;
+        c.loads = p; p += nLoad;
+        c.disp = p; p += nLoad;
+        c.react = p; p += nLoad;
+        c.forces = p; p += nForce;
+        c.status = (int32_t *)p;
+        c.fail = c.status + m;
+        c.bytes = bytes;
+        if (!c.evIn) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c.evIn, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c.evK, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c.evOut, cudaEventDisableTiming));
+        }
+    }
+    if (!t->sIn) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&t->sIn, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&t->sK, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&t->sOut, cudaStreamNonBlocking));
+    }
+    t->chunkModels = chunkModels;
+    t->chunkLC = nLC;
+    return HDB_OK;
+}
+
+int hdb_static_batch(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
+                     double *disp, double *forces, double *react, int32_t *status, int32_t *failCase)
+{
+    if (!t || nModels < 0 || nLC < 0 || !sections || !status || (nLC > 0 && !loads)) return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    if (nModels == 0) return HDB_OK;
+    const bool dev = is_device_ptr(sections);
+    const void *ptrs[] = {loads, disp, forces, react, status, failCase};
+    for (const void *p : ptrs)
+        if (p && is_device_ptr(p) != dev) {
+            set_error_detail("hdb_static_batch: host and device pointers mixed in one call");
+            return HDB_ERR_ARG;
+        }
+    if (dev) {
+        rc = hdb_static_batch_dev(t, nModels, sections, nLC, loads, disp, forces, react, status, failCase, nullptr);
+        if (rc != HDB_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(nullptr));
+        return HDB_OK;
+    }
+    // ---- host memory: chunked three-stage pipeline. copy-in, compute and copy-out each own a stream;
+    //      NBUF device buffers rotate, so H2D(i+1), kernels(i) and D2H(i-1) overlap. ----
+    const Symbolic &S = t->S;
+    const size_t perModel = ((size_t)S.nB * 3 + 3 * (size_t)nLC * S.dof + (size_t)nLC * S.nB * 6) * sizeof(double);
+    int cm = (int)(((size_t)192 << 20) / std::max<size_t>(perModel, 1));
+    cm = std::max(32, std::min(cm, 1024));
+    cm = std::min(cm, nModels);
+    cm = std::min(cm, t->subBatch);
+    rc = ensure_chunks(t, cm, nLC);
+    if (rc != HDB_OK) return rc;
+    prof_reset(t);
+    int it = 0;
+    for (int m0 = 0; m0 < nModels; m0 += t->chunkModels, it++) {
+        HostChunk &c = t->chunk[it % NBUF];
+        const int nm = std::min(t->chunkModels, nModels - m0);
+        if (it >= NBUF) CUDA_TRY(cudaStreamWaitEvent(t->sIn, c.evOut, 0)); // buffer is free again
+        CUDA_TRY(cudaMemcpyAsync(c.sec, sections + (size_t)m0 * S.nB * 3, (size_t)nm * S.nB * 3 * sizeof(double),
+                                 cudaMemcpyHostToDevice, t->sIn));
+        CUDA_TRY(cudaMemcpyAsync(c.loads, loads + (size_t)m0 * nLC * S.dof, (size_t)nm * nLC * S.dof * sizeof(double),
+                                 cudaMemcpyHostToDevice, t->sIn));
+        CUDA_TRY(cudaEventRecord(c.evIn, t->sIn));
+        CUDA_TRY(cudaStreamWaitEvent(t->sK, c.evIn, 0));
+        rc = static_enqueue(t, nm, c.sec, nLC, c.loads, disp ? c.disp : nullptr, forces ? c.forces : nullptr,
+                            react ? c.react : nullptr, c.status, c.fail, nullptr, t->sK, true);
+        if (rc != HDB_OK) return rc;
+        CUDA_TRY(cudaEventRecord(c.evK, t->sK));
+        CUDA_TRY(cudaStreamWaitEvent(t->sOut, c.evK, 0));
+        if (disp)
+            CUDA_TRY(cudaMemcpyAsync(disp + (size_t)m0 * nLC * S.dof, c.disp, (size_t)nm * nLC * S.dof * sizeof(double),
+                                     cudaMemcpyDeviceToHost, t->sOut));
+        if (forces)
+            CUDA_TRY(cudaMemcpyAsync(forces + (size_t)m0 * nLC * S.nB * 6, c.forces,
+                                     (size_t)nm * nLC * S.nB * 6 * sizeof(double), cudaMemcpyDeviceToHost, t->sOut));
+        if (react)
+            CUDA_TRY(cudaMemcpyAsync(react + (size_t)m0 * nLC * S.dof, c.react, (size_t)nm * nLC * S.dof * sizeof(double),
+                                     cudaMemcpyDeviceToHost, t->sOut));
+        CUDA_TRY(cudaMemcpyAsync(status + m0, c.status, (size_t)nm * sizeof(int32_t), cudaMemcpyDeviceToHost, t->sOut));
+        if (failCase)
+            CUDA_TRY(cudaMemcpyAsync(failCase + m0, c.fail, (size_t)nm * sizeof(int32_t), cudaMemcpyDeviceToHost, t->sOut));
+        CUDA_TRY(cudaEventRecord(c.evOut, t->sOut));
+    }
+    CUDA_TRY(cudaStreamSynchronize(t->sOut));
+    return HDB_OK;
+}
+
+// stage a host array on the device for the small test entry points
+struct Staged {
+    void *dev = nullptr;
+    bool owned = false;
+    ~Staged()
+    {
+        if (owned && dev) cudaFree(dev);
+    }
+};
+
+static int stage_in(const void *p, size_t bytes, Staged &s)
+{
+    if (is_device_ptr(p)) {
+        s.dev = const_cast<void *>(p);
+        return HDB_OK;
+    }
+    CUDA_TRY(cudaMalloc(&s.dev, std::max<size_t>(bytes, 1)));
+    s.owned = true;
+    if (p && bytes) CUDA_TRY(cudaMemcpy(s.dev, p, bytes, cudaMemcpyHostToDevice));
+    return HDB_OK;
+}
+
+static int stage_out(void *p, size_t bytes, Staged &s)
+{
+    if (!p) return HDB_OK;
+    if (is_device_ptr(p)) {
+        s.dev = p;
+        return HDB_OK;
+    }
+    CUDA_TRY(cudaMalloc(&s.dev, std::max<size_t>(bytes, 1)));
+    s.owned = true;
+    return HDB_OK;
+}
+
+static int fetch_out(void *p, size_t bytes, Staged &s)
+{
+    if (p && s.owned && bytes) CUDA_TRY(cudaMemcpy(p, s.dev, bytes, cudaMemcpyDeviceToHost));
+    return HDB_OK;
+}
+
+int hdb_assemble_batch(hdb_topology *t, int32_t nModels, const double *sections, double *kval, int32_t *status)
+{
+    if (!t || nModels <= 0 || !sections || !kval || !status) return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    const Symbolic &S = t->S;
+    Staged sec, kv, stt;
+    const size_t bSec = (size_t)nModels * S.nB * 3 * sizeof(double), bK = (size_t)nModels * S.nnzK * sizeof(double),
+                 bSt = (size_t)nModels * sizeof(int32_t);
+    if ((rc = stage_in(sections, bSec, sec)) != HDB_OK) return rc;
+    if ((rc = stage_out(kval, bK, kv)) != HDB_OK) return rc;
+    if ((rc = stage_out(status, bSt, stt)) != HDB_OK) return rc;
+    prof_reset(t);
+    rc = static_enqueue(t, nModels, (const double *)sec.dev, 0, nullptr, nullptr, nullptr, nullptr, (int32_t *)stt.dev,
+                        nullptr, (double *)kv.dev, nullptr, false);
+    if (rc != HDB_OK) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if ((rc = fetch_out(kval, bK, kv)) != HDB_OK) return rc;
+    return fetch_out(status, bSt, stt);
+}
+
+int hdb_element_batch(hdb_topology *t, int32_t nModels, const double *sections, double *klocal, double *tr,
+                      double *kglobal)
+{
+    if (!t || nModels <= 0 || !sections) return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    const Symbolic &S = t->S;
+    Staged sec, a, b, c;
+    const size_t bSec = (size_t)nModels * S.nB * 3 * sizeof(double), bM = (size_t)nModels * S.nB * 36 * sizeof(double);
+    if ((rc = stage_in(sections, bSec, sec)) != HDB_OK) return rc;
+    if ((rc = stage_out(klocal, bM, a)) != HDB_OK) return rc;
+    if ((rc = stage_out(tr, bM, b)) != HDB_OK) return rc;
+    if ((rc = stage_out(kglobal, bM, c)) != HDB_OK) return rc;
+    CUDA_TRY(launch_elements(t->D, nModels, (const double *)sec.dev, (double *)a.dev, (double *)b.dev, (double *)c.dev,
+                             nullptr));
+    count_launch(1);
+    CUDA_TRY(cudaDeviceSynchronize());
+    if ((rc = fetch_out(klocal, bM, a)) != HDB_OK) return rc;
+    if ((rc = fetch_out(tr, bM, b)) != HDB_OK) return rc;
+    return fetch_out(kglobal, bM, c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: Modal batch (kernels in kernels_modal.cu)
+// ------------------------------------------------------------------------------------------------
+int hdb_modal_mode_count(const hdb_topology *t, int32_t nMass, const int64_t *massN)
+{
+    if (!t || nMass < 0 || (nMass > 0 && !massN)) return HDB_ERR_ARG;
+    std::vector<int32_t> rows;
+    return modal_mass_rows(t->S, nMass, massN, rows, nullptr);
+}
+
+int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nMass, const int64_t *massN,
+                        const double *mass, int32_t maxModes, int32_t *nModes, double *hz, double *shapes,
+                        int32_t *status, void *stream)
+{
+    if (!t || nModels < 0 || !sections || nMass < 0 || (nMass > 0 && (!massN || !mass)) || !nModes || !hz || !status)
+        return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    if (nModels == 0) return HDB_OK;
+    prof_reset(t);
+    const int sb = std::min<int>(nModels, t->subBatch);
+    rc = ensure_workspace(t, (size_t)sb);
+    if (rc != HDB_OK) return rc;
+    ModalArgs A{};
+    A.nModels = nModels; A.sections = sections; A.nMass = nMass; A.massN = massN; A.mass = mass;
+    A.maxModes = maxModes; A.nModes = nModes; A.hz = hz; A.shapes = shapes; A.status = status;
+    A.W = t->W; A.Ksf = t->Ksf; A.keScratch = t->keScratch; A.ld = (int)t->wsModels; A.subBatch = sb;
+    A.smemOptin = t->smemOptin;
+    std::string detail;
+    int launches = 0;
+    rc = modal_enqueue(t->S, t->D, &t->modal, A, (cudaStream_t)stream, detail, launches);
+    count_launch(launches);
+    if (rc != HDB_OK) set_error_detail(detail);
+    return rc;
+}
+
+int hdb_modal_batch(hdb_topology *t, int32_t nModels, const double *sections, int32_t nMass, const int64_t *massN,
+                    const double *mass, int32_t maxModes, int32_t *nModes, double *hz, double *shapes, int32_t *status)
+{
+    if (!t || nModels < 0 || !sections || nMass < 0 || (nMass > 0 && (!massN || !mass)) || !nModes || !hz || !status ||
+        maxModes < 0)
+        return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    if (nModels == 0) return HDB_OK;
+    if (is_device_ptr(sections)) {
+        rc = hdb_modal_batch_dev(t, nModels, sections, nMass, massN, mass, maxModes, nModes, hz, shapes, status, nullptr);
+        if (rc != HDB_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(nullptr));
+        return HDB_OK;
+    }
+    const Symbolic &S = t->S;
+    Staged sec, ms, nm, hzS, sh, stt;
+    const size_t bSec = (size_t)nModels * S.nB * 3 * sizeof(double), bMass = (size_t)nModels * nMass * sizeof(double);
+    const size_t bN = (size_t)nModels * sizeof(int32_t), bHz = (size_t)nModels * maxModes * sizeof(double);
+    const size_t bSh = (size_t)nModels * maxModes * S.dof * sizeof(double);
+    if ((rc = stage_in(sections, bSec, sec)) != HDB_OK) return rc;
+    if ((rc = stage_in(mass, bMass, ms)) != HDB_OK) return rc;
+    if ((rc = stage_out(nModes, bN, nm)) != HDB_OK) return rc;
+    if ((rc = stage_out(hz, bHz, hzS)) != HDB_OK) return rc;
+    if ((rc = stage_out(shapes, bSh, sh)) != HDB_OK) return rc;
+    if ((rc = stage_out(status, bN, stt)) != HDB_OK) return rc;
+    rc = hdb_modal_batch_dev(t, nModels, (const double *)sec.dev, nMass, massN, (const double *)ms.dev, maxModes,
+                             (int32_t *)nm.dev, (double *)hzS.dev, (double *)sh.dev, (int32_t *)stt.dev, nullptr);
+    if (rc != HDB_OK) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if ((rc = fetch_out(nModes, bN, nm)) != HDB_OK) return rc;
+    if ((rc = fetch_out(hz, bHz, hzS)) != HDB_OK) return rc;
+    if ((rc = fetch_out(shapes, bSh, sh)) != HDB_OK) return rc;
+    return fetch_out(status, bN, stt);
+}
+
+} // extern "C"

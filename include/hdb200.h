@@ -1,0 +1,202 @@
+/*
+ * hdb200.h — C ABI of libhdb200.so: the B200-native batched replacement of the
+ * linear-analysis hot path of Konstantin8105/hd.
+ *
+ * Boundary (reference side, paths relative to the reference repository root):
+ *   hd.Run(out, *Model, []LoadCase, []ModalCase)            model.go:926-969
+ *   hd.LinearStatic(out, *Model, ...*LoadCase)              model.go:358-605
+ *   hd.Modal(out, *Model, *ModalCase)                       model.go:719-851
+ * A Go shim keeps those three signatures and the exported structs, keeps check.go and the
+ * text reports in Go, flattens the structs and makes ONE cgo call per phase into the entry
+ * points below (see INTEGRATION.md for the cgo binding).  Everything the reference delegates
+ * to Konstantin8105/sparse and gonum/mat on this path is computed on the GPU; there is no CPU
+ * fallback: without a CUDA device every compute entry returns HDB_ERR_NO_DEVICE.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays are dense, row-major, C order;
+ *   - data pointers of the *_batch calls may be HOST (pageable or pinned, see hdb_host_alloc)
+ *     or DEVICE memory of the topology's device — detected per pointer; host data is staged
+ *     through pinned buffers in chunks with copies overlapped with compute;
+ *   - no Go pointer is retained after a call returns; calls are synchronous unless a stream is
+ *     passed to a *_dev variant;
+ *   - return value: 0 ok, <0 API / CUDA error (hdb_error_string). Per-model numerical outcomes
+ *     are reported in status[model] (HDB_STATUS_*), so one bad model never poisons a batch;
+ *   - thread safety: a topology handle is single-owner (one call at a time per handle);
+ *     distinct handles may be used from distinct threads. Every entry sets its device.
+ */
+#ifndef HDB200_H
+#define HDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDB_VERSION 100
+
+/* ---- return codes ---- */
+enum {
+    HDB_OK = 0,
+    HDB_ERR_ARG = -1,         /* NULL / negative size / inconsistent argument          */
+    HDB_ERR_NO_DEVICE = -2,   /* no CUDA device: the product has no CPU path           */
+    HDB_ERR_CUDA = -3,        /* CUDA runtime error (hdb_last_error_detail)            */
+    HDB_ERR_NOMEM = -4,
+    HDB_ERR_UNSUPPORTED = -5, /* model too large for the resident kernels, see DESIGN.md */
+    HDB_ERR_INPUT = -6,       /* topology rejected (what check.go rejects for shared data) */
+    HDB_ERR_SMALL_BUFFER = -7
+};
+
+/* ---- per-model status (int32) ---- */
+enum {
+    HDB_STATUS_OK = 0,
+    HDB_STATUS_NONFINITE = 1,   /* NaN/Inf/non-positive section or NaN/Inf matrix entry or load:
+                                   check.go:301-324, model.go:692-696                          */
+    HDB_STATUS_SINGULAR = 2,    /* zero / negative / non-finite pivot: "LU error factorization",
+                                   model.go:326-331                                            */
+    HDB_STATUS_IGNORE_LOAD = 3, /* non-zero load on an `ignore` DOF, model.go:424-437; the
+                                   offending case index is written to fail_case[model]          */
+    HDB_STATUS_EIGEN = 4,       /* eigen iteration did not converge, model.go:809-811           */
+    HDB_STATUS_PATTERN = 5      /* an element entry that is exactly 0.0 in the topology's
+                                   representative model is non-zero in this model: its sparsity
+                                   pattern (model.go:645-649) differs, solve it under its own
+                                   topology handle                                              */
+};
+
+/* Go hd.BeamProp memory layout (model.go:58-77): N [2]int, A, J, E float64 = 40 bytes. */
+typedef struct hdb_beam {
+    int64_t n0, n1;
+    double A, J, E;
+} hdb_beam;
+
+/* Go hd.LoadNode (model.go:304-315): N int, Forces [3]float64 = 32 bytes. */
+typedef struct hdb_load_node {
+    int64_t n;
+    double forces[3];
+} hdb_load_node;
+
+/* Go hd.ModalMass (model.go:294-301): N int, Mass float64 = 16 bytes. */
+typedef struct hdb_modal_mass {
+    int64_t n;
+    double mass;
+} hdb_modal_mass;
+
+typedef struct hdb_options {
+    int32_t device;    /* CUDA device ordinal; -1 = current device                         */
+    int32_t ordering;  /* 0 natural (identity permutation: what the reference's LU uses),
+                          1 reverse Cuthill-McKee on the free-DOF node graph               */
+    int32_t reserved[6];
+} hdb_options;
+
+typedef struct hdb_topology hdb_topology; /* opaque */
+
+typedef struct hdb_topology_info {
+    int32_t nP, nB, dof;
+    int32_t nFree, nElim, nIgnore, nSupported;
+    int32_t nnzK;      /* entries of the assembled K after model.go:645-652 (zeros dropped, duplicates summed) */
+    int32_t nnzKff;    /* of which both row and column are free                                               */
+    int32_t nnzL;      /* strictly-lower entries of the LDL^T factor incl. fill                               */
+    int32_t nnzR;      /* entries of the supported rows x free columns block used for reactions               */
+    int32_t nUpdates;  /* multiply-subtract operations of one numeric factorization                           */
+    int32_t device;
+    int32_t reserved[3];
+} hdb_topology_info;
+
+/* integer structures, for bit-exact comparison against the reference / oracle */
+enum {
+    HDB_Q_ELIMINATED = 0, /* int32[nElim]   sort-unique(ignore ++ supports), model.go:326-328, 700-710 */
+    HDB_Q_IGNORE = 1,     /* int32[nIgnore] DOFs without a diagonal entry, model.go:657-678            */
+    HDB_Q_CSR_ROWPTR = 2, /* int32[dof+1]   pattern of K, canonical CSR, ascending columns             */
+    HDB_Q_CSR_COLIND = 3, /* int32[nnzK]                                                               */
+    HDB_Q_SCATTER = 4,    /* int32[nB*36]   triplet (beam, p1,p2,r1,r2 order of model.go:622-635) ->
+                                            CSR slot, -1 where the entry is exactly zero (dropped)     */
+    HDB_Q_FREE_INDEX = 5, /* int32[dof]     reduced index of a DOF or -1 (eliminated)                  */
+    HDB_Q_PERM = 6,       /* int32[nFree]   elimination order: position -> reduced index               */
+    HDB_Q_L_COLPTR = 7,   /* int32[nFree+1] pattern of L (strictly lower, CSC, permuted numbering)     */
+    HDB_Q_L_ROWIND = 8    /* int32[nnzL]                                                               */
+};
+
+/* ---- symbolic phase: replaces the structural half of getK/assemblyK (model.go:318-333, 607-681) ----
+ * points[nP][2], beams[nB] (Go layout; A,J,E of this call are the REPRESENTATIVE sections that
+ * define the value-dependent pattern), pins[nB][6] or NULL (= all rigid, model.go:344-346),
+ * supports[nP][3].  Runs entirely on the host; needs no GPU until the first compute call. */
+int hdb_topology_create(int32_t nP, const double *points, int32_t nB, const hdb_beam *beams,
+                        const uint8_t *pins, const uint8_t *supports, const hdb_options *opts,
+                        hdb_topology **out);
+void hdb_topology_destroy(hdb_topology *t);
+int hdb_topology_get_info(const hdb_topology *t, hdb_topology_info *info);
+/* copies structure `which` into buf (capacity in bytes); returns the element count or <0 */
+int64_t hdb_topology_query(const hdb_topology *t, int32_t which, void *buf, int64_t capacity);
+
+/* ---- input validation of check.go, for host shims that do not carry their own ----
+ * Returns HDB_OK or HDB_ERR_INPUT; a human-readable list is written to msg (may be NULL).
+ * nPins / nSupports are the lengths of the caller's slices (check.go:333, 353). */
+int hdb_check_model(int32_t nP, const double *points, int32_t nB, const hdb_beam *beams,
+                    int32_t nPins, const uint8_t *pins, int32_t nSupports, const uint8_t *supports,
+                    char *msg, int32_t msgLen);                                   /* check.go:12-109, 223-397 */
+int hdb_check_loads(int32_t nP, int32_t nLoads, const hdb_load_node *loads,
+                    char *msg, int32_t msgLen);                                   /* check.go:127-163 */
+int hdb_check_modal(int32_t nP, int32_t nSupports, const uint8_t *supports, int32_t nMasses,
+                    const hdb_modal_mass *masses, char *msg, int32_t msgLen);     /* check.go:411-452 */
+/* assemblyNodeLoad (model.go:683-698): LoadNodes -> dense p[dof], accumulated in order. */
+int hdb_assemble_node_loads(int32_t nP, int32_t nLoads, const hdb_load_node *loads, double *p);
+
+/* ---- LinearStatic for a batch of models sharing the topology (model.go:401-490) ----
+ * sections[nModels][nB][3] (A,J,E per beam), loads[nModels][nLC][dof] (assemblyNodeLoad output),
+ * disp[nModels][nLC][nP][3], forces[nModels][nLC][nB][6], react[nModels][nLC][nP][3] (zero on
+ * unsupported DOFs), status[nModels], failCase[nModels] (may be NULL).  Any of disp / forces /
+ * react may be NULL (not materialised). */
+int hdb_static_batch(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC,
+                     const double *loads, double *disp, double *forces, double *react,
+                     int32_t *status, int32_t *failCase);
+/* all pointers are device memory; enqueues on `stream` (a cudaStream_t, NULL = default stream)
+ * and returns without synchronising.  Workspace lives in the handle and grows on demand. */
+int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC,
+                         const double *loads, double *disp, double *forces, double *react,
+                         int32_t *status, int32_t *failCase, void *stream);
+
+/* assembled stiffness values only (tests): kval[nModels][nnzK] in HDB_Q_CSR_* order, bit-exact
+ * against the reference's summation order (beam order, model.go:652). Host or device pointers. */
+int hdb_assemble_batch(hdb_topology *t, int32_t nModels, const double *sections, double *kval,
+                       int32_t *status);
+/* element matrices only (tests): klocal[nModels][nB][36] (getStiffBeam2d, feBeam2d.go:22-140),
+ * tr[nModels][nB][36] (getCoordTransStiffBeam2d, feBeam2d.go:142-172), kglobal[nModels][nB][36]
+ * ((T^T k) T, model.go:619-620); any may be NULL. Host or device pointers. */
+int hdb_element_batch(hdb_topology *t, int32_t nModels, const double *sections, double *klocal,
+                      double *tr, double *kglobal);
+
+/* ---- Modal for a batch (model.go:719-851) ----
+ * masses: massN[nMass] (shared), mass[nModels][nMass] in newtons (divided by Gravity on device,
+ * model.go:787).  Outputs ascending in Hz: nModes[nModels], hz[nModels][maxModes],
+ * shapes[nModels][maxModes][nP][3] (unit 2-norm over 3*nP entries; sign is implementation-
+ * defined as in LAPACK), status[nModels].  maxModes >= number of distinct free mass DOFs
+ * (hdb_modal_mode_count). */
+int hdb_modal_mode_count(const hdb_topology *t, int32_t nMass, const int64_t *massN);
+int hdb_modal_batch(hdb_topology *t, int32_t nModels, const double *sections, int32_t nMass,
+                    const int64_t *massN, const double *mass, int32_t maxModes, int32_t *nModes,
+                    double *hz, double *shapes, int32_t *status);
+int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nMass,
+                        const int64_t *massN /*host*/, const double *mass, int32_t maxModes,
+                        int32_t *nModes, double *hz, double *shapes, int32_t *status, void *stream);
+
+/* ---- pinned host memory for asynchronous batches (cgo: wrap with unsafe.Slice) ---- */
+int hdb_host_alloc(void **ptr, int64_t bytes);
+int hdb_host_free(void *ptr);
+
+/* ---- measurement: CUDA-event time of each kernel of the last *_dev / *_batch call ----
+ * ms[0..n): static: {assemble, factor, solve_recover}; modal: {assemble, factor, reduce, eigen,
+ * shapes}.  Blocks until the events have completed.  Returns the count written. */
+int hdb_set_profiling(hdb_topology *t, int32_t on);
+int hdb_last_kernel_ms(hdb_topology *t, float *ms, int32_t capacity);
+/* number of kernels this library has launched in the process (the bench's gpu_launches). */
+int64_t hdb_launch_count(void);
+
+int hdb_device_count(void);
+const char *hdb_error_string(int code);
+const char *hdb_last_error_detail(void);
+int hdb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDB200_H */

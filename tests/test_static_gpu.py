@@ -1,0 +1,370 @@
+"""GPU parity tests of the batched LinearStatic path, all through the C ABI (libhdb200.so):
+element matrices and assembled K bit-exact against the oracle; displacements, beam forces and
+reactions within 1e-9 (mod.Compare rule, mod/compare.go:28-66); the reference's goldens; status
+codes; ragged / edge shapes; full-size property checks."""
+import os
+
+import numpy as np
+import pytest
+
+import fixtures
+from hd_b200 import _lib, api, frames
+from hd_b200.model import LoadCase, LoadNode
+from test_oracle_golden import GOLD, close
+
+pytestmark = pytest.mark.gpu
+EPS = 1e-9
+
+
+def topo_of(oracle, m, **kw):
+    fm = oracle.flatten_model(m)
+    return fm, _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports, **kw)
+
+
+def compare_rule(exp, act, eps=EPS):
+    """mod.Compare: relative difference per component, absolute when the expected value is 0."""
+    exp, act = np.asarray(exp), np.asarray(act)
+    z = exp == 0.0
+    assert np.all(np.abs(act[z]) <= eps), np.abs(act[z]).max()
+    rel = np.abs((exp[~z] - act[~z]) / exp[~z])
+    assert rel.size == 0 or rel.max() <= eps, rel.max()
+
+
+def force_rule(exp, act, eps=EPS):
+    """Beam forces: relative per component, with components below 1e-6 of the case's largest force
+    judged against that scale (they are differences of O(1) terms)."""
+    exp, act = np.asarray(exp), np.asarray(act)
+    scale = np.abs(exp).max(axis=(-1, -2), keepdims=True)
+    den = np.maximum(np.abs(exp), 1e-6 * scale)
+    den[den == 0] = 1.0
+    assert (np.abs(exp - act) / den).max() <= eps, (np.abs(exp - act) / den).max()
+
+
+def random_sections(fm, n, seed=1):
+    rng = np.random.default_rng(seed)
+    return fm.sections[None] * rng.uniform(0.5, 2.0, size=(n, fm.nB, 3))
+
+
+# ------------------------------------------------------------------ elements, assembly: bit-exact
+@pytest.mark.parametrize("name", ["truss", "truss-modal", "model.String", "g-beam", "beam-frame-modal"])
+def test_element_and_assembly_bit_exact_examples(oracle, name):
+    m = fixtures.GOLDEN[name]()[0]
+    fm, t = topo_of(oracle, m)
+    secs = np.concatenate([fm.sections[None], random_sections(fm, 7)])
+    k, tr, kg = t.element_batch(secs)
+    for mi in range(secs.shape[0]):
+        for b in range(fm.nB):
+            xy = np.concatenate([fm.points[fm.beamN[b, 0]], fm.points[fm.beamN[b, 1]]])
+            ko = oracle.stiff_beam2d(xy, *secs[mi, b], fm.pins[b])
+            to = oracle.trans_beam2d(xy)
+            assert np.array_equal(k[mi, b], ko), (name, mi, b)
+            assert np.array_equal(tr[mi, b], to)
+            assert np.array_equal(kg[mi, b], oracle.rotate_to_global(ko, to))
+    status, kval = t.assemble_batch(secs)
+    assert not status.any()
+    for mi in range(secs.shape[0]):
+        a = oracle.assemble(fm.with_sections(secs[mi]))
+        assert np.array_equal(kval[mi], a["csr"][2]), (name, mi)
+    t.close()
+
+
+def test_element_all_pin_patterns_bit_exact(oracle):
+    """every pin combination check.go:357-391 admits, on a skewed member."""
+    pts = np.array([[0.0, 0.0], [3.0, 4.0]])
+    for mask in range(64):
+        pins = [(mask >> i) & 1 for i in range(6)]
+        if sum(pins) > 4 or (pins[0] and pins[3]) or (pins[2] and pins[5] and not (pins[1] and pins[4])):
+            continue
+        ko = oracle.stiff_beam2d([0, 0, 3, 4], 12e-4, 120e-6, 2e11, pins)
+        if not np.all(np.isfinite(ko)) or not np.any(np.diag(oracle.rotate_to_global(ko, oracle.trans_beam2d([0, 0, 3, 4])))[:3]):
+            continue
+        try:
+            t = _lib.Topology(pts, [[0, 1]], [[12e-4, 120e-6, 2e11]], [pins], [[1, 1, 1], [0, 0, 0]])
+        except _lib.HdbError:
+            continue
+        k, tr, kg = t.element_batch(np.array([[[12e-4, 120e-6, 2e11]]]))
+        assert np.array_equal(k[0, 0], ko), pins
+        assert np.array_equal(kg[0, 0], oracle.rotate_to_global(ko, oracle.trans_beam2d([0, 0, 3, 4]))), pins
+        t.close()
+
+
+@pytest.mark.parametrize("N", [8, 128])
+def test_assembly_bit_exact_uniform_frame(oracle, N):
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    secs = frames.uniform_frame_sections(N, 3, 5)
+    status, kval = t.assemble_batch(secs)
+    assert not status.any()
+    for mi in range(5):
+        assert np.array_equal(kval[mi], oracle.assemble(fm.with_sections(secs[mi]))["csr"][2])
+    t.close()
+
+
+# ------------------------------------------------------------------ static parity vs oracle
+@pytest.mark.parametrize("N,nM", [(8, 33), (64, 6), (128, 4)])
+def test_static_uniform_frame_vs_oracle(oracle, N, nM):
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    secs = frames.uniform_frame_sections(N, 100, nM)
+    loads = frames.uniform_frame_loads(N, 100, nM)
+    status, fail, disp, forces, react = t.static_batch(secs, loads)
+    assert not status.any() and np.all(fail == -1)
+    ost, od, of, orr = oracle.static_batch(fm, secs, loads)
+    assert not ost.any()
+    compare_rule(od, disp)
+    compare_rule(orr, react)
+    force_rule(of, forces)
+    t.close()
+
+
+@pytest.mark.parametrize("ic", [8, 32])
+def test_static_bench_cantilever_vs_oracle(oracle, ic):
+    """the reference's own benchmark model (mod/split_test.go:93-124); cond(K) grows like ic^4, so the
+    1e-9 rule is only meaningful for the smaller splits."""
+    m, lcs, _ = frames.bench_cantilever(ic)
+    fm, t = topo_of(oracle, m)
+    loads = np.stack([oracle.node_loads(fm.nP, lc.LoadNodes) for lc in lcs])[None]
+    status, fail, disp, forces, react = t.static_batch(fm.sections[None], loads)
+    assert not status.any()
+    rc, od, of, orr, _ = oracle.linear_static(fm, loads[0])
+    assert rc == 0
+    eps = 1e-9 if ic <= 8 else 1e-8
+    compare_rule(od, disp[0], eps)
+    compare_rule(orr, react[0], eps)
+    force_rule(of, forces[0], eps)
+    t.close()
+
+
+def test_static_cantilever128_against_refined_solution(oracle):
+    """bench_cantilever(128) has cond(K_ff) = 6.4e9: the oracle and the GPU are each only defined to a
+    few 1e-9 there.  Both are measured against an iteratively refined (longdouble residual) solution
+    and the GPU must not be worse than the reference-style oracle (SURVEY.md §8(d) parity protocol)."""
+    m, lcs, _ = frames.bench_cantilever(128)
+    fm, t = topo_of(oracle, m)
+    loads = np.stack([oracle.node_loads(fm.nP, lc.LoadNodes) for lc in lcs])[None]
+    status, fail, disp, forces, react = t.static_batch(fm.sections[None], loads)
+    assert not status.any()
+    rc, od, _, _, _ = oracle.linear_static(fm, loads[0])
+    a = oracle.assemble(fm)
+    rp, ci, val = a["csr"]
+    K = np.zeros((fm.dof, fm.dof))
+    for i in range(fm.dof):
+        K[i, ci[rp[i]:rp[i + 1]]] = val[rp[i]:rp[i + 1]]
+    _, elim, _ = oracle.eliminated(fm)
+    free = np.setdiff1d(np.arange(fm.dof), elim)
+    Kf = K[np.ix_(free, free)]
+    Kl = Kf.astype(np.longdouble)
+    p = loads[0, 0][free]
+    x = np.linalg.solve(Kf, p)
+    for _ in range(5):
+        r = (p.astype(np.longdouble) - Kl @ x.astype(np.longdouble)).astype(np.float64)
+        x = x + np.linalg.solve(Kf, r)
+    g = disp[0, 0].reshape(-1)[free]
+    o = od[0].reshape(-1)[free]
+    err_gpu = np.abs((g - x) / x).max()
+    err_orc = np.abs((o - x) / x).max()
+    assert err_gpu <= max(2 * err_orc, 1e-8), (err_gpu, err_orc)
+    t.close()
+
+
+# ------------------------------------------------------------------ the reference's goldens, via hd.Run mirror
+@pytest.mark.parametrize("name", sorted(k for k, v in GOLD.items() if v["static"] and all(c["buckling"] is None for c in v["static"])))
+def test_golden_static_through_run(oracle, name):
+    m, lcs, mcs = fixtures.GOLDEN[name]()
+    err = api.LinearStatic(None, m, *lcs)
+    assert err is None, err
+    m2, lcs2, _ = fixtures.GOLDEN[name]()
+    oerr, ostat, _ = oracle.run(m2, lcs2, [])
+    for ci, g in enumerate(GOLD[name]["static"]):
+        close(lcs[ci].PointDisplacementGlobal, g["disp"], f"{name} disp")
+        close(lcs[ci].BeamForces, g["forces"], f"{name} forces")
+        react = np.zeros((len(m.Points), 3))
+        for pt, v in g["react"].items():
+            react[int(pt)] = v
+        close(lcs[ci].Reactions, react, f"{name} react")
+        compare_rule(ostat[ci]["disp"], lcs[ci].PointDisplacementGlobal)
+        compare_rule(ostat[ci]["react"], lcs[ci].Reactions)
+        force_rule(ostat[ci]["forces"], np.array(lcs[ci].BeamForces))
+
+
+def test_split_property_on_gpu(oracle):
+    """TestSplit (mod/split_test.go:31-91): refining every beam leaves reactions and displacements of the
+    original points unchanged at 1e-9."""
+    for ctor in (fixtures.console_beam, fixtures.g_beam, fixtures.truss):
+        m, lcs, _ = ctor()
+        assert api.LinearStatic(None, m, *lcs) is None
+        nP0 = len(m.Points)
+        for i in (1, 4, 9):
+            ml, lcl, _ = ctor()
+            for j in range(len(ml.Beams)):
+                frames.split_beam(ml, j, i)
+            assert api.LinearStatic(None, ml, *lcl) is None
+            act = [LoadCase(PointDisplacementGlobal=lc.PointDisplacementGlobal[:nP0], Reactions=lc.Reactions[:nP0]) for lc in lcl]
+            assert frames.compare(lcs, act, 1e-9) == []
+
+
+def test_direction_and_rotation_on_gpu(oracle):
+    import math
+    from test_oracle_properties import _rot_model
+    m, _, _ = fixtures.console_beam()
+    lcs = [LoadCase(LoadNodes=[LoadNode(1, f)]) for f in ([100.0, 0, 0], [0, 100.0, 0], [0, 0, 100.0])]
+    assert api.Run(None, m, lcs, []) is None
+    assert lcs[0].PointDisplacementGlobal[1][0] > 0 and lcs[1].PointDisplacementGlobal[1][1] > 0 and lcs[2].PointDisplacementGlobal[1][1] > 0
+    for angle in np.arange(0.0, 361.0, 35.0):
+        mm = _rot_model(angle)
+        lc = LoadCase(LoadNodes=[LoadNode(2, [100 * math.cos(math.pi / 180 * angle), 100 * math.sin(math.pi / 180 * angle), 0.0])])
+        assert api.LinearStatic(None, mm, lc) is None
+        for b, o in ((0, 0), (0, 3), (1, 0), (1, 3)):
+            assert abs(math.hypot(lc.BeamForces[b][o], lc.BeamForces[b][o + 1]) - 100) / 100 <= 1e-6
+        assert abs(math.hypot(lc.Reactions[0][0], lc.Reactions[0][1]) - 100) / 100 <= 1e-6
+
+
+# ------------------------------------------------------------------ status codes, negative tests
+def test_status_codes(oracle):
+    # ignore-load (TestWrongLoad, model_test.go:18-25): moment on a fully pinned truss node
+    m, lcs, _ = fixtures.truss()
+    lcs = [lcs[0], LoadCase(LoadNodes=[LoadNode(1, [-70000, 0, 42.0])])]
+    err = api.LinearStatic(None, m, *lcs)
+    assert err is not None and "not valid directions" in str(err)
+    assert lcs[0].PointDisplacementGlobal is not None and lcs[1].PointDisplacementGlobal is None
+    # singular: no supports at all (model_test.go:101-129)
+    from test_oracle_properties import fail_models
+    for i in (1, 2, 3, 5):
+        mm, ll, mc = fail_models()[i]
+        assert api.Run(None, mm, ll, []) is not None, i
+    # per-model statuses inside one batch: one bad model does not poison the others
+    fm, t = topo_of(oracle, frames.uniform_frame(4))
+    secs = frames.uniform_frame_sections(4, 0, 6)
+    secs[1, 2, 0] = np.nan
+    secs[3, 0, 1] = -1.0
+    secs[4, 5, 2] = np.inf
+    loads = frames.uniform_frame_loads(4, 0, 6)
+    loads[5, 7, 4] = np.inf
+    with np.errstate(all="ignore"):
+        status, fail, disp, forces, react = t.static_batch(secs, loads)
+    assert list(status) == [0, 1, 0, 1, 1, 1]
+    ost, od, of, orr = oracle.static_batch(fm, secs[[0, 2]], loads[[0, 2]])
+    compare_rule(od, disp[[0, 2]])
+    t.close()
+
+
+def test_pattern_mismatch_is_flagged(oracle):
+    """A skewed member whose (X,Y) coupling cancels exactly for the representative sections: that entry is
+    dropped from the pattern (model.go:645-649); a batch member with other sections must be flagged."""
+    found = None
+    xy = [0.0, 0.0, 3.0, 4.0]
+    for J in np.arange(1.0, 400.0):
+        A = 12.0 * J / 25.0
+        kg = oracle.rotate_to_global(oracle.stiff_beam2d(xy, A, J, 1.0, [0] * 6), oracle.trans_beam2d(xy))
+        if kg[0, 1] == 0.0 and kg[3, 4] == 0.0:
+            found = (A, J)
+            break
+    if found is None:
+        pytest.skip("no exactly cancelling section found")
+    A, J = found
+    pts = np.array([[0.0, 0.0], [3.0, 4.0]])
+    t = _lib.Topology(pts, [[0, 1]], [[A, J, 1.0]], None, [[1, 1, 1], [0, 0, 0]])
+    secs = np.array([[[A, J, 1.0]], [[A * 1.5, J, 1.0]]])
+    status, fail, disp, forces, react = t.static_batch(secs, np.ones((2, 1, 6)))
+    assert status[0] == _lib.STATUS_OK and status[1] == _lib.STATUS_PATTERN
+    fm = oracle.FlatModel(pts, [[0, 1]], [[A, J, 1.0]], None, [[1, 1, 1], [0, 0, 0]])
+    rc, od, of, orr, _ = oracle.linear_static(fm, np.ones((1, 6)))
+    compare_rule(od, disp[0])
+    assert np.array_equal(t.query(_lib.Q_CSR_COLIND), oracle.assemble(fm)["csr"][1])
+    t.close()
+
+
+# ------------------------------------------------------------------ shapes and paths
+@pytest.mark.parametrize("nLC", [1, 7, 33, 70])
+def test_ragged_case_counts(oracle, nLC):
+    N, nM = 6, 3
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    secs = frames.uniform_frame_sections(N, 9, nM)
+    loads = frames.uniform_frame_loads(N, 9, nM, n_cases=nLC)
+    status, fail, disp, forces, react = t.static_batch(secs, loads)
+    assert not status.any()
+    ost, od, of, orr = oracle.static_batch(fm, secs, loads)
+    compare_rule(od, disp)
+    compare_rule(orr, react)
+    force_rule(of, forces)
+    # outputs may be skipped individually
+    s2, _, d2, f2, r2 = t.static_batch(secs, loads, want=("react",))
+    assert d2 is None and f2 is None and np.array_equal(r2, react)
+    t.close()
+
+
+def test_device_pointers_sub_batches_and_rcm(oracle):
+    import torch
+    N, nM = 16, 70
+    m = frames.uniform_frame(N)
+    secs = frames.uniform_frame_sections(N, 0, nM)
+    loads = frames.uniform_frame_loads(N, 0, nM)
+    fm, t = topo_of(oracle, m)
+    ref = t.static_batch(secs, loads)
+    t.close()
+    os.environ["HDB_SUB_BATCH"] = "32"  # 70 models -> sub-batches 32, 32, 6
+    try:
+        for ordering in (0, 1):
+            fm, t = topo_of(oracle, m, ordering=ordering)
+            dev = torch.device("cuda:0")
+            ds, dl = torch.from_numpy(secs).to(dev), torch.from_numpy(loads).to(dev)
+            dd = torch.empty((nM, 20, fm.nP, 3), dtype=torch.float64, device=dev)
+            df = torch.empty((nM, 20, fm.nB, 6), dtype=torch.float64, device=dev)
+            dr = torch.empty((nM, 20, fm.nP, 3), dtype=torch.float64, device=dev)
+            st = torch.full((nM,), -7, dtype=torch.int32, device=dev)
+            fc = torch.zeros((nM,), dtype=torch.int32, device=dev)
+            t.static_batch_dev(nM, ds, 20, dl, dd, df, dr, st, fc, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert not st.cpu().numpy().any()
+            if ordering == 0:
+                assert np.array_equal(dd.cpu().numpy(), ref[2]) and np.array_equal(df.cpu().numpy(), ref[3])
+                assert np.array_equal(dr.cpu().numpy(), ref[4])
+            else:
+                compare_rule(ref[2], dd.cpu().numpy())
+                compare_rule(ref[4], dr.cpu().numpy())
+                force_rule(ref[3], df.cpu().numpy())
+            t.close()
+    finally:
+        del os.environ["HDB_SUB_BATCH"]
+
+
+def test_batch_is_deterministic(oracle):
+    N, nM = 32, 40
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    secs = frames.uniform_frame_sections(N, 0, nM)
+    loads = frames.uniform_frame_loads(N, 0, nM)
+    a = t.static_batch(secs, loads)
+    b = t.static_batch(secs, loads)
+    for x, y in zip(a[2:], b[2:]):
+        assert np.array_equal(x, y)
+    t.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json sizes: properties
+def test_full_size_batch_properties(oracle):
+    """config 3 shape (uniform_frame(128) x 20 cases), 1024 models: sampled models against the oracle,
+    and for every model global equilibrium (sum of reactions + sum of loads = 0) and linearity in the load."""
+    N, nM = 128, 1024
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    secs = frames.uniform_frame_sections(N, 0, nM)
+    loads = frames.uniform_frame_loads(N, 0, nM)
+    status, fail, disp, forces, react = t.static_batch(secs, loads)
+    assert not status.any()
+    sample = [0, 1, 511, 777, 1023]
+    ost, od, of, orr = oracle.static_batch(fm, secs[sample], loads[sample])
+    compare_rule(od, disp[sample])
+    compare_rule(orr, react[sample])
+    force_rule(of, forces[sample])
+    L3 = loads.reshape(nM, 20, fm.nP, 3)
+    for c in range(2):  # sum Fx, sum Fy
+        tot = react[..., c].sum(axis=2) + L3[..., c].sum(axis=2)
+        assert np.abs(tot).max() <= 1e-9 * np.abs(L3[..., c]).sum(axis=2).max()
+    # moment equilibrium about the origin
+    x, y = fm.points[:, 0], fm.points[:, 1]
+    mom = ((react[..., 2] + L3[..., 2]) + x * (react[..., 1] + L3[..., 1]) - y * (react[..., 0] + L3[..., 0])).sum(axis=2)
+    assert np.abs(mom).max() <= 1e-9 * (np.abs(x * L3[..., 1]).sum(axis=2).max() + 1)
+    # beam end forces are self-equilibrated along the member axis and in shear
+    assert np.abs(forces[..., 0] + forces[..., 3]).max() <= 1e-9 * np.abs(forces[..., 0]).max()
+    assert np.abs(forces[..., 1] + forces[..., 4]).max() <= 1e-9 * np.abs(forces[..., 1]).max()
+    # linearity: d(2.5 p) = 2.5 d(p)
+    s2, _, d2, _, _ = t.static_batch(secs[:64], 2.5 * loads[:64], want=("disp",))
+    compare_rule(2.5 * disp[:64], d2, 1e-12)
+    t.close()
