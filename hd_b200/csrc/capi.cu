@@ -119,14 +119,14 @@ static int ensure_device(hdb_topology *t)
         return o;
     };
     std::vector<uint8_t> dropped((size_t)S.nB * 36, 0);
-    { // scatter is in triplet order (p1,p2,r1,r2); dropped[] is indexed by beam*36 + local row-major
+    { // posSlot is in triplet order (p1,p2,r1,r2); dropped[] is indexed by beam*36 + local row-major
         size_t q = 0;
         for (int b = 0; b < S.nB; b++)
             for (int p1 = 0; p1 < 2; p1++)
                 for (int p2 = 0; p2 < 2; p2++)
                     for (int r1 = 0; r1 < 3; r1++)
                         for (int r2 = 0; r2 < 3; r2++, q++)
-                            if (S.scatter[q] < 0) dropped[(size_t)b * 36 + (p1 * 3 + r1) * 6 + (p2 * 3 + r2)] = 1;
+                            if (S.posSlot[q] < 0) dropped[(size_t)b * 36 + (p1 * 3 + r1) * 6 + (p2 * 3 + r2)] = 1;
     }
     int rc;
 #define UP(vec, field)                                  \

@@ -21,6 +21,7 @@ struct Symbolic {
 
     // ---- pattern of K exactly as model.go:607-681 leaves it ----
     std::vector<int32_t> scatter;   // [nB*36] -> CSR slot or -1 (exact zero, dropped by model.go:645)
+    std::vector<int32_t> posSlot;   // [nB*36] -> CSR slot of the triplet's position or -1 (position absent)
     std::vector<int32_t> rowptr, colind; // canonical CSR (ascending columns)
     std::vector<int32_t> ignore;    // DOFs without diagonal entry (model.go:657-678)
     std::vector<int32_t> elim;      // sort-unique(ignore ++ supports) (model.go:326-328)

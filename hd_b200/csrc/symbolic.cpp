@@ -278,20 +278,26 @@ int build_symbolic(int32_t nP, const double *points, int32_t nB, const hdb_beam 
         auto it = std::lower_bound(b, e, c);
         return (it != e && *it == c) ? (int32_t)(it - S.colind.begin()) : -1;
     };
+    // scatter (API): per triplet, -1 where the representative value is exactly zero (dropped by the
+    // reference).  posSlot (kernels): the slot of the triplet's POSITION whenever that position exists in
+    // the pattern, even if this beam's own contribution is an exact zero in the representative model —
+    // another model of the batch may carry a round-off residue there (pin condensation, feBeam2d.go:58-137)
+    // which the reference would add; adding the representative's exact 0.0 changes no sum.
     S.scatter.assign((size_t)nB * 36, -1);
+    S.posSlot.assign((size_t)nB * 36, -1);
     S.kptr.assign(S.nnzK + 1, 0);
-    for (size_t q = 0; q < trips.size(); q++)
-        if (!trips[q].zero) {
-            int32_t slot = csr_slot(trips[q].row, trips[q].col);
-            S.scatter[q] = slot;
-            S.kptr[slot + 1]++;
-        }
+    for (size_t q = 0; q < trips.size(); q++) {
+        const int32_t slot = csr_slot(trips[q].row, trips[q].col);
+        S.posSlot[q] = slot;
+        if (!trips[q].zero) S.scatter[q] = slot;
+        if (slot >= 0) S.kptr[slot + 1]++;
+    }
     for (int s = 0; s < S.nnzK; s++) S.kptr[s + 1] += S.kptr[s];
     S.ksrc.resize(S.kptr[S.nnzK]);
     {
         std::vector<int32_t> w(S.kptr.begin(), S.kptr.end() - 1);
         for (size_t q = 0; q < trips.size(); q++) // beam order = summation order of cs_dupl
-            if (S.scatter[q] >= 0) S.ksrc[w[S.scatter[q]]++] = trips[q].code;
+            if (S.posSlot[q] >= 0) S.ksrc[w[S.posSlot[q]]++] = trips[q].code;
     }
 
     // ---- ignore, eliminated, free numbering ----
@@ -407,7 +413,7 @@ int build_symbolic(int32_t nP, const double *points, int32_t nB, const hdb_beam 
     std::vector<std::vector<int32_t>> slotSrc(S.nSlots);
     std::vector<std::map<int32_t, std::vector<int32_t>>> rrow(S.nSup); // column DOF -> codes
     for (size_t q = 0; q < trips.size(); q++) {
-        if (S.scatter[q] < 0) continue;
+        if (S.posSlot[q] < 0) continue;
         const Trip &t = trips[q];
         const int xi = S.xrow[t.row], xj = S.xrow[t.col];
         if (xi >= 0 && xj >= 0) {

@@ -52,15 +52,15 @@ enum {
     HDB_STATUS_OK = 0,
     HDB_STATUS_NONFINITE = 1,   /* NaN/Inf/non-positive section or NaN/Inf matrix entry or load:
                                    check.go:301-324, model.go:692-696                          */
-    HDB_STATUS_SINGULAR = 2,    /* zero / negative / non-finite pivot: "LU error factorization",
-                                   model.go:326-331                                            */
+    HDB_STATUS_SINGULAR = 2,    /* exactly zero or non-finite pivot: "LU error factorization",
+                                   model.go:326-331 (round-off sized pivots pass, as in the reference) */
     HDB_STATUS_IGNORE_LOAD = 3, /* non-zero load on an `ignore` DOF, model.go:424-437; the
                                    offending case index is written to fail_case[model]          */
     HDB_STATUS_EIGEN = 4,       /* eigen iteration did not converge, model.go:809-811           */
-    HDB_STATUS_PATTERN = 5      /* an element entry that is exactly 0.0 in the topology's
-                                   representative model is non-zero in this model: its sparsity
-                                   pattern (model.go:645-649) differs, solve it under its own
-                                   topology handle                                              */
+    HDB_STATUS_PATTERN = 5      /* this model has a non-zero element entry at a matrix position that
+                                   is absent from the pattern of the topology's representative
+                                   model (exact zeros dropped, model.go:645-649): its sparsity
+                                   pattern differs, solve it under its own topology handle     */
 };
 
 /* Go hd.BeamProp memory layout (model.go:58-77): N [2]int, A, J, E float64 = 40 bytes. */
