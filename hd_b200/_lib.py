@@ -239,7 +239,7 @@ class Topology:
 
     # ---- measurement ----
     def set_profiling(self, on=True):
-        check(lib().hdb_set_profiling(self._h, 1 if on else 0), "hdb_set_profiling")
+        check(lib().hdb_set_profiling(self._h, int(on)), "hdb_set_profiling")
 
     def last_kernel_ms(self):
         ms = np.zeros(8, dtype=np.float32)

@@ -69,7 +69,7 @@ struct hdb_topology {
     cudaStream_t sIn = nullptr, sK = nullptr, sOut = nullptr; // copy-in, compute, copy-out
     int chunkModels = 0, chunkLC = 0;
     // profiling
-    bool profiling = false;
+    int profiling = 0; // 0 off, 1 per call (reset at every call), 2 accumulate until hdb_set_profiling is called again
     std::vector<cudaEvent_t> events;
     std::vector<int> evKind; // kernel kind of interval [2i, 2i+1]
     int lastKinds = 0;
@@ -194,7 +194,7 @@ enum { KIND_ASSEMBLE = 0, KIND_FACTOR = 1, KIND_SOLVE = 2, KIND_MODAL0 = 3 };
 
 static void prof_reset(hdb_topology *t)
 {
-    t->evKind.clear();
+    if (t->profiling != 2) t->evKind.clear();
 }
 
 static cudaEvent_t prof_event(hdb_topology *t, size_t i)
@@ -212,7 +212,7 @@ struct ProfScope {
     cudaStream_t st;
     size_t slot;
     bool on;
-    ProfScope(hdb_topology *t_, int kind, cudaStream_t s) : t(t_), st(s), slot(0), on(t_->profiling)
+    ProfScope(hdb_topology *t_, int kind, cudaStream_t s) : t(t_), st(s), slot(0), on(t_->profiling != 0)
     {
         if (!on) return;
         slot = t->evKind.size();
@@ -451,7 +451,8 @@ int hdb_host_free(void *ptr)
 int hdb_set_profiling(hdb_topology *t, int32_t on)
 {
     if (!t) return HDB_ERR_ARG;
-    t->profiling = on != 0;
+    t->profiling = on;
+    t->evKind.clear();
     return HDB_OK;
 }
 

@@ -185,7 +185,8 @@ int hdb_host_free(void *ptr);
 
 /* ---- measurement: CUDA-event time of each kernel of the last *_dev / *_batch call ----
  * ms[0..n): static: {assemble, factor, solve_recover}; modal: {assemble, factor, reduce, eigen,
- * shapes}.  Blocks until the events have completed.  Returns the count written. */
+ * shapes}.  Blocks until the events have completed.  Returns the count written.
+ * hdb_set_profiling: 0 off, 1 time the last call only, 2 accumulate over calls until set again. */
 int hdb_set_profiling(hdb_topology *t, int32_t on);
 int hdb_last_kernel_ms(hdb_topology *t, float *ms, int32_t capacity);
 /* number of kernels this library has launched in the process (the bench's gpu_launches). */
