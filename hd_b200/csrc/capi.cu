@@ -62,6 +62,7 @@ struct hdb_topology {
     std::vector<void *> devAllocs;
     // workspace of the device path
     double *W = nullptr, *Ksf = nullptr, *keScratch = nullptr;
+    long long *dbgClocks = nullptr; // HDB_DEBUG_CLOCKS=1: per-model phase stamps of k_solve_recover
     size_t wsModels = 0;
     int subBatch = 4096;
     // host path
@@ -110,8 +111,9 @@ static int ensure_device(hdb_topology *t)
     CUDA_TRY(cudaDeviceGetAttribute(&t->smCount, cudaDevAttrMultiProcessorCount, t->device));
     const Symbolic &S = t->S;
     DevTopo &D = t->D;
-    D.nP = S.nP; D.nB = S.nB; D.dof = S.dof; D.nFree = S.nFree; D.nnzL = S.nnzL; D.nSlots = S.nSlots;
-    D.nSup = S.nSup; D.nnzR = S.nnzR; D.nnzK = S.nnzK; D.maxColCount = S.maxColCount;
+    D.nP = S.nP; D.nB = S.nB; D.dof = S.dof; D.nFree = S.nFree; D.nBlk = S.nBlk; D.nPad = S.nPad; D.nSlots = S.nSlots;
+    D.nSup = S.nSup; D.nnzR = S.nnzR; D.nnzK = S.nnzK; D.nDummy = (int)S.dummyPos.size(); D.maxBlkCount = S.maxBlkCount;
+    D.winNeed = S.winNeed; D.nFwdOps = (int)S.fwdOps.size() / 2; D.nBwdOps = (int)S.bwdOps.size() / 2;
     // gather codes -> padded shared-memory indices
     auto pad = [](const std::vector<int32_t> &src) {
         std::vector<int32_t> o(src.size());
@@ -137,22 +139,31 @@ static int ensure_device(hdb_topology *t)
     UP(dropped, dropped);
     UP(S.gptr, gptr);
     UP(pad(S.gsrc), gsrc);
+    UP(S.slotInit, slotInit);
     UP(S.rgptr, rgptr);
     UP(pad(S.rgsrc), rgsrc);
     UP(S.kptr, kptr);
     UP(pad(S.ksrc), ksrc);
-    UP(S.Lp, Lp);
-    UP(S.Li, Li);
-    UP(S.uptr, uptr);
-    UP(S.utgt, utgt);
-    UP(S.rLp, rLp);
-    UP(S.rLcol, rLcol);
-    UP(S.rLslot, rLslot);
+    UP(S.BLp, BLp);
+    UP(S.BLi, BLi);
+    UP(S.colOff, colOff);
+    UP(S.blkSlot, blkSlot);
+    UP(S.pairPtr, pairPtr);
+    UP(S.pairTgt, pairTgt);
+    UP(S.needUpto, needUpto);
+    {
+        const int32_t *f = nullptr, *b = nullptr;
+        if ((rc = upload(t, S.fwdOps, &f)) != HDB_OK) return rc;
+        if ((rc = upload(t, S.bwdOps, &b)) != HDB_OK) return rc;
+        D.fwdOps = reinterpret_cast<const int2 *>(f);
+        D.bwdOps = reinterpret_cast<const int2 *>(b);
+    }
     UP(S.xrow, xrow);
     UP(S.beamRows, beamRows);
     UP(S.supIndex, supIndex);
     UP(S.rptr, rptr);
     UP(S.rcol, rcol);
+    UP(S.dummyPos, dummyPos);
 #undef UP
     if (const char *e = std::getenv("HDB_SUB_BATCH")) {
         int v = std::atoi(e);
@@ -171,6 +182,11 @@ static int ensure_workspace(hdb_topology *t, size_t models)
     t->W = t->Ksf = t->keScratch = nullptr;
     t->wsModels = 0;
     const size_t ld = (models + 31) / 32 * 32;
+    if (std::getenv("HDB_DEBUG_CLOCKS")) {
+        if (t->dbgClocks) cudaFree(t->dbgClocks);
+        CUDA_TRY(cudaMalloc(&t->dbgClocks, ld * 8 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(t->dbgClocks, 0, ld * 8 * sizeof(long long)));
+    }
     CUDA_TRY(cudaMalloc(&t->W, (size_t)t->S.nSlots * ld * sizeof(double)));
     CUDA_TRY(cudaMalloc(&t->Ksf, std::max<size_t>(1, models * (size_t)t->S.nnzR) * sizeof(double)));
     if (!assemble_fits_smem(t->D, t->smemOptin))
@@ -506,6 +522,7 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
         L.Ksf = t->Ksf;
         L.kval = kval ? kval + (size_t)m0 * S.nnzK : nullptr;
         L.keScratch = t->keScratch;
+        L.dbgClocks = t->dbgClocks;
         {
             ProfScope ps(t, KIND_ASSEMBLE, st);
             CUDA_TRY(launch_assemble(t->D, L, st));
@@ -525,6 +542,20 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
     return HDB_OK;
 }
 
+static void debug_report_clocks(hdb_topology *t, int nModels)
+{
+    if (!t->dbgClocks) return;
+    cudaDeviceSynchronize();
+    const int n = std::min<int>(nModels, (int)t->wsModels);
+    std::vector<long long> h((size_t)n * 8);
+    cudaMemcpy(h.data(), t->dbgClocks, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int m = 0; m < n; m++)
+        for (int i = 0; i < 5; i++) acc[i] += (double)(h[(size_t)m * 8 + i + 1] - h[(size_t)m * 8 + i]);
+    std::fprintf(stderr, "[hdb] k_solve_recover cycles/model: load %.0f fwd %.0f bwd %.0f barrier %.0f recover %.0f\n",
+                 acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n);
+}
+
 int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
                          double *disp, double *forces, double *react, int32_t *status, int32_t *failCase, void *stream)
 {
@@ -533,8 +564,10 @@ int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *section
     if (rc != HDB_OK) return rc;
     if (nModels == 0) return HDB_OK;
     prof_reset(t);
-    return static_enqueue(t, nModels, sections, nLC, loads, disp, forces, react, status, failCase, nullptr,
-                          (cudaStream_t)stream, true);
+    rc = static_enqueue(t, nModels, sections, nLC, loads, disp, forces, react, status, failCase, nullptr,
+                        (cudaStream_t)stream, true);
+    if (rc == HDB_OK) debug_report_clocks(t, nModels);
+    return rc;
 }
 
 static int ensure_chunks(hdb_topology *t, int chunkModels, int nLC)
@@ -546,9 +579,10 @@ static int ensure_chunks(hdb_topology *t, int chunkModels, int nLC)
         c.base = nullptr;
     }
     const size_t m = (size_t)chunkModels;
-    const size_t nSec = m * S.nB * 3, nLoad = m * nLC * S.dof, nForce = m * nLC * S.nB * 6;
+    auto al = [](size_t doubles) { return (doubles + 31) / 32 * 32; }; // keep every sub-buffer 256-byte aligned
+    const size_t nSec = al(m * S.nB * 3), nLoad = al(m * nLC * S.dof), nForce = al(m * nLC * S.nB * 6);
     const size_t doubles = nSec + 3 * nLoad + nForce;
-    const size_t bytes = doubles * sizeof(double) + 2 * m * sizeof(int32_t) + 256;
+    const size_t bytes = doubles * sizeof(double) + 2 * al(m) * sizeof(int32_t) + 256;
     for (auto &c : t->chunk) {
         CUDA_TRY(cudaMalloc(&c.base, bytes));
         double *p = (double *)c.base;
@@ -558,7 +592,7 @@ static int ensure_chunks(hdb_topology *t, int chunkModels, int nLC)
         c.react = p; p += nLoad;
         c.forces = p; p += nForce;
         c.status = (int32_t *)p;
-        c.fail = c.status + m;
+        c.fail = c.status + al(m);
         c.bytes = bytes;
         if (!c.evIn) {
             CUDA_TRY(cudaEventCreateWithFlags(&c.evIn, cudaEventDisableTiming));

@@ -7,25 +7,36 @@
 
 namespace hdb {
 
+// substitution op list (one warp walks it, one lane per load case); see build_solve_ops()
+enum : int { OP_PULL = 0, OP_DIAG = 1, OP_FUSED = 2 };
+constexpr int OPF_FIRST = 1 << 27; // first op of a block: reset the accumulator
+constexpr int OPF_PREV = 1 << 26;  // source block is the block finished just before (values are in registers)
+constexpr int OP_KIND_SHIFT = 28;
+constexpr int OP_BLK_MASK = (1 << 26) - 1;
+
 struct DevTopo {
-    int nP, nB, dof, nFree, nnzL, nSlots, nSup, nnzR, nnzK, maxColCount;
+    int nP, nB, dof, nFree, nBlk, nPad, nSlots, nSup, nnzR, nnzK, nDummy, maxBlkCount, winNeed;
+    int nFwdOps, nBwdOps;
     // geometry / topology (shared by every model of a batch)
     const double *points;      // [nP][2]
     const int32_t *beamN;      // [nB][2]
     const uint32_t *pinMask;   // [nB]
-    const uint8_t *dropped;    // [nB*36] 1 = entry is exactly zero in the representative model
+    const uint8_t *dropped;    // [nB*36] 1 = matrix position absent from the representative pattern
     // assembly gather lists (codes are padded smem indices beam*KE_LD + local)
     const int32_t *gptr, *gsrc;   // factor slots
+    const uint8_t *slotInit;      // [nSlots]
     const int32_t *rgptr, *rgsrc; // reaction entries
     const int32_t *kptr, *ksrc;   // full CSR pattern (tests)
-    // factorization schedule
-    const int32_t *Lp, *Li, *uptr, *utgt;
-    // solve / recovery
-    const int32_t *rLp, *rLcol, *rLslot;
+    // block factorization schedule
+    const int32_t *BLp, *BLi, *colOff, *blkSlot, *pairPtr, *pairTgt, *needUpto;
+    // substitution op lists: int2 {slot, blk | flags | kind << 28}
+    const int2 *fwdOps, *bwdOps;
+    // recovery
     const int32_t *xrow;       // [dof]
     const int32_t *beamRows;   // [nB*6]
     const int32_t *supIndex;   // [dof]
     const int32_t *rptr, *rcol;
+    const int32_t *dummyPos;   // [nDummy]
 };
 
 constexpr int KE_LD = 37; // padded leading dimension of one element matrix in shared memory
@@ -40,6 +51,7 @@ struct StaticLaunch {
     double *Ksf;               // [nModels][nnzR]
     double *kval;              // [nModels][nnzK] or NULL
     double *keScratch;         // [nModels][nB*KE_LD] or NULL (NULL = element matrices live in shared memory)
+    long long *dbgClocks;      // [nModels][8] phase time stamps of k_solve_recover (HDB_DEBUG_CLOCKS=1) or NULL
 };
 
 // each returns cudaGetLastError() of its launch

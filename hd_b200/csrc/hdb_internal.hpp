@@ -8,6 +8,10 @@
 
 namespace hdb {
 
+constexpr int BLK_HDR = 6;        // 1/d (3) + strictly lower part of the diagonal block (3)
+constexpr int BLK_STRIDE = 10;    // 9 values of an off block + 1 pad (keeps every block 16-byte aligned)
+constexpr int FACTOR_PREFETCH = 2; // block columns the factor kernel prefetches ahead
+
 // Result of the host symbolic phase.  All index arrays are int32 and identical for every model
 // of a batch (same topology, geometry, pins, supports).
 struct Symbolic {
@@ -29,12 +33,27 @@ struct Symbolic {
     std::vector<int32_t> freeDofs;  // [nFree] reduced index -> DOF
     int nFree = 0, nSup = 0, nnzK = 0, nnzKff = 0;
 
-    // ---- elimination order and factor pattern ----
+    // ---- elimination order and (informational) scalar factor pattern ----
     std::vector<int32_t> perm;      // [nFree] position -> reduced index
     std::vector<int32_t> iperm;     // [nFree] reduced index -> position
-    std::vector<int32_t> Lp, Li;    // strictly lower CSC pattern of L in position numbering
+    std::vector<int32_t> Lp, Li;    // strictly lower CSC pattern of the scalar L (minimal fill), exported
     int nnzL = 0;
-    int nSlots = 0;                 // nnzL + nFree (L entries, then the diagonal)
+    int maxColCount = 0;
+
+    // ---- node-block structure used by the kernels ----
+    // every point with a free DOF is a 3x3 block; non-free components are dummy unknowns (unit diagonal)
+    int nBlk = 0, nPad = 0;
+    std::vector<int32_t> blkOfPoint; // [nP] block (in elimination order) or -1
+    std::vector<int32_t> pointOfBlk; // [nBlk]
+    std::vector<int32_t> BLp, BLi;   // strictly lower block pattern of L incl. fill, CSC over blocks
+    int maxBlkCount = 0;
+    // value slots: block column J occupies [colOff[J], colOff[J+1]):
+    //   [1/d0 1/d1 1/d2 | l10 l20 l21 | per off block (ascending row block): 9 values row-major + 1 pad]
+    std::vector<int32_t> colOff;     // [nBlk+1]
+    std::vector<int32_t> blkSlot;    // [nOff] first slot of off block q
+    int nSlots = 0;
+    std::vector<uint8_t> slotInit;   // [nSlots] 1 = the slot starts at 1.0 (diagonal of a dummy unknown)
+    std::vector<int32_t> dummyPos;   // padded positions that are not free DOFs
 
     // ---- numeric schedules ----
     // gather lists: factor slot s sums element entries gsrc[gptr[s]..gptr[s+1]) (code = beam*36+local),
@@ -46,21 +65,23 @@ struct Symbolic {
     std::vector<int32_t> supDofs;   // [nSup]
     std::vector<int32_t> supIndex;  // [dof] index into supDofs or -1
     std::vector<int32_t> rptr;      // [nSup+1]
-    std::vector<int32_t> rcol;      // [nnzR] position (permuted reduced index) of the column
+    std::vector<int32_t> rcol;      // [nnzR] padded position of the column
     std::vector<int32_t> rgptr, rgsrc; // gather lists of the K[r][j] values
     int nnzR = 0;
-    // factorization: column j updates targets utgt[uptr[j]..uptr[j+1]) enumerated a outer, b<=a inner
-    std::vector<int32_t> uptr, utgt;
-    // row access of L for the forward solve: row i has entries (column rLcol, value slot rLslot)
-    std::vector<int32_t> rLp, rLcol, rLslot;
-    // DOF -> x row (position) for free DOFs, -1 supported/eliminated, -2 ignore (load must be zero)
+    // block factorization: for column J the Schur target of every pair (a >= b) of its off blocks,
+    // a outer, b inner: first slot of block (I_a, I_b), or the header of diagonal block I_a when a == b
+    std::vector<int32_t> pairPtr, pairTgt;
+    std::vector<int32_t> needUpto;  // [nBlk] slots [0, needUpto[J]) must be resident to eliminate column J
+    int winNeed = 0;                // shared-memory window (slots) the factor kernel needs incl. prefetch
+    // forward substitution: row block I pulls from (J, slot) ascending J
+    std::vector<int32_t> fwdPtr, fwdJ, fwdSlot;
+    // substitution op lists walked by the solve kernel: pairs {slot, blk | flags | kind << 28}
+    std::vector<int32_t> fwdOps, bwdOps;
+    // DOF -> x row (padded position) for free DOFs, -1 supported/eliminated, -2 ignore (load must be zero)
     std::vector<int32_t> xrow;      // [dof]
-    // per beam: x rows of its 6 global DOFs
-    std::vector<int32_t> beamRows;  // [nB*6]
-    // per beam: pin mask
+    std::vector<int32_t> beamRows;  // [nB*6] x rows of a beam's 6 global DOFs or -1
     std::vector<uint32_t> pinMask;  // [nB]
     std::vector<int32_t> beamN32;   // [nB*2]
-    int maxColCount = 0;            // largest |struct(L_j)|
     int64_t nUpdates = 0;
 };
 

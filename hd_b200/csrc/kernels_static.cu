@@ -19,6 +19,7 @@
 
 #include "device_topo.hpp"
 #include "element.cuh"
+#include "hdb_internal.hpp"
 
 namespace hdb {
 
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble(const DevTopo T, const
 
     // phase B: gather; one thread per slot, contributions in beam order
     for (int s = tid; s < T.nSlots; s += ASM_THREADS) {
-        double sum = 0.0;
+        double sum = T.slotInit[s] ? 1.0 : 0.0; // unit diagonal of a dummy unknown
         const int q1 = T.gptr[s + 1];
         for (int q = T.gptr[s]; q < q1; q++) sum = __dadd_rn(sum, ke[T.gsrc[q]]);
         L.W[(size_t)s * L.ld + model] = sum;
@@ -157,93 +158,158 @@ cudaError_t launch_elements(const DevTopo &T, int nModels, const double *section
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_factor: thread per model, interleaved workspace W[slot][ld]
+// k_factor: block LDL^T, one THREAD per model (a warp = 32 models), 3x3 node blocks.
+//
+// The factor workspace W[slot][ld] is interleaved over models, so lane = model makes every global
+// access a coalesced 256-byte row.  The slots a block column touches form a contiguous range that
+// slides forward with the elimination (the symbolic phase bounds it: T.winNeed), so the working set
+// lives in a circular shared-memory window win[WS][32]: slots stream in with cp.async two block
+// columns ahead, every dependent read-modify-write of the pivot chain is a shared-memory access,
+// and each finished block column streams out once.  WS == 0: the window does not fit, work in
+// global memory directly.
 // ------------------------------------------------------------------------------------------------
-constexpr int FAC_THREADS = 64;
-
-template <int CNT>
-__device__ __forceinline__ void factor_column(double *__restrict__ w, const size_t ld, const int p0,
-                                              const int32_t *__restrict__ tg, const double inv)
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem)
 {
-    constexpr int NU = CNT * (CNT + 1) / 2;
-    double u[CNT], tv[NU];
-    int ti[NU];
-#pragma unroll
-    for (int a = 0; a < CNT; a++) u[a] = w[(size_t)(p0 + a) * ld];
-#pragma unroll
-    for (int q = 0; q < NU; q++) ti[q] = __ldg(tg + q);
-#pragma unroll
-    for (int q = 0; q < NU; q++) tv[q] = w[(size_t)ti[q] * ld];
-    int q = 0;
-#pragma unroll
-    for (int a = 0; a < CNT; a++) {
-        const double la = u[a] * inv;
-#pragma unroll
-        for (int b = 0; b <= a; b++, q++) tv[q] = fma(-la, u[b], tv[q]);
-        w[(size_t)(p0 + a) * ld] = la;
-    }
-#pragma unroll
-    for (int q2 = 0; q2 < NU; q2++) w[(size_t)ti[q2] * ld] = tv[q2];
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __noinline__ void factor_column_any(double *__restrict__ w, const size_t ld, const int p0, const int cnt,
-                                               const int32_t *__restrict__ tg, const double inv)
+template <int WS>
+__global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaunch L)
 {
-    // generic column: entries stay unscaled until every update of this column is done
-    int q = 0;
-    for (int a = 0; a < cnt; a++) {
-        const double la = w[(size_t)(p0 + a) * ld] * inv;
-        for (int b = 0; b <= a; b++, q++) {
-            const size_t t = (size_t)__ldg(tg + q) * ld;
-            w[t] = fma(-la, w[(size_t)(p0 + b) * ld], w[t]);
+    extern __shared__ __align__(16) double smem_d[];
+    const int lane = threadIdx.x;
+    const int model = blockIdx.x * 32 + lane; // ld is a multiple of 32: padding lanes work on scratch columns
+    double *wg = L.W + model;
+    const size_t ld = (size_t)L.ld;
+    double *win = smem_d + lane;
+#define WIN(s) (*(WS ? (win + (((s) & (WS ? WS - 1 : 0)) << 5)) : (wg + (size_t)(s) * ld)))
+    const int nBlk = T.nBlk;
+    int loaded = 0;
+    if (WS) {
+        for (int pf = 0; pf < FACTOR_PREFETCH; pf++) {
+            const int upto = __ldg(T.needUpto + min(pf, nBlk - 1));
+            for (; loaded < upto; loaded++) cp_async8(&WIN(loaded), wg + (size_t)loaded * ld);
+            cp_async_commit();
         }
     }
-    for (int a = 0; a < cnt; a++) w[(size_t)(p0 + a) * ld] *= inv;
-}
-
-__global__ void __launch_bounds__(FAC_THREADS) k_factor(const DevTopo T, const StaticLaunch L)
-{
-    const int model = blockIdx.x * FAC_THREADS + threadIdx.x;
-    if (model >= L.nModels) return;
-    double *w = L.W + model;
-    const size_t ld = (size_t)L.ld;
     bool bad = false;
-    const int n = T.nFree, nnzL = T.nnzL;
-    for (int j = 0; j < n; j++) {
-        const size_t dj = (size_t)(nnzL + j) * ld;
-        const double d = w[dj];
+    for (int J = 0; J < nBlk; J++) {
+        if (WS) {
+            const int upto = __ldg(T.needUpto + min(J + FACTOR_PREFETCH, nBlk - 1));
+            for (; loaded < upto; loaded++) cp_async8(&WIN(loaded), wg + (size_t)loaded * ld);
+            cp_async_commit();
+            cp_async_wait<FACTOR_PREFETCH>();
+        }
+        const int base = __ldg(T.colOff + J);
+        // ---- scalar LDL^T of the 3x3 diagonal block ----
+        double d0 = WIN(base + 0), d1 = WIN(base + 1), d2 = WIN(base + 2);
+        const double a10 = WIN(base + 3), a20 = WIN(base + 4), a21 = WIN(base + 5);
         // the reference's LU gives up only when a column has no non-zero pivot candidate (cs_lu: a <= 0):
         // tiny or negative round-off pivots of pin mechanisms pass there and must pass here (TestSplit)
-        if (d == 0.0 || !isfinite(d)) bad = true;
-        const double inv = __drcp_rn(d);
-        const int p0 = __ldg(T.Lp + j);
-        const int cnt = __ldg(T.Lp + j + 1) - p0;
-        const int32_t *tg = T.utgt + __ldg(T.uptr + j);
-        switch (cnt) {
-        case 0: break;
-        case 1: factor_column<1>(w, ld, p0, tg, inv); break;
-        case 2: factor_column<2>(w, ld, p0, tg, inv); break;
-        case 3: factor_column<3>(w, ld, p0, tg, inv); break;
-        case 4: factor_column<4>(w, ld, p0, tg, inv); break;
-        case 5: factor_column<5>(w, ld, p0, tg, inv); break;
-        case 6: factor_column<6>(w, ld, p0, tg, inv); break;
-        default: factor_column_any(w, ld, p0, cnt, tg, inv); break;
+        if (d0 == 0.0 || !isfinite(d0)) bad = true;
+        const double inv0 = __drcp_rn(d0);
+        const double l10 = a10 * inv0, l20 = a20 * inv0;
+        d1 = fma(-l10, a10, d1);
+        const double u21 = fma(-l20, a10, a21);
+        if (d1 == 0.0 || !isfinite(d1)) bad = true;
+        const double inv1 = __drcp_rn(d1);
+        const double l21 = u21 * inv1;
+        d2 = fma(-l21, u21, fma(-l20, a20, d2));
+        if (d2 == 0.0 || !isfinite(d2)) bad = true;
+        const double inv2 = __drcp_rn(d2);
+        WIN(base + 0) = inv0; WIN(base + 1) = inv1; WIN(base + 2) = inv2;
+        WIN(base + 3) = l10;  WIN(base + 4) = l20;  WIN(base + 5) = l21;
+        const int q0 = __ldg(T.BLp + J), nb = __ldg(T.BLp + J + 1) - q0;
+        // ---- off blocks: rows of L = A (L_JJ D_J)^-T ; stored scaled, u = l * d recovered when needed ----
+        for (int a = 0; a < nb; a++) {
+            const int sa = base + BLK_HDR + BLK_STRIDE * a;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const double u0 = WIN(sa + 3 * r);
+                const double u1 = fma(-l10, u0, WIN(sa + 3 * r + 1));
+                const double u2 = fma(-l21, u1, fma(-l20, u0, WIN(sa + 3 * r + 2)));
+                WIN(sa + 3 * r) = u0 * inv0;
+                WIN(sa + 3 * r + 1) = u1 * inv1;
+                WIN(sa + 3 * r + 2) = u2 * inv2;
+            }
         }
-        w[dj] = inv;
+        // ---- Schur updates of every pair of off blocks ----
+        const int32_t *tg = T.pairTgt + __ldg(T.pairPtr + J);
+        for (int a = 0; a < nb; a++) {
+            const int sa = base + BLK_HDR + BLK_STRIDE * a;
+            double la[9];
+#pragma unroll
+            for (int e = 0; e < 9; e++) la[e] = WIN(sa + e);
+            for (int b = 0; b <= a; b++) {
+                const int sb = base + BLK_HDR + BLK_STRIDE * b;
+                double ub[9];
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    ub[3 * r] = WIN(sb + 3 * r) * d0;
+                    ub[3 * r + 1] = WIN(sb + 3 * r + 1) * d1;
+                    ub[3 * r + 2] = WIN(sb + 3 * r + 2) * d2;
+                }
+                const int t = __ldg(tg++);
+                if (a == b) { // diagonal block of row block I_a: header [d0 d1 d2 | (1,0) (2,0) (2,1)]
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+                        WIN(t + r) = fma(-la[3 * r + 2], ub[3 * r + 2], fma(-la[3 * r + 1], ub[3 * r + 1], fma(-la[3 * r], ub[3 * r], WIN(t + r))));
+                    WIN(t + 3) = fma(-la[5], ub[2], fma(-la[4], ub[1], fma(-la[3], ub[0], WIN(t + 3))));
+                    WIN(t + 4) = fma(-la[8], ub[2], fma(-la[7], ub[1], fma(-la[6], ub[0], WIN(t + 4))));
+                    WIN(t + 5) = fma(-la[8], ub[5], fma(-la[7], ub[4], fma(-la[6], ub[3], WIN(t + 5))));
+                } else { // block (I_a, I_b): rows from a, columns from b
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+#pragma unroll
+                        for (int rp = 0; rp < 3; rp++)
+                            WIN(t + 3 * r + rp) = fma(-la[3 * r + 2], ub[3 * rp + 2],
+                                                      fma(-la[3 * r + 1], ub[3 * rp + 1], fma(-la[3 * r], ub[3 * rp], WIN(t + 3 * r + rp))));
+                }
+            }
+        }
+        // ---- block column J is final: stream it out ----
+        if (WS) {
+            const int end = __ldg(T.colOff + J + 1);
+            for (int s2 = base; s2 < end; s2++) wg[(size_t)s2 * ld] = WIN(s2);
+        }
     }
-    if (bad && L.status[model] == HDB_STATUS_OK) L.status[model] = HDB_STATUS_SINGULAR;
+#undef WIN
+    if (bad && model < L.nModels && L.status[model] == HDB_STATUS_OK) L.status[model] = HDB_STATUS_SINGULAR;
 }
 
 cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t st)
 {
-    k_factor<<<(L.nModels + FAC_THREADS - 1) / FAC_THREADS, FAC_THREADS, 0, st>>>(T, L);
+    const int grid = (L.nModels + 31) / 32;
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+#define LAUNCH_WIN(WS)                                                                                             \
+    do {                                                                                                           \
+        const size_t smem = (size_t)(WS) * 32 * sizeof(double);                                                    \
+        if (smem > 48 * 1024) {                                                                                    \
+            cudaError_t e = cudaFuncSetAttribute(k_factor<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                        \
+        }                                                                                                          \
+        k_factor<WS><<<grid, 32, smem, st>>>(T, L);                                                                \
+    } while (0)
+    if (T.winNeed <= 64) LAUNCH_WIN(64);
+    else if (T.winNeed <= 128) LAUNCH_WIN(128);
+    else if (T.winNeed <= 256) LAUNCH_WIN(256);
+    else if (T.winNeed <= 512 && (size_t)512 * 32 * 8 + 1024 <= (size_t)optin) LAUNCH_WIN(512);
+    else LAUNCH_WIN(0);
+#undef LAUNCH_WIN
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_solve_recover
 // ------------------------------------------------------------------------------------------------
-constexpr int SOL_THREADS = 256;
+constexpr int SOL_MAX_THREADS = 256;
+constexpr int LV_PAD = 16; // the substitution reads 16 doubles around any slot: pad both ends of the factor
 
 struct SolveCfg {
     int casesPerPass; // <= 32
@@ -252,143 +318,347 @@ struct SolveCfg {
 
 __host__ __device__ inline int odd_stride(int c) { return c | 1; }
 
+static size_t solve_smem_bytes(const DevTopo &T, int cp)
+{
+    return ((size_t)(T.nSlots + 2 * LV_PAD) + (size_t)T.nPad * odd_stride(cp)) * sizeof(double);
+}
+
 bool solve_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes)
 {
     int cp = nLC < 32 ? nLC : 32;
+    if (cp < 1) cp = 1;
     for (; cp >= 1; cp--) {
-        const size_t bytes = ((size_t)T.nFree * odd_stride(cp) + 2 * (size_t)T.nnzL + T.nFree + T.nnzR) * sizeof(double);
+        const size_t bytes = solve_smem_bytes(T, cp);
         if (bytes + 2048 <= (size_t)smemOptin) {
             casesPerPass = cp;
             smemBytes = bytes;
             return true;
         }
-        if (cp > 16) cp = 17; // try 16 next, then count down
     }
     return false;
 }
 
-__global__ void __launch_bounds__(SOL_THREADS) k_solve_recover(const DevTopo T, const StaticLaunch L, const SolveCfg cfg)
+// Block substitution, one lane per load case.  The warp walks an op list (device_topo.hpp): OP_PULL
+// accumulates s += L_IJ z_J for one off block, OP_DIAG finishes a block with its diagonal part, OP_FUSED
+// does both for the common banded case (single pull from the block finished just before, whose values
+// are still in registers).  The 16 doubles around rec.x are laid out per pass so that every register
+// index is static:
+//   forward : [off block 9 + pad | 1/d0 1/d1 1/d2 l10 l20 l21]   (OP_DIAG points 10 before its header)
+//   backward: [1/d0 1/d1 1/d2 l10 l20 l21 | off block 9 + pad]   (OP_PULL points 6 before its block)
+// Software pipeline: the loads of op k+1 are issued in the middle of op k, right after its off-block
+// values have been consumed, so their shared-memory latency hides behind the diagonal solve chain.
+template <bool FWD>
+struct OpVals {
+    double L00, L01, L02, L10, L11, L12, L20, L21, L22;
+    double i0, i1, i2; // 1/d (backward only)
+    double l10, l20, l21;
+    double p0, p1, p2; // x rows of rec's block: right-hand side of its own block, or a pulled source
+};
+
+template <bool FWD>
+__device__ __forceinline__ void op_load(const int2 rec, const double *Lv, const double *xs, const int CS, const int c,
+                                        OpVals<FWD> &o)
 {
-    extern __shared__ double smem_d[];
+    const double *base = Lv + rec.x;
+    const double2 *src = reinterpret_cast<const double2 *>(base);
+    double2 t;
+    if (FWD) {
+        t = src[0]; o.L00 = t.x; o.L01 = t.y;
+        t = src[1]; o.L02 = t.x; o.L10 = t.y;
+        t = src[2]; o.L11 = t.x; o.L12 = t.y;
+        t = src[3]; o.L20 = t.x; o.L21 = t.y;
+        o.L22 = base[8];
+        o.l10 = base[13];
+        t = src[7]; o.l20 = t.x; o.l21 = t.y;
+        o.i0 = o.i1 = o.i2 = 0.0;
+    } else {
+        t = src[0]; o.i0 = t.x; o.i1 = t.y;
+        t = src[1]; o.i2 = t.x; o.l10 = t.y;
+        t = src[2]; o.l20 = t.x; o.l21 = t.y;
+        t = src[3]; o.L00 = t.x; o.L01 = t.y;
+        t = src[4]; o.L02 = t.x; o.L10 = t.y;
+        t = src[5]; o.L11 = t.x; o.L12 = t.y;
+        t = src[6]; o.L20 = t.x; o.L21 = t.y;
+        o.L22 = base[14];
+    }
+    const double *x = xs + (size_t)(3 * (rec.y & OP_BLK_MASK)) * CS + c;
+    o.p0 = x[0];
+    o.p1 = x[CS];
+    o.p2 = x[2 * CS];
+}
+
+template <bool FWD>
+__device__ __noinline__ void substitute(const int2 *__restrict__ ops, const int nOps, const double *Lv, double *xs,
+                                        const int CS, const int c)
+{
+    if (nOps <= 0) return;
+    double h0 = 0, h1 = 0, h2 = 0; // the block finished last
+    double s0 = 0, s1 = 0, s2 = 0; // pulled sum of the block in progress
+    int2 rec = __ldg(ops), recN = __ldg(ops + min(1, nOps - 1));
+    OpVals<FWD> v;
+    op_load<FWD>(rec, Lv, xs, CS, c, v);
+    for (int k = 0; k < nOps; k++) {
+        const int2 recNN = __ldg(ops + min(k + 2, nOps - 1));
+        const int kind = (unsigned)rec.y >> OP_KIND_SHIFT;
+        // ---- stage 1: off block ----
+        double t0, t1, t2; // right-hand side of the diagonal stage
+        if (kind == OP_FUSED) { // source = block finished just before (registers), fresh accumulator
+            if (FWD) {
+                t0 = fma(-v.L02, h2, fma(-v.L01, h1, fma(-v.L00, h0, v.p0)));
+                t1 = fma(-v.L12, h2, fma(-v.L11, h1, fma(-v.L10, h0, v.p1)));
+                t2 = fma(-v.L22, h2, fma(-v.L21, h1, fma(-v.L20, h0, v.p2)));
+            } else {
+                t0 = fma(-v.L20, h2, fma(-v.L10, h1, fma(-v.L00, h0, v.p0 * v.i0)));
+                t1 = fma(-v.L21, h2, fma(-v.L11, h1, fma(-v.L01, h0, v.p1 * v.i1)));
+                t2 = fma(-v.L22, h2, fma(-v.L12, h1, fma(-v.L02, h0, v.p2 * v.i2)));
+            }
+        } else if (kind == OP_PULL) {
+            if (rec.y & OPF_FIRST) s0 = s1 = s2 = 0.0;
+            double z0 = h0, z1 = h1, z2 = h2;
+            if (!(rec.y & OPF_PREV)) { z0 = v.p0; z1 = v.p1; z2 = v.p2; }
+            if (FWD) {
+                s0 = fma(v.L02, z2, fma(v.L01, z1, fma(v.L00, z0, s0)));
+                s1 = fma(v.L12, z2, fma(v.L11, z1, fma(v.L10, z0, s1)));
+                s2 = fma(v.L22, z2, fma(v.L21, z1, fma(v.L20, z0, s2)));
+            } else {
+                s0 = fma(v.L20, z2, fma(v.L10, z1, fma(v.L00, z0, s0)));
+                s1 = fma(v.L21, z2, fma(v.L11, z1, fma(v.L01, z0, s1)));
+                s2 = fma(v.L22, z2, fma(v.L12, z1, fma(v.L02, z0, s2)));
+            }
+            t0 = t1 = t2 = 0.0;
+        } else { // OP_DIAG
+            if (rec.y & OPF_FIRST) s0 = s1 = s2 = 0.0;
+            if (FWD) { t0 = v.p0 - s0; t1 = v.p1 - s1; t2 = v.p2 - s2; }
+            else { t0 = fma(v.p0, v.i0, -s0); t1 = fma(v.p1, v.i1, -s1); t2 = fma(v.p2, v.i2, -s2); }
+        }
+        const double l10 = v.l10, l20 = v.l20, l21 = v.l21;
+        const int blk = rec.y & OP_BLK_MASK;
+        // ---- issue the loads of the next op: they complete behind the diagonal chain below ----
+        if (k + 1 < nOps) op_load<FWD>(recN, Lv, xs, CS, c, v);
+        // ---- stage 2: diagonal block ----
+        if (kind != OP_PULL) {
+            double r0, r1, r2;
+            if (FWD) { // unit lower solve; the D scaling is applied by the backward pass
+                r0 = t0;
+                r1 = fma(-l10, r0, t1);
+                r2 = fma(-l21, r1, fma(-l20, r0, t2));
+            } else { // unit upper (transposed) solve
+                r2 = t2;
+                r1 = fma(-l21, r2, t1);
+                r0 = fma(-l10, r1, fma(-l20, r2, t0));
+            }
+            double *x = xs + (size_t)(3 * blk) * CS + c;
+            x[0] = r0;
+            x[CS] = r1;
+            x[2 * CS] = r2;
+            h0 = r0; h1 = r1; h2 = r2;
+        }
+        rec = recN;
+        recN = recNN;
+    }
+}
+
+__global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevTopo T, const StaticLaunch L, const SolveCfg cfg)
+{
+    extern __shared__ __align__(16) double smem_d[];
     __shared__ int s_failCase, s_flag;
     const int model = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int n = T.nFree, nnzL = T.nnzL, dof = T.dof, nB = T.nB;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int dof = T.dof, nB = T.nB;
     const int CS = cfg.cs;
-    double *xs = smem_d;                   // [n][CS]
-    double *Lv = xs + (size_t)n * CS;      // [nnzL] CSC order
-    double *LvRow = Lv + nnzL;             // [nnzL] row order (forward pass)
-    double *dinv = LvRow + nnzL;           // [n]
-    double *Kr = dinv + n;                 // [nnzR]
+    double *Lv = smem_d + LV_PAD;                 // [-LV_PAD, nSlots + LV_PAD) factor of this model
+    double *xs = smem_d + T.nSlots + 2 * LV_PAD;  // [nPad][CS]
 
     if (tid == 0) {
         s_failCase = 0x7fffffff;
         s_flag = 0;
     }
-    // phase 0: factor of this model -> shared memory
+#define STAMP(i)                                                                              \
+    do {                                                                                      \
+        if (L.dbgClocks && tid == 0) L.dbgClocks[(size_t)model * 8 + (i)] = clock64();        \
+    } while (0)
+    STAMP(0);
+    // phase 0: factor of this model -> shared memory (strided gather from the interleaved workspace);
+    // eight independent loads in flight per thread
     {
         const double *w = L.W + model;
         const size_t ld = (size_t)L.ld;
-        for (int s = tid; s < nnzL; s += SOL_THREADS) {
-            Lv[s] = w[(size_t)s * ld];
-            LvRow[s] = w[(size_t)__ldg(T.rLslot + s) * ld];
+        for (int s0 = 0; s0 < T.nSlots; s0 += NT * 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * NT + tid;
+                v[u] = s < T.nSlots ? w[(size_t)s * ld] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * NT + tid;
+                if (s < T.nSlots) Lv[s] = v[u];
+            }
         }
-        for (int s = tid; s < n; s += SOL_THREADS) dinv[s] = w[(size_t)(nnzL + s) * ld];
-        const double *ksf = L.Ksf + (size_t)model * T.nnzR;
-        for (int s = tid; s < T.nnzR; s += SOL_THREADS) Kr[s] = ksf[s];
+        for (int s = tid; s < LV_PAD; s += NT) Lv[T.nSlots + s] = Lv[s - LV_PAD] = 0.0;
     }
-    __syncthreads();
+    const double *ksf = L.Ksf + (size_t)model * T.nnzR;
 
     for (int c0 = 0; c0 < L.nLC; c0 += cfg.casesPerPass) {
         const int nc = min(cfg.casesPerPass, L.nLC - c0);
         const double *p = L.loads + ((size_t)model * L.nLC + c0) * dof;
-        // phase 1: load cases -> xs (free rows only); model.go:692-696 and 424-437 checks
-        for (int idx = tid; idx < nc * dof; idx += SOL_THREADS) {
-            const int c = idx / dof, g = idx - c * dof;
-            const double v = p[idx];
-            const int xr = __ldg(T.xrow + g);
-            if (!isfinite(v)) atomicMax(&s_flag, 1);
-            if (xr >= 0) xs[xr * CS + c] = v;
-            else if (xr == -2 && v != 0.0) atomicMin(&s_failCase, c0 + c);
+        // phase 1: load cases -> xs (free rows), dummy rows = 0; model.go:692-696 and 424-437 checks.
+        // A thread owns up to four DOFs (index maps read once) and streams the cases two at a time:
+        // eight independent coalesced loads in flight.
+        for (int g0 = 0; g0 < dof; g0 += NT * 4) {
+            int xr[4];
+            bool in[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int g = g0 + u * NT + tid;
+                in[u] = g < dof;
+                xr[u] = in[u] ? __ldg(T.xrow + g) : -1;
+            }
+            for (int c = 0; c < nc; c += 2) {
+                double v[2][4];
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        v[j][u] = (in[u] && c + j < nc) ? p[(size_t)(c + j) * dof + g0 + u * NT + tid] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (!(in[u] && c + j < nc)) continue;
+                        const double val = v[j][u];
+                        if (!isfinite(val)) atomicMax(&s_flag, 1);
+                        if (xr[u] >= 0) xs[xr[u] * CS + c + j] = val;
+                        else if (xr[u] == -2 && val != 0.0) atomicMin(&s_failCase, c0 + c + j);
+                    }
+            }
+        }
+        for (int idx = tid; idx < T.nDummy * nc; idx += NT) {
+            const int q = idx / nc, c = idx - q * nc;
+            xs[__ldg(T.dummyPos + q) * CS + c] = 0.0;
         }
         __syncthreads();
+        STAMP(1);
 
-        // phase 2: L z = p, y = D^-1 z, L^T x = y ; one lane per load case
+        // phase 2: L z = p, then L^T x = D^-1 z; one lane per load case walks the block op lists
         if (tid < nc) {
-            const int c = tid;
-            for (int i = 0; i < n; i++) {
-                double acc = xs[i * CS + c];
-                const int q1 = __ldg(T.rLp + i + 1);
-                for (int q = __ldg(T.rLp + i); q < q1; q++) acc = fma(-LvRow[q], xs[__ldg(T.rLcol + q) * CS + c], acc);
-                xs[i * CS + c] = acc;
-            }
-            for (int i = n - 1; i >= 0; i--) {
-                double acc = xs[i * CS + c] * dinv[i];
-                const int q1 = __ldg(T.Lp + i + 1);
-                for (int q = __ldg(T.Lp + i); q < q1; q++) acc = fma(-Lv[q], xs[__ldg(T.Li + q) * CS + c], acc);
-                xs[i * CS + c] = acc;
-            }
+            substitute<true>(T.fwdOps, T.nFwdOps, Lv, xs, CS, tid);
+            STAMP(2);
+            substitute<false>(T.bwdOps, T.nBwdOps, Lv, xs, CS, tid);
         }
+        STAMP(3);
         __syncthreads();
+        STAMP(4);
 
-        // phase 3a: displacements, model.go:446-451
-        if (L.disp) {
-            double *out = L.disp + ((size_t)model * L.nLC + c0) * dof;
-            for (int idx = tid; idx < nc * dof; idx += SOL_THREADS) {
-                const int c = idx / dof, g = idx - c * dof;
-                const int xr = __ldg(T.xrow + g);
-                out[idx] = xr >= 0 ? xs[xr * CS + c] : 0.0;
-            }
-        }
-        // phase 3b: reactions, model.go:470-489 (columns ascending; eliminated columns carry d = 0)
-        if (L.react) {
-            double *out = L.react + ((size_t)model * L.nLC + c0) * dof;
-            for (int idx = tid; idx < nc * dof; idx += SOL_THREADS) {
-                const int c = idx / dof, g = idx - c * dof;
-                const int si = __ldg(T.supIndex + g);
-                double r = 0.0;
-                if (si >= 0) {
-                    r = -p[idx];
-                    const int q1 = __ldg(T.rptr + si + 1);
-                    for (int q = __ldg(T.rptr + si); q < q1; q++) r = fma(Kr[q], xs[__ldg(T.rcol + q) * CS + c], r);
+        // phase 3a+b: displacements (model.go:446-451) and reactions (model.go:470-489: columns ascending,
+        // eliminated columns carry d = 0).  Same DOF ownership as phase 1; cases in groups of four.
+        if (L.disp || L.react) {
+            double *od = L.disp ? L.disp + ((size_t)model * L.nLC + c0) * dof : nullptr;
+            double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof : nullptr;
+            for (int g0 = 0; g0 < dof; g0 += NT * 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int g = g0 + u * NT + tid;
+                    if (g >= dof) continue;
+                    const int xr = __ldg(T.xrow + g);
+                    const int si = orr ? __ldg(T.supIndex + g) : -1;
+                    int q0 = 0, q1 = 0;
+                    if (si >= 0) {
+                        q0 = __ldg(T.rptr + si);
+                        q1 = __ldg(T.rptr + si + 1);
+                    }
+                    for (int c = 0; c < nc; c += 4) {
+                        double acc[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[j] = (si >= 0 && c + j < nc) ? -p[(size_t)(c + j) * dof + g] : 0.0;
+                        if (od) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (c + j < nc) od[(size_t)(c + j) * dof + g] = xr >= 0 ? xs[xr * CS + c + j] : 0.0;
+                        }
+                        if (orr) {
+                            for (int q = q0; q < q1; q++) {
+                                const double kv = __ldg(ksf + q);
+                                const double *xc = xs + __ldg(T.rcol + q) * CS + c;
+#pragma unroll
+                                for (int j = 0; j < 4; j++)
+                                    if (c + j < nc) acc[j] = fma(kv, xc[j], acc[j]);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (c + j < nc) orr[(size_t)(c + j) * dof + g] = acc[j];
+                        }
+                    }
                 }
-                out[idx] = r;
             }
         }
-        // phase 3c: beam end forces s = k (T Zo), model.go:455-468; one thread per beam, k in registers
+        // phase 3c: beam end forces s = k (T Zo), model.go:455-468.  One thread per beam for all cases; the
+        // beams beyond the last full round of the block are spread case by case over the threads.
         if (L.forces) {
             double *out = L.forces + ((size_t)model * L.nLC + c0) * nB * 6;
+            const bool vec16 = (reinterpret_cast<uintptr_t>(L.forces) & 15) == 0;
             const double *sec = L.sections + (size_t)model * nB * 3;
-            for (int b = tid; b < nB; b += SOL_THREADS) {
+            const int nMain = (nB / NT) * NT, nRest = nB - nMain;
+            const int nItems = nMain + nRest * nc;
+            for (int it = tid; it < nItems; it += NT) {
+                int b, cBeg, cEnd;
+                if (it < nMain) { b = it; cBeg = 0; cEnd = nc; }
+                else { b = nMain + (it - nMain) / nc; cBeg = (it - nMain) % nc; cEnd = cBeg + 1; }
                 const BeamGeom g = beam_geom(T, b);
                 const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
-                double k[36];
-                stiff_beam2d(cf, T.pinMask[b], k);
+                const uint32_t pm = T.pinMask[b];
                 int rows[6];
 #pragma unroll
                 for (int e = 0; e < 6; e++) rows[e] = __ldg(T.beamRows + b * 6 + e);
-                for (int c = 0; c < nc; c++) {
-                    double u[6], z[6];
+                if (pm == 0) { // rigid ends: the matrix has five distinct values (feBeam2d.go:28-56)
+                    for (int c = cBeg; c < cEnd; c++) {
+                        double u[6];
 #pragma unroll
-                    for (int e = 0; e < 6; e++) u[e] = rows[e] >= 0 ? xs[rows[e] * CS + c] : 0.0;
-                    z[0] = fma(g.s, u[1], g.c * u[0]);
-                    z[1] = fma(g.c, u[1], -g.s * u[0]);
-                    z[2] = u[2];
-                    z[3] = fma(g.s, u[4], g.c * u[3]);
-                    z[4] = fma(g.c, u[4], -g.s * u[3]);
-                    z[5] = u[5];
-                    double *o = out + ((size_t)c * nB + b) * 6;
+                        for (int e = 0; e < 6; e++) u[e] = rows[e] >= 0 ? xs[rows[e] * CS + c] : 0.0;
+                        const double z0 = fma(g.s, u[1], g.c * u[0]), z1 = fma(g.c, u[1], -g.s * u[0]), z2 = u[2];
+                        const double z3 = fma(g.s, u[4], g.c * u[3]), z4 = fma(g.c, u[4], -g.s * u[3]), z5 = u[5];
+                        const double ax = cf.EFL * (z0 - z3);
+                        const double sh = fma(cf.EJL2, z2 + z5, cf.EJL3 * (z1 - z4));
+                        const double m0 = fma(cf.EJL, z5, fma(cf.EJL4, z2, cf.EJL2 * (z1 - z4)));
+                        const double m1 = fma(cf.EJL4, z5, fma(cf.EJL, z2, cf.EJL2 * (z1 - z4)));
+                        double *of = out + ((size_t)c * nB + b) * 6;
+                        if (vec16) { // 48-byte records: 16-byte aligned whenever the base pointer is
+                            double2 *o = reinterpret_cast<double2 *>(of);
+                            o[0] = make_double2(ax, sh);
+                            o[1] = make_double2(m0, -ax);
+                            o[2] = make_double2(-sh, m1);
+                        } else {
+                            of[0] = ax; of[1] = sh; of[2] = m0; of[3] = -ax; of[4] = -sh; of[5] = m1;
+                        }
+                    }
+                } else { // released ends: the condensed matrix is dense
+                    double k[36];
+                    stiff_beam2d(cf, pm, k);
+                    for (int c = cBeg; c < cEnd; c++) {
+                        double u[6], z[6];
 #pragma unroll
-                    for (int i = 0; i < 6; i++) {
-                        double acc = k[i * 6] * z[0];
+                        for (int e = 0; e < 6; e++) u[e] = rows[e] >= 0 ? xs[rows[e] * CS + c] : 0.0;
+                        z[0] = fma(g.s, u[1], g.c * u[0]);
+                        z[1] = fma(g.c, u[1], -g.s * u[0]);
+                        z[2] = u[2];
+                        z[3] = fma(g.s, u[4], g.c * u[3]);
+                        z[4] = fma(g.c, u[4], -g.s * u[3]);
+                        z[5] = u[5];
+                        double *o = out + ((size_t)c * nB + b) * 6;
 #pragma unroll
-                        for (int l = 1; l < 6; l++) acc = fma(k[i * 6 + l], z[l], acc);
-                        o[i] = acc;
+                        for (int i = 0; i < 6; i++) {
+                            double acc = k[i * 6] * z[0];
+#pragma unroll
+                            for (int l = 1; l < 6; l++) acc = fma(k[i * 6 + l], z[l], acc);
+                            o[i] = acc;
+                        }
                     }
                 }
             }
         }
         __syncthreads(); // xs is reused by the next pass
+        STAMP(5);
     }
     if (tid == 0) {
         int st = L.status[model];
@@ -412,7 +682,11 @@ cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaSt
         cudaError_t e = cudaFuncSetAttribute(k_solve_recover, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_solve_recover<<<L.nModels, SOL_THREADS, smem, st>>>(T, L, cfg);
+    // one thread per beam in the force phase when the model is small enough, whole warps
+    int threads = ((T.nB + 31) / 32) * 32;
+    if (threads < 128) threads = 128;
+    if (threads > SOL_MAX_THREADS) threads = 256;
+    k_solve_recover<<<L.nModels, threads, smem, st>>>(T, L, cfg);
     return cudaGetLastError();
 }
 

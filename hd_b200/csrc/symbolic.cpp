@@ -355,51 +355,132 @@ int build_symbolic(int32_t nP, const double *points, int32_t nB, const hdb_beam 
         v.erase(std::unique(v.begin(), v.end()), v.end());
     }
 
-    // ---- elimination order ----
-    if (ordering == 1) {
-        rcm_order(n, adj, S.perm);
-    } else { // natural = identity: what the reference's sparse.LU uses
-        S.perm.resize(n);
-        std::iota(S.perm.begin(), S.perm.end(), 0);
+    // ---- node blocks: every point with at least one free DOF is one 3x3 block (X, Y, M) ----
+    // Positions 3*blk + component; components that are supported or ignored are DUMMY unknowns
+    // (unit diagonal, zero right-hand side), so every block of the factor is a dense 3x3.
+    S.blkOfPoint.assign(nP, -1);
+    std::vector<int> blockPoints;
+    for (int p = 0; p < nP; p++)
+        if (S.freeIndex[3 * p] >= 0 || S.freeIndex[3 * p + 1] >= 0 || S.freeIndex[3 * p + 2] >= 0) blockPoints.push_back(p);
+    const int nBlk = (int)blockPoints.size();
+    // block adjacency from K_ff
+    std::vector<int> rankOfPoint(nP, -1);
+    for (int i = 0; i < nBlk; i++) rankOfPoint[blockPoints[i]] = i;
+    std::vector<std::vector<int>> badj(nBlk);
+    for (int i = 0; i < n; i++)
+        for (int j : adj[i]) {
+            const int bi = rankOfPoint[S.freeDofs[i] / 3], bj = rankOfPoint[S.freeDofs[j] / 3];
+            if (bi != bj) badj[bi].push_back(bj);
+        }
+    for (auto &v : badj) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
     }
+    // elimination order of the blocks
+    std::vector<int32_t> border; // position -> rank in blockPoints
+    if (ordering == 1) {
+        rcm_order(nBlk, badj, border);
+    } else { // natural: ascending point index = ascending DOF = identity permutation of the free DOFs,
+             // which is what the reference's sparse.LU uses
+        border.resize(nBlk);
+        std::iota(border.begin(), border.end(), 0);
+    }
+    std::vector<int> bpos(nBlk);
+    S.pointOfBlk.resize(nBlk);
+    for (int pos = 0; pos < nBlk; pos++) {
+        bpos[border[pos]] = pos;
+        S.pointOfBlk[pos] = blockPoints[border[pos]];
+        S.blkOfPoint[blockPoints[border[pos]]] = pos;
+    }
+    S.nBlk = nBlk;
+    S.nPad = 3 * nBlk;
+    // scalar permutation implied by the block order (exported; identity for natural ordering)
+    S.perm.clear();
+    for (int b = 0; b < nBlk; b++)
+        for (int c = 0; c < 3; c++) {
+            const int fi = S.freeIndex[3 * S.pointOfBlk[b] + c];
+            if (fi >= 0) S.perm.push_back(fi);
+        }
     S.iperm.assign(n, 0);
     for (int pos = 0; pos < n; pos++) S.iperm[S.perm[pos]] = pos;
 
-    // ---- symbolic LDL^T: column structures by merging along the elimination tree ----
-    std::vector<std::vector<int32_t>> cols(n);
-    for (int i = 0; i < n; i++) {
-        const int pi = S.iperm[i];
-        for (int j : adj[i]) {
-            const int pj = S.iperm[j];
-            if (pj > pi) cols[pi].push_back(pj);
+    // ---- scalar symbolic LDL^T (informational: the minimal fill pattern, exported for tests) ----
+    {
+        std::vector<std::vector<int32_t>> cols(n);
+        for (int i = 0; i < n; i++) {
+            const int pi = S.iperm[i];
+            for (int j : adj[i]) {
+                const int pj = S.iperm[j];
+                if (pj > pi) cols[pi].push_back(pj);
+            }
         }
+        S.Lp.assign(n + 1, 0);
+        for (int j = 0; j < n; j++) {
+            auto &v = cols[j];
+            std::sort(v.begin(), v.end());
+            v.erase(std::unique(v.begin(), v.end()), v.end());
+            if (!v.empty()) {
+                const int parent = v[0];
+                cols[parent].insert(cols[parent].end(), v.begin() + 1, v.end());
+            }
+            S.Lp[j + 1] = S.Lp[j] + (int32_t)v.size();
+            S.maxColCount = std::max(S.maxColCount, (int)v.size());
+        }
+        S.nnzL = S.Lp[n];
+        S.Li.resize(S.nnzL);
+        for (int j = 0; j < n; j++) std::copy(cols[j].begin(), cols[j].end(), S.Li.begin() + S.Lp[j]);
     }
-    S.Lp.assign(n + 1, 0);
-    for (int j = 0; j < n; j++) {
-        auto &v = cols[j];
+
+    // ---- block symbolic LDL^T ----
+    std::vector<std::vector<int32_t>> bcols(nBlk);
+    for (int i = 0; i < nBlk; i++)
+        for (int j : badj[i])
+            if (bpos[j] > bpos[i]) bcols[bpos[i]].push_back(bpos[j]);
+    S.BLp.assign(nBlk + 1, 0);
+    for (int J = 0; J < nBlk; J++) {
+        auto &v = bcols[J];
         std::sort(v.begin(), v.end());
         v.erase(std::unique(v.begin(), v.end()), v.end());
-        if (!v.empty()) {
-            const int parent = v[0];
-            cols[parent].insert(cols[parent].end(), v.begin() + 1, v.end());
-        }
-        S.Lp[j + 1] = S.Lp[j] + (int32_t)v.size();
-        S.maxColCount = std::max(S.maxColCount, (int)v.size());
+        if (!v.empty()) bcols[v[0]].insert(bcols[v[0]].end(), v.begin() + 1, v.end());
+        S.BLp[J + 1] = S.BLp[J] + (int32_t)v.size();
+        S.maxBlkCount = std::max(S.maxBlkCount, (int)v.size());
     }
-    S.nnzL = S.Lp[n];
-    S.nSlots = S.nnzL + n;
-    S.Li.resize(S.nnzL);
-    for (int j = 0; j < n; j++) std::copy(cols[j].begin(), cols[j].end(), S.Li.begin() + S.Lp[j]);
-    auto l_slot = [&](int row, int col) -> int32_t { // row > col, position numbering
-        auto b = S.Li.begin() + S.Lp[col], e = S.Li.begin() + S.Lp[col + 1];
-        auto it = std::lower_bound(b, e, row);
-        return (it != e && *it == row) ? (int32_t)(it - S.Li.begin()) : -1;
+    const int nOff = S.BLp[nBlk];
+    S.BLi.resize(nOff);
+    for (int J = 0; J < nBlk; J++) std::copy(bcols[J].begin(), bcols[J].end(), S.BLi.begin() + S.BLp[J]);
+    // slot layout: block column J = [d0 d1 d2 | l10 l20 l21 | off blocks: 9 values row-major + 1 pad each]
+    S.colOff.assign(nBlk + 1, 0);
+    S.blkSlot.resize(nOff);
+    for (int J = 0; J < nBlk; J++) {
+        for (int q = S.BLp[J]; q < S.BLp[J + 1]; q++) S.blkSlot[q] = S.colOff[J] + BLK_HDR + BLK_STRIDE * (q - S.BLp[J]);
+        S.colOff[J + 1] = S.colOff[J] + BLK_HDR + BLK_STRIDE * (S.BLp[J + 1] - S.BLp[J]);
+    }
+    S.nSlots = S.colOff[nBlk];
+    auto off_block = [&](int I, int J) -> int32_t { // I > J
+        auto b = S.BLi.begin() + S.BLp[J], e = S.BLi.begin() + S.BLp[J + 1];
+        auto it = std::lower_bound(b, e, I);
+        return (it != e && *it == I) ? (int32_t)(it - S.BLi.begin()) : -1;
+    };
+    auto slot_of = [&](int pr, int pc) -> int32_t { // pr >= pc, padded positions
+        const int I = pr / 3, r = pr % 3, J = pc / 3, c = pc % 3;
+        if (pr == pc) return S.colOff[J] + c;
+        if (I == J) return S.colOff[J] + 3 + (r == 1 ? 0 : (c == 0 ? 1 : 2));
+        const int32_t q = off_block(I, J);
+        return q < 0 ? -1 : S.blkSlot[q] + r * 3 + c;
     };
 
-    // ---- DOF -> x row ----
+    // ---- DOF -> x row (padded position) ----
     S.xrow.assign(dof, -1);
-    for (int g = 0; g < dof; g++)
-        if (S.freeIndex[g] >= 0) S.xrow[g] = S.iperm[S.freeIndex[g]];
+    S.slotInit.assign(S.nSlots, 0);
+    for (int b = 0; b < nBlk; b++)
+        for (int c = 0; c < 3; c++) {
+            const int g = 3 * S.pointOfBlk[b] + c;
+            if (S.freeIndex[g] >= 0) S.xrow[g] = 3 * b + c;
+            else {
+                S.dummyPos.push_back(3 * b + c);
+                S.slotInit[S.colOff[b] + c] = 1; // unit diagonal of a dummy unknown
+            }
+        }
     for (int32_t g : S.ignore) S.xrow[g] = -2;
     S.beamRows.resize((size_t)nB * 6);
     for (int b = 0; b < nB; b++)
@@ -416,24 +497,21 @@ int build_symbolic(int32_t nP, const double *points, int32_t nB, const hdb_beam 
         if (S.posSlot[q] < 0) continue;
         const Trip &t = trips[q];
         const int xi = S.xrow[t.row], xj = S.xrow[t.col];
-        if (xi >= 0 && xj >= 0) {
-            if (xi == xj) slotSrc[S.nnzL + xi].push_back(t.code);
-            else if (xi > xj) {
-                const int32_t sl = l_slot(xi, xj);
-                if (sl < 0) {
-                    detail = "internal: factor slot missing";
-                    return HDB_ERR_ARG;
-                }
-                slotSrc[sl].push_back(t.code);
+        if (xi >= 0 && xj >= 0 && xi >= xj) { // the factor takes the lower triangle (in elimination order)
+            const int32_t sl = slot_of(xi, xj);
+            if (sl < 0) {
+                detail = "internal: factor slot missing";
+                return HDB_ERR_ARG;
             }
+            slotSrc[sl].push_back(t.code);
         }
         const int si = S.supIndex[t.row];
         if (si >= 0 && xj >= 0) rrow[si][t.col].push_back(t.code);
     }
     S.gptr.assign(S.nSlots + 1, 0);
-    for (int s = 0; s < S.nSlots; s++) S.gptr[s + 1] = S.gptr[s] + (int32_t)slotSrc[s].size();
+    for (int s2 = 0; s2 < S.nSlots; s2++) S.gptr[s2 + 1] = S.gptr[s2] + (int32_t)slotSrc[s2].size();
     S.gsrc.resize(S.gptr[S.nSlots]);
-    for (int s = 0; s < S.nSlots; s++) std::copy(slotSrc[s].begin(), slotSrc[s].end(), S.gsrc.begin() + S.gptr[s]);
+    for (int s2 = 0; s2 < S.nSlots; s2++) std::copy(slotSrc[s2].begin(), slotSrc[s2].end(), S.gsrc.begin() + S.gptr[s2]);
     S.rptr.assign(S.nSup + 1, 0);
     S.rgptr.assign(1, 0);
     for (int si = 0; si < S.nSup; si++) {
@@ -446,42 +524,82 @@ int build_symbolic(int32_t nP, const double *points, int32_t nB, const hdb_beam 
     }
     S.nnzR = (int)S.rcol.size();
 
-    // ---- numeric factorization schedule ----
-    S.uptr.assign(n + 1, 0);
-    for (int j = 0; j < n; j++) {
-        const int cnt = S.Lp[j + 1] - S.Lp[j];
-        S.uptr[j + 1] = S.uptr[j] + cnt * (cnt + 1) / 2;
+    // ---- block factorization schedule: Schur targets of every pair of off blocks of a column ----
+    S.pairPtr.assign(nBlk + 1, 0);
+    for (int J = 0; J < nBlk; J++) {
+        const int nb = S.BLp[J + 1] - S.BLp[J];
+        S.pairPtr[J + 1] = S.pairPtr[J] + nb * (nb + 1) / 2;
+        S.nUpdates += 3 * (3 + 3 * nb) * (4 + 3 * nb) / 2; // scalar multiply-subtracts, upper bound
     }
-    S.nUpdates = S.uptr[n];
-    S.utgt.resize(S.uptr[n]);
-    for (int j = 0; j < n; j++) {
-        int32_t q = S.uptr[j];
-        for (int a = S.Lp[j]; a < S.Lp[j + 1]; a++)
-            for (int b = S.Lp[j]; b <= a; b++) {
-                const int ra = S.Li[a], rb = S.Li[b];
-                int32_t tg = (a == b) ? S.nnzL + ra : l_slot(ra, rb);
-                if (tg < 0) {
-                    detail = "internal: fill slot missing";
-                    return HDB_ERR_ARG;
+    S.pairTgt.resize(S.pairPtr[nBlk]);
+    S.needUpto.assign(nBlk, 0);
+    for (int J = 0; J < nBlk; J++) {
+        int32_t k = S.pairPtr[J];
+        int maxI = J;
+        for (int a = S.BLp[J]; a < S.BLp[J + 1]; a++) {
+            maxI = std::max(maxI, (int)S.BLi[a]);
+            for (int b = S.BLp[J]; b <= a; b++) {
+                int32_t tg;
+                if (a == b) tg = S.colOff[S.BLi[a]]; // diagonal block header of row block I
+                else {
+                    const int32_t q = off_block(S.BLi[a], S.BLi[b]);
+                    if (q < 0) {
+                        detail = "internal: fill block missing";
+                        return HDB_ERR_ARG;
+                    }
+                    tg = S.blkSlot[q];
                 }
-                S.utgt[q++] = tg;
+                S.pairTgt[k++] = tg;
+            }
+        }
+        S.needUpto[J] = S.colOff[maxI + 1];
+    }
+    for (int J = 1; J < nBlk; J++) S.needUpto[J] = std::max(S.needUpto[J], S.needUpto[J - 1]);
+    S.winNeed = 0;
+    for (int J = 0; J < nBlk; J++)
+        S.winNeed = std::max(S.winNeed, S.needUpto[std::min(J + FACTOR_PREFETCH, nBlk - 1)] - S.colOff[J]);
+
+    // ---- row access of the off blocks for the forward substitution ----
+    S.fwdPtr.assign(nBlk + 1, 0);
+    for (int q = 0; q < nOff; q++) S.fwdPtr[S.BLi[q] + 1]++;
+    for (int I = 0; I < nBlk; I++) S.fwdPtr[I + 1] += S.fwdPtr[I];
+    S.fwdJ.resize(nOff);
+    S.fwdSlot.resize(nOff);
+    {
+        std::vector<int32_t> w(S.fwdPtr.begin(), S.fwdPtr.end() - 1);
+        for (int J = 0; J < nBlk; J++) // ascending J inside every row
+            for (int q = S.BLp[J]; q < S.BLp[J + 1]; q++) {
+                const int e = w[S.BLi[q]]++;
+                S.fwdJ[e] = J;
+                S.fwdSlot[e] = S.blkSlot[q];
             }
     }
 
-    // ---- row access of L ----
-    S.rLp.assign(n + 1, 0);
-    for (int p = 0; p < S.nnzL; p++) S.rLp[S.Li[p] + 1]++;
-    for (int i = 0; i < n; i++) S.rLp[i + 1] += S.rLp[i];
-    S.rLcol.resize(S.nnzL);
-    S.rLslot.resize(S.nnzL);
-    {
-        std::vector<int32_t> w(S.rLp.begin(), S.rLp.end() - 1);
-        for (int j = 0; j < n; j++)
-            for (int p = S.Lp[j]; p < S.Lp[j + 1]; p++) {
-                const int q = w[S.Li[p]]++;
-                S.rLcol[q] = j;
-                S.rLslot[q] = p;
-            }
+    // ---- substitution op lists (see device_topo.hpp): {slot, blk | flags | kind << 28} ----
+    auto rec = [](std::vector<int32_t> &v, int slot, int blk, int flags, int kind) {
+        v.push_back(slot);
+        v.push_back(blk | flags | (kind << 28));
+    };
+    const int KPULL = 0, KDIAG = 1, KFUSED = 2, FFIRST = 1 << 27, FPREV = 1 << 26;
+    for (int I = 0; I < nBlk; I++) { // forward: values laid out [off block 10 | header 6] from rec.slot
+        const int e0 = S.fwdPtr[I], e1 = S.fwdPtr[I + 1];
+        if (e1 - e0 == 1 && S.fwdJ[e0] == I - 1 && S.fwdSlot[e0] + BLK_STRIDE == S.colOff[I]) {
+            rec(S.fwdOps, S.fwdSlot[e0], I, FFIRST | FPREV, KFUSED);
+            continue;
+        }
+        for (int e = e0; e < e1; e++)
+            rec(S.fwdOps, S.fwdSlot[e], S.fwdJ[e], (e == e0 ? FFIRST : 0) | (S.fwdJ[e] == I - 1 ? FPREV : 0), KPULL);
+        rec(S.fwdOps, S.colOff[I] - BLK_STRIDE, I, (e0 == e1 ? FFIRST : 0), KDIAG);
+    }
+    for (int J = nBlk - 1; J >= 0; J--) { // backward: [header 6 | off block 10] from rec.slot
+        const int q0 = S.BLp[J], q1 = S.BLp[J + 1];
+        if (q1 - q0 == 1 && S.BLi[q0] == J + 1) {
+            rec(S.bwdOps, S.colOff[J], J, FFIRST | FPREV, KFUSED);
+            continue;
+        }
+        for (int q = q0; q < q1; q++)
+            rec(S.bwdOps, S.blkSlot[q] - BLK_HDR, S.BLi[q], (q == q0 ? FFIRST : 0) | (S.BLi[q] == J + 1 ? FPREV : 0), KPULL);
+        rec(S.bwdOps, S.colOff[J], J, (q0 == q1 ? FFIRST : 0), KDIAG);
     }
     return HDB_OK;
 }
