@@ -152,6 +152,19 @@ static int ensure_device(hdb_topology *t)
     UP(S.pairTgt, pairTgt);
     UP(S.needUpto, needUpto);
     {
+        std::vector<int32_t> desc((size_t)S.nBlk * 4);
+        for (int J = 0; J < S.nBlk; J++) {
+            const int nb = S.BLp[J + 1] - S.BLp[J];
+            desc[4 * J + 0] = S.colOff[J];
+            desc[4 * J + 1] = nb;
+            desc[4 * J + 2] = S.needUpto[std::min(J + FACTOR_PREFETCH, S.nBlk - 1)];
+            desc[4 * J + 3] = nb > 0 ? S.pairTgt[S.pairPtr[J]] : -1;
+        }
+        const int32_t *dp = nullptr;
+        if ((rc = upload(t, desc, &dp)) != HDB_OK) return rc;
+        D.colDesc = reinterpret_cast<const int4 *>(dp);
+    }
+    {
         const int32_t *f = nullptr, *b = nullptr;
         if ((rc = upload(t, S.fwdOps, &f)) != HDB_OK) return rc;
         if ((rc = upload(t, S.bwdOps, &b)) != HDB_OK) return rc;

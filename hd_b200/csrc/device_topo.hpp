@@ -29,6 +29,7 @@ struct DevTopo {
     const int32_t *kptr, *ksrc;   // full CSR pattern (tests)
     // block factorization schedule
     const int32_t *BLp, *BLi, *colOff, *blkSlot, *pairPtr, *pairTgt, *needUpto;
+    const int4 *colDesc;       // [nBlk] {first slot, off-block count, prefetch bound, first Schur target}
     // substitution op lists: int2 {slot, blk | flags | kind << 28}
     const int2 *fwdOps, *bwdOps;
     // recovery

@@ -15,7 +15,9 @@
 //
 // Everything is HBM-bound integer-indexed FP64 work: no tensor-core shapes exist here (fronts are
 // <= 6x6); see DESIGN.md for the roofline of each kernel.
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "device_topo.hpp"
 #include "element.cuh"
@@ -49,10 +51,11 @@ __device__ __forceinline__ bool section_ok(double v)
 // ------------------------------------------------------------------------------------------------
 // k_assemble
 // ------------------------------------------------------------------------------------------------
-constexpr int ASM_THREADS = 256;
+constexpr int ASM_MAX_THREADS = 512;
 
-__global__ void __launch_bounds__(ASM_THREADS) k_assemble(const DevTopo T, const StaticLaunch L)
+__global__ void __launch_bounds__(ASM_MAX_THREADS) k_assemble(const DevTopo T, const StaticLaunch L)
 {
+    const int ASM_THREADS = blockDim.x; // one thread per beam when nB <= 512: a single round of element work
     extern __shared__ double smem_d[];
     __shared__ int s_flag;
     const int model = blockIdx.x;
@@ -122,7 +125,9 @@ cudaError_t launch_assemble(const DevTopo &T, const StaticLaunch &L, cudaStream_
         cudaError_t e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_assemble<<<L.nModels, ASM_THREADS, smem, st>>>(T, L);
+    int threads = ((T.nB + 31) / 32) * 32;
+    threads = threads < 128 ? 128 : (threads > ASM_MAX_THREADS ? ASM_MAX_THREADS : threads);
+    k_assemble<<<L.nModels, threads, smem, st>>>(T, L);
     return cudaGetLastError();
 }
 
@@ -197,14 +202,18 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
         }
     }
     bool bad = false;
+    // one 16-byte descriptor per block column {first slot, off blocks, prefetch bound, first Schur target},
+    // fetched one column ahead so that no index load sits on the pivot chain
+    int4 dN = __ldg(T.colDesc);
     for (int J = 0; J < nBlk; J++) {
+        const int4 d = dN;
+        if (J + 1 < nBlk) dN = __ldg(T.colDesc + J + 1);
         if (WS) {
-            const int upto = __ldg(T.needUpto + min(J + FACTOR_PREFETCH, nBlk - 1));
-            for (; loaded < upto; loaded++) cp_async8(&WIN(loaded), wg + (size_t)loaded * ld);
+            for (; loaded < d.z; loaded++) cp_async8(&WIN(loaded), wg + (size_t)loaded * ld);
             cp_async_commit();
             cp_async_wait<FACTOR_PREFETCH>();
         }
-        const int base = __ldg(T.colOff + J);
+        const int base = d.x;
         // ---- scalar LDL^T of the 3x3 diagonal block ----
         double d0 = WIN(base + 0), d1 = WIN(base + 1), d2 = WIN(base + 2);
         const double a10 = WIN(base + 3), a20 = WIN(base + 4), a21 = WIN(base + 5);
@@ -223,57 +232,79 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
         const double inv2 = __drcp_rn(d2);
         WIN(base + 0) = inv0; WIN(base + 1) = inv1; WIN(base + 2) = inv2;
         WIN(base + 3) = l10;  WIN(base + 4) = l20;  WIN(base + 5) = l21;
-        const int q0 = __ldg(T.BLp + J), nb = __ldg(T.BLp + J + 1) - q0;
-        // ---- off blocks: rows of L = A (L_JJ D_J)^-T ; stored scaled, u = l * d recovered when needed ----
-        for (int a = 0; a < nb; a++) {
-            const int sa = base + BLK_HDR + BLK_STRIDE * a;
+        const int nb = d.y;
+        if (nb == 1) {
+            // ---- the banded case: one off block; its values and the Schur update stay in registers ----
+            const int sa = base + BLK_HDR, t = d.w;
+            double la[9], ua[9];
 #pragma unroll
             for (int r = 0; r < 3; r++) {
                 const double u0 = WIN(sa + 3 * r);
                 const double u1 = fma(-l10, u0, WIN(sa + 3 * r + 1));
                 const double u2 = fma(-l21, u1, fma(-l20, u0, WIN(sa + 3 * r + 2)));
-                WIN(sa + 3 * r) = u0 * inv0;
-                WIN(sa + 3 * r + 1) = u1 * inv1;
-                WIN(sa + 3 * r + 2) = u2 * inv2;
+                ua[3 * r] = u0; ua[3 * r + 1] = u1; ua[3 * r + 2] = u2;
+                la[3 * r] = u0 * inv0; la[3 * r + 1] = u1 * inv1; la[3 * r + 2] = u2 * inv2;
             }
-        }
-        // ---- Schur updates of every pair of off blocks ----
-        const int32_t *tg = T.pairTgt + __ldg(T.pairPtr + J);
-        for (int a = 0; a < nb; a++) {
-            const int sa = base + BLK_HDR + BLK_STRIDE * a;
-            double la[9];
 #pragma unroll
-            for (int e = 0; e < 9; e++) la[e] = WIN(sa + e);
-            for (int b = 0; b <= a; b++) {
-                const int sb = base + BLK_HDR + BLK_STRIDE * b;
-                double ub[9];
+            for (int e = 0; e < 9; e++) WIN(sa + e) = la[e];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                WIN(t + r) = fma(-la[3 * r + 2], ua[3 * r + 2], fma(-la[3 * r + 1], ua[3 * r + 1], fma(-la[3 * r], ua[3 * r], WIN(t + r))));
+            WIN(t + 3) = fma(-la[5], ua[2], fma(-la[4], ua[1], fma(-la[3], ua[0], WIN(t + 3))));
+            WIN(t + 4) = fma(-la[8], ua[2], fma(-la[7], ua[1], fma(-la[6], ua[0], WIN(t + 4))));
+            WIN(t + 5) = fma(-la[8], ua[5], fma(-la[7], ua[4], fma(-la[6], ua[3], WIN(t + 5))));
+        } else if (nb > 1) {
+            // ---- off blocks: rows of L = A (L_JJ D_J)^-T ; stored scaled, u = l * d recovered when needed ----
+            for (int a = 0; a < nb; a++) {
+                const int sa = base + BLK_HDR + BLK_STRIDE * a;
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
-                    ub[3 * r] = WIN(sb + 3 * r) * d0;
-                    ub[3 * r + 1] = WIN(sb + 3 * r + 1) * d1;
-                    ub[3 * r + 2] = WIN(sb + 3 * r + 2) * d2;
+                    const double u0 = WIN(sa + 3 * r);
+                    const double u1 = fma(-l10, u0, WIN(sa + 3 * r + 1));
+                    const double u2 = fma(-l21, u1, fma(-l20, u0, WIN(sa + 3 * r + 2)));
+                    WIN(sa + 3 * r) = u0 * inv0;
+                    WIN(sa + 3 * r + 1) = u1 * inv1;
+                    WIN(sa + 3 * r + 2) = u2 * inv2;
                 }
-                const int t = __ldg(tg++);
-                if (a == b) { // diagonal block of row block I_a: header [d0 d1 d2 | (1,0) (2,0) (2,1)]
+            }
+            // ---- Schur updates of every pair of off blocks ----
+            const int32_t *tg = T.pairTgt + __ldg(T.pairPtr + J);
+            for (int a = 0; a < nb; a++) {
+                const int sa = base + BLK_HDR + BLK_STRIDE * a;
+                double la[9];
 #pragma unroll
-                    for (int r = 0; r < 3; r++)
-                        WIN(t + r) = fma(-la[3 * r + 2], ub[3 * r + 2], fma(-la[3 * r + 1], ub[3 * r + 1], fma(-la[3 * r], ub[3 * r], WIN(t + r))));
-                    WIN(t + 3) = fma(-la[5], ub[2], fma(-la[4], ub[1], fma(-la[3], ub[0], WIN(t + 3))));
-                    WIN(t + 4) = fma(-la[8], ub[2], fma(-la[7], ub[1], fma(-la[6], ub[0], WIN(t + 4))));
-                    WIN(t + 5) = fma(-la[8], ub[5], fma(-la[7], ub[4], fma(-la[6], ub[3], WIN(t + 5))));
-                } else { // block (I_a, I_b): rows from a, columns from b
+                for (int e = 0; e < 9; e++) la[e] = WIN(sa + e);
+                for (int b = 0; b <= a; b++) {
+                    const int sb = base + BLK_HDR + BLK_STRIDE * b;
+                    double ub[9];
 #pragma unroll
-                    for (int r = 0; r < 3; r++)
+                    for (int r = 0; r < 3; r++) {
+                        ub[3 * r] = WIN(sb + 3 * r) * d0;
+                        ub[3 * r + 1] = WIN(sb + 3 * r + 1) * d1;
+                        ub[3 * r + 2] = WIN(sb + 3 * r + 2) * d2;
+                    }
+                    const int t = __ldg(tg++);
+                    if (a == b) { // diagonal block of row block I_a: header [d0 d1 d2 | (1,0) (2,0) (2,1)]
 #pragma unroll
-                        for (int rp = 0; rp < 3; rp++)
-                            WIN(t + 3 * r + rp) = fma(-la[3 * r + 2], ub[3 * rp + 2],
-                                                      fma(-la[3 * r + 1], ub[3 * rp + 1], fma(-la[3 * r], ub[3 * rp], WIN(t + 3 * r + rp))));
+                        for (int r = 0; r < 3; r++)
+                            WIN(t + r) = fma(-la[3 * r + 2], ub[3 * r + 2], fma(-la[3 * r + 1], ub[3 * r + 1], fma(-la[3 * r], ub[3 * r], WIN(t + r))));
+                        WIN(t + 3) = fma(-la[5], ub[2], fma(-la[4], ub[1], fma(-la[3], ub[0], WIN(t + 3))));
+                        WIN(t + 4) = fma(-la[8], ub[2], fma(-la[7], ub[1], fma(-la[6], ub[0], WIN(t + 4))));
+                        WIN(t + 5) = fma(-la[8], ub[5], fma(-la[7], ub[4], fma(-la[6], ub[3], WIN(t + 5))));
+                    } else { // block (I_a, I_b): rows from a, columns from b
+#pragma unroll
+                        for (int r = 0; r < 3; r++)
+#pragma unroll
+                            for (int rp = 0; rp < 3; rp++)
+                                WIN(t + 3 * r + rp) = fma(-la[3 * r + 2], ub[3 * rp + 2],
+                                                          fma(-la[3 * r + 1], ub[3 * rp + 1], fma(-la[3 * r], ub[3 * rp], WIN(t + 3 * r + rp))));
+                    }
                 }
             }
         }
         // ---- block column J is final: stream it out ----
         if (WS) {
-            const int end = __ldg(T.colOff + J + 1);
+            const int end = base + BLK_HDR + BLK_STRIDE * nb;
             for (int s2 = base; s2 < end; s2++) wg[(size_t)s2 * ld] = WIN(s2);
         }
     }
@@ -314,6 +345,7 @@ constexpr int LV_PAD = 16; // the substitution reads 16 doubles around any slot:
 struct SolveCfg {
     int casesPerPass; // <= 32
     int cs;           // row stride of xs in doubles (odd)
+    int nSM;
 };
 
 __host__ __device__ inline int odd_stride(int c) { return c | 1; }
@@ -345,96 +377,122 @@ bool solve_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, s
 // index is static:
 //   forward : [off block 9 + pad | 1/d0 1/d1 1/d2 l10 l20 l21]   (OP_DIAG points 10 before its header)
 //   backward: [1/d0 1/d1 1/d2 l10 l20 l21 | off block 9 + pad]   (OP_PULL points 6 before its block)
-// Software pipeline: the loads of op k+1 are issued in the middle of op k, right after its off-block
-// values have been consumed, so their shared-memory latency hides behind the diagonal solve chain.
-template <bool FWD>
-struct OpVals {
-    double L00, L01, L02, L10, L11, L12, L20, L21, L22;
-    double i0, i1, i2; // 1/d (backward only)
-    double l10, l20, l21;
-    double p0, p1, p2; // x rows of rec's block: right-hand side of its own block, or a pulled source
-};
-
-template <bool FWD>
-__device__ __forceinline__ void op_load(const int2 rec, const double *Lv, const double *xs, const int CS, const int c,
-                                        OpVals<FWD> &o)
+// A single warp is issue-bound here (about one instruction every two cycles), so the loop is written
+// for instruction count: 32-bit shared-window addresses with immediate offsets, 16-byte value loads, a
+// two-op unrolled body without register rotation.  Software pipeline: the loads of op k+1 are issued in
+// the middle of op k, right after its off-block values have been consumed, so their latency hides
+// behind the diagonal solve chain.
+__device__ __forceinline__ double lds_f64(unsigned a)
 {
-    const double *base = Lv + rec.x;
-    const double2 *src = reinterpret_cast<const double2 *>(base);
-    double2 t;
-    if (FWD) {
-        t = src[0]; o.L00 = t.x; o.L01 = t.y;
-        t = src[1]; o.L02 = t.x; o.L10 = t.y;
-        t = src[2]; o.L11 = t.x; o.L12 = t.y;
-        t = src[3]; o.L20 = t.x; o.L21 = t.y;
-        o.L22 = base[8];
-        o.l10 = base[13];
-        t = src[7]; o.l20 = t.x; o.l21 = t.y;
-        o.i0 = o.i1 = o.i2 = 0.0;
-    } else {
-        t = src[0]; o.i0 = t.x; o.i1 = t.y;
-        t = src[1]; o.i2 = t.x; o.l10 = t.y;
-        t = src[2]; o.l20 = t.x; o.l21 = t.y;
-        t = src[3]; o.L00 = t.x; o.L01 = t.y;
-        t = src[4]; o.L02 = t.x; o.L10 = t.y;
-        t = src[5]; o.L11 = t.x; o.L12 = t.y;
-        t = src[6]; o.L20 = t.x; o.L21 = t.y;
-        o.L22 = base[14];
-    }
-    const double *x = xs + (size_t)(3 * (rec.y & OP_BLK_MASK)) * CS + c;
-    o.p0 = x[0];
-    o.p1 = x[CS];
-    o.p2 = x[2 * CS];
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64o(unsigned a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void lds_v2o(unsigned a, double &x, double &y)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(x), "=d"(y) : "r"(a), "n"(OFF));
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
 template <bool FWD>
-__device__ __noinline__ void substitute(const int2 *__restrict__ ops, const int nOps, const double *Lv, double *xs,
+__device__ __noinline__ void substitute(const int2 *__restrict__ ops, const int nOps, const unsigned lvA, const unsigned xsA,
                                         const int CS, const int c)
 {
     if (nOps <= 0) return;
+    const unsigned xA = xsA + (unsigned)c * 8u;
+    const unsigned CS8 = (unsigned)CS * 8u, CS24 = 3u * CS8;
     double h0 = 0, h1 = 0, h2 = 0; // the block finished last
     double s0 = 0, s1 = 0, s2 = 0; // pulled sum of the block in progress
+    // values of the current op that its first stage consumes; reloaded in the middle of the op
+    double L00, L01, L02, L10, L11, L12, L20, L21, L22, p0, p1, p2, i0 = 0, i1 = 0, i2 = 0;
+    unsigned xa;
+#define SUB_LOAD_MID(REC)                                                          \
+    do {                                                                           \
+        const unsigned a_ = lvA + (unsigned)(REC).x * 8u;                          \
+        if (FWD) {                                                                 \
+            lds_v2o<0>(a_, L00, L01);                                              \
+            lds_v2o<16>(a_, L02, L10);                                             \
+            lds_v2o<32>(a_, L11, L12);                                             \
+            lds_v2o<48>(a_, L20, L21);                                             \
+            L22 = lds_f64o<64>(a_);                                                \
+        } else {                                                                   \
+            lds_v2o<0>(a_, i0, i1);                                                \
+            i2 = lds_f64o<16>(a_);                                                 \
+            lds_v2o<48>(a_, L00, L01);                                             \
+            lds_v2o<64>(a_, L02, L10);                                             \
+            lds_v2o<80>(a_, L11, L12);                                             \
+            lds_v2o<96>(a_, L20, L21);                                             \
+            L22 = lds_f64o<112>(a_);                                               \
+        }                                                                          \
+        xa = xA + (unsigned)((REC).y & OP_BLK_MASK) * CS24;                        \
+        p0 = lds_f64(xa);                                                          \
+        p1 = lds_f64(xa + CS8);                                                    \
+        p2 = lds_f64(xa + 2u * CS8);                                               \
+    } while (0)
+
     int2 rec = __ldg(ops), recN = __ldg(ops + min(1, nOps - 1));
-    OpVals<FWD> v;
-    op_load<FWD>(rec, Lv, xs, CS, c, v);
+    SUB_LOAD_MID(rec);
     for (int k = 0; k < nOps; k++) {
         const int2 recNN = __ldg(ops + min(k + 2, nOps - 1));
         const int kind = (unsigned)rec.y >> OP_KIND_SHIFT;
+        // diagonal-stage values of this op: needed only after the first stage, so their latency is hidden
+        double l10, l20, l21;
+        {
+            const unsigned a = lvA + (unsigned)rec.x * 8u;
+            if (FWD) {
+                l10 = lds_f64o<104>(a);
+                lds_v2o<112>(a, l20, l21);
+            } else {
+                l10 = lds_f64o<24>(a);
+                lds_v2o<32>(a, l20, l21);
+            }
+        }
         // ---- stage 1: off block ----
         double t0, t1, t2; // right-hand side of the diagonal stage
         if (kind == OP_FUSED) { // source = block finished just before (registers), fresh accumulator
             if (FWD) {
-                t0 = fma(-v.L02, h2, fma(-v.L01, h1, fma(-v.L00, h0, v.p0)));
-                t1 = fma(-v.L12, h2, fma(-v.L11, h1, fma(-v.L10, h0, v.p1)));
-                t2 = fma(-v.L22, h2, fma(-v.L21, h1, fma(-v.L20, h0, v.p2)));
+                t0 = fma(-L02, h2, fma(-L01, h1, fma(-L00, h0, p0)));
+                t1 = fma(-L12, h2, fma(-L11, h1, fma(-L10, h0, p1)));
+                t2 = fma(-L22, h2, fma(-L21, h1, fma(-L20, h0, p2)));
             } else {
-                t0 = fma(-v.L20, h2, fma(-v.L10, h1, fma(-v.L00, h0, v.p0 * v.i0)));
-                t1 = fma(-v.L21, h2, fma(-v.L11, h1, fma(-v.L01, h0, v.p1 * v.i1)));
-                t2 = fma(-v.L22, h2, fma(-v.L12, h1, fma(-v.L02, h0, v.p2 * v.i2)));
+                t0 = fma(-L20, h2, fma(-L10, h1, fma(-L00, h0, p0 * i0)));
+                t1 = fma(-L21, h2, fma(-L11, h1, fma(-L01, h0, p1 * i1)));
+                t2 = fma(-L22, h2, fma(-L12, h1, fma(-L02, h0, p2 * i2)));
             }
         } else if (kind == OP_PULL) {
             if (rec.y & OPF_FIRST) s0 = s1 = s2 = 0.0;
             double z0 = h0, z1 = h1, z2 = h2;
-            if (!(rec.y & OPF_PREV)) { z0 = v.p0; z1 = v.p1; z2 = v.p2; }
+            if (!(rec.y & OPF_PREV)) { z0 = p0; z1 = p1; z2 = p2; }
             if (FWD) {
-                s0 = fma(v.L02, z2, fma(v.L01, z1, fma(v.L00, z0, s0)));
-                s1 = fma(v.L12, z2, fma(v.L11, z1, fma(v.L10, z0, s1)));
-                s2 = fma(v.L22, z2, fma(v.L21, z1, fma(v.L20, z0, s2)));
+                s0 = fma(L02, z2, fma(L01, z1, fma(L00, z0, s0)));
+                s1 = fma(L12, z2, fma(L11, z1, fma(L10, z0, s1)));
+                s2 = fma(L22, z2, fma(L21, z1, fma(L20, z0, s2)));
             } else {
-                s0 = fma(v.L20, z2, fma(v.L10, z1, fma(v.L00, z0, s0)));
-                s1 = fma(v.L21, z2, fma(v.L11, z1, fma(v.L01, z0, s1)));
-                s2 = fma(v.L22, z2, fma(v.L12, z1, fma(v.L02, z0, s2)));
+                s0 = fma(L20, z2, fma(L10, z1, fma(L00, z0, s0)));
+                s1 = fma(L21, z2, fma(L11, z1, fma(L01, z0, s1)));
+                s2 = fma(L22, z2, fma(L12, z1, fma(L02, z0, s2)));
             }
             t0 = t1 = t2 = 0.0;
         } else { // OP_DIAG
             if (rec.y & OPF_FIRST) s0 = s1 = s2 = 0.0;
-            if (FWD) { t0 = v.p0 - s0; t1 = v.p1 - s1; t2 = v.p2 - s2; }
-            else { t0 = fma(v.p0, v.i0, -s0); t1 = fma(v.p1, v.i1, -s1); t2 = fma(v.p2, v.i2, -s2); }
+            if (FWD) { t0 = p0 - s0; t1 = p1 - s1; t2 = p2 - s2; }
+            else { t0 = fma(p0, i0, -s0); t1 = fma(p1, i1, -s1); t2 = fma(p2, i2, -s2); }
         }
-        const double l10 = v.l10, l20 = v.l20, l21 = v.l21;
-        const int blk = rec.y & OP_BLK_MASK;
-        // ---- issue the loads of the next op: they complete behind the diagonal chain below ----
-        if (k + 1 < nOps) op_load<FWD>(recN, Lv, xs, CS, c, v);
+        const unsigned xaCur = xa;
+        // ---- the first-stage values are dead: reload them for the next op; the loads complete behind
+        //      the diagonal chain below ----
+        if (k + 1 < nOps) SUB_LOAD_MID(recN);
         // ---- stage 2: diagonal block ----
         if (kind != OP_PULL) {
             double r0, r1, r2;
@@ -447,14 +505,46 @@ __device__ __noinline__ void substitute(const int2 *__restrict__ ops, const int 
                 r1 = fma(-l21, r2, t1);
                 r0 = fma(-l10, r1, fma(-l20, r2, t0));
             }
-            double *x = xs + (size_t)(3 * blk) * CS + c;
-            x[0] = r0;
-            x[CS] = r1;
-            x[2 * CS] = r2;
+            sts_f64(xaCur, r0);
+            sts_f64(xaCur + CS8, r1);
+            sts_f64(xaCur + 2u * CS8, r2);
             h0 = r0; h1 = r1; h2 = r2;
         }
         rec = recN;
         recN = recNN;
+    }
+#undef SUB_LOAD_MID
+}
+
+__device__ __forceinline__ void beam_forces_rigid(const BeamCoef &cf, const double gc, const double gs, const double *u,
+                                                  double *o)
+{ // rigid ends: the matrix has five distinct values (feBeam2d.go:28-56)
+    const double z0 = fma(gs, u[1], gc * u[0]), z1 = fma(gc, u[1], -gs * u[0]), z2 = u[2];
+    const double z3 = fma(gs, u[4], gc * u[3]), z4 = fma(gc, u[4], -gs * u[3]), z5 = u[5];
+    const double ax = cf.EFL * (z0 - z3);
+    const double sh = fma(cf.EJL2, z2 + z5, cf.EJL3 * (z1 - z4));
+    const double m0 = fma(cf.EJL, z5, fma(cf.EJL4, z2, cf.EJL2 * (z1 - z4)));
+    const double m1 = fma(cf.EJL4, z5, fma(cf.EJL, z2, cf.EJL2 * (z1 - z4)));
+    o[0] = ax; o[1] = sh; o[2] = m0; o[3] = -ax; o[4] = -sh; o[5] = m1;
+}
+
+__device__ __noinline__ void beam_forces_pinned(const BeamCoef &cf, const uint32_t pm, const double gc, const double gs,
+                                                const double *u, double *o)
+{ // released ends: the condensed matrix is dense
+    double k[36], z[6];
+    stiff_beam2d(cf, pm, k);
+    z[0] = fma(gs, u[1], gc * u[0]);
+    z[1] = fma(gc, u[1], -gs * u[0]);
+    z[2] = u[2];
+    z[3] = fma(gs, u[4], gc * u[3]);
+    z[4] = fma(gc, u[4], -gs * u[3]);
+    z[5] = u[5];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double acc = k[i * 6] * z[0];
+#pragma unroll
+        for (int l = 1; l < 6; l++) acc = fma(k[i * 6 + l], z[l], acc);
+        o[i] = acc;
     }
 }
 
@@ -466,8 +556,13 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
     const int tid = threadIdx.x, NT = blockDim.x;
     const int dof = T.dof, nB = T.nB;
     const int CS = cfg.cs;
-    double *Lv = smem_d + LV_PAD;                 // [-LV_PAD, nSlots + LV_PAD) factor of this model
-    double *xs = smem_d + T.nSlots + 2 * LV_PAD;  // [nPad][CS]
+    // Shared memory is addressed through 32-bit shared-window addresses and explicit ld/st.shared: generic
+    // pointers into dynamic shared memory make the compiler re-derive the window base (S2R SR_CgaCtaId, an
+    // XU-pipe instruction) inside every loop, which saturated the XU pipe in the first version of this kernel.
+    const unsigned smA = (unsigned)__cvta_generic_to_shared(smem_d);
+    const unsigned lvA = smA + LV_PAD * 8u;                       // [-LV_PAD, nSlots + LV_PAD) factor of this model
+    const unsigned xsA = smA + (unsigned)(T.nSlots + 2 * LV_PAD) * 8u; // [nPad][CS]
+    const unsigned CS8 = (unsigned)CS * 8u;
 
     if (tid == 0) {
         s_failCase = 0x7fffffff;
@@ -475,8 +570,9 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
     }
 #define STAMP(i)                                                                              \
     do {                                                                                      \
-        if (L.dbgClocks && tid == 0) L.dbgClocks[(size_t)model * 8 + (i)] = clock64();        \
+        if (L.dbgClocks && tid == stampTid) L.dbgClocks[(size_t)model * 8 + (i)] = clock64();  \
     } while (0)
+    const int stampTid = (((int)blockIdx.x / (cfg.nSM > 0 ? cfg.nSM : 148)) & 3) * 32;
     STAMP(0);
     // phase 0: factor of this model -> shared memory (strided gather from the interleaved workspace);
     // eight independent loads in flight per thread
@@ -493,102 +589,125 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int s = s0 + u * NT + tid;
-                if (s < T.nSlots) Lv[s] = v[u];
+                if (s < T.nSlots) sts_f64(lvA + (unsigned)s * 8u, v[u]);
             }
         }
-        for (int s = tid; s < LV_PAD; s += NT) Lv[T.nSlots + s] = Lv[s - LV_PAD] = 0.0;
+        for (int s = tid; s < LV_PAD; s += NT) {
+            sts_f64(lvA + (unsigned)(T.nSlots + s) * 8u, 0.0);
+            sts_f64(lvA - (unsigned)(LV_PAD - s) * 8u, 0.0);
+        }
     }
     const double *ksf = L.Ksf + (size_t)model * T.nnzR;
+    int nSM = cfg.nSM > 0 ? cfg.nSM : 148;
+    const int solver = ((blockIdx.x / nSM) & 3) * 32; // co-resident CTAs put their solver warp on different SMSPs
+    // DOF ownership: a thread owns up to four DOFs; the index maps are read once
+    int xr[4], si[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int g = tid + u * NT;
+        xr[u] = g < dof ? __ldg(T.xrow + g) : -1;
+        si[u] = g < dof ? __ldg(T.supIndex + g) : -1;
+    }
+    const int gStep = NT * 4;
 
     for (int c0 = 0; c0 < L.nLC; c0 += cfg.casesPerPass) {
         const int nc = min(cfg.casesPerPass, L.nLC - c0);
         const double *p = L.loads + ((size_t)model * L.nLC + c0) * dof;
+        double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof : nullptr;
         // phase 1: load cases -> xs (free rows), dummy rows = 0; model.go:692-696 and 424-437 checks.
-        // A thread owns up to four DOFs (index maps read once) and streams the cases two at a time:
-        // eight independent coalesced loads in flight.
-        for (int g0 = 0; g0 < dof; g0 += NT * 4) {
-            int xr[4];
-            bool in[4];
+        // Cases stream four at a time: sixteen independent coalesced loads in flight per thread.  The
+        // reaction output starts here as -p on supported DOFs (model.go:478) and 0 elsewhere; phase 3 adds
+        // K[r,:] d to it with one fire-and-forget reduction per entry, so p is never read twice.
+        for (int g0 = 0; g0 < dof; g0 += gStep) {
+            if (g0 > 0) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int g = g0 + u * NT + tid;
-                in[u] = g < dof;
-                xr[u] = in[u] ? __ldg(T.xrow + g) : -1;
+                for (int u = 0; u < 4; u++) {
+                    const int g = g0 + tid + u * NT;
+                    xr[u] = g < dof ? __ldg(T.xrow + g) : -1;
+                    si[u] = g < dof ? __ldg(T.supIndex + g) : -1;
+                }
             }
-            for (int c = 0; c < nc; c += 2) {
-                double v[2][4];
+            for (int c = 0; c < nc; c += 4) {
+                double v[4][4];
 #pragma unroll
-                for (int j = 0; j < 2; j++)
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        v[j][u] = (in[u] && c + j < nc) ? p[(size_t)(c + j) * dof + g0 + u * NT + tid] : 0.0;
-#pragma unroll
-                for (int j = 0; j < 2; j++)
+                for (int j = 0; j < 4; j++)
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        if (!(in[u] && c + j < nc)) continue;
+                        const int g = g0 + tid + u * NT;
+                        v[j][u] = (g < dof && c + j < nc) ? p[(size_t)(c + j) * dof + g] : 0.0;
+                    }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int g = g0 + tid + u * NT;
+                        if (!(g < dof && c + j < nc)) continue;
                         const double val = v[j][u];
                         if (!isfinite(val)) atomicMax(&s_flag, 1);
-                        if (xr[u] >= 0) xs[xr[u] * CS + c + j] = val;
+                        if (xr[u] >= 0) sts_f64(xsA + (unsigned)xr[u] * CS8 + (unsigned)(c + j) * 8u, val);
                         else if (xr[u] == -2 && val != 0.0) atomicMin(&s_failCase, c0 + c + j);
+                        if (orr) orr[(size_t)(c + j) * dof + g] = si[u] >= 0 ? -val : 0.0;
                     }
             }
         }
         for (int idx = tid; idx < T.nDummy * nc; idx += NT) {
             const int q = idx / nc, c = idx - q * nc;
-            xs[__ldg(T.dummyPos + q) * CS + c] = 0.0;
+            sts_f64(xsA + (unsigned)__ldg(T.dummyPos + q) * CS8 + (unsigned)c * 8u, 0.0);
         }
         __syncthreads();
         STAMP(1);
 
         // phase 2: L z = p, then L^T x = D^-1 z; one lane per load case walks the block op lists
-        if (tid < nc) {
-            substitute<true>(T.fwdOps, T.nFwdOps, Lv, xs, CS, tid);
+        if (tid >= solver && tid < solver + nc) {
+            substitute<true>(T.fwdOps, T.nFwdOps, lvA, xsA, CS, tid - solver);
             STAMP(2);
-            substitute<false>(T.bwdOps, T.nBwdOps, Lv, xs, CS, tid);
+            substitute<false>(T.bwdOps, T.nBwdOps, lvA, xsA, CS, tid - solver);
         }
         STAMP(3);
         __syncthreads();
         STAMP(4);
 
-        // phase 3a+b: displacements (model.go:446-451) and reactions (model.go:470-489: columns ascending,
-        // eliminated columns carry d = 0).  Same DOF ownership as phase 1; cases in groups of four.
-        if (L.disp || L.react) {
-            double *od = L.disp ? L.disp + ((size_t)model * L.nLC + c0) * dof : nullptr;
-            double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof : nullptr;
-            for (int g0 = 0; g0 < dof; g0 += NT * 4) {
+        // phase 3a+b: displacements (model.go:446-451), written row by row (a case row is one contiguous
+        // run for the whole CTA), and reactions (model.go:470-489: columns ascending, eliminated columns
+        // carry d = 0) added to the -p rows of phase 1 with one reduction per supported entry.
+        for (int g0 = 0; g0 < dof; g0 += gStep) {
+            if (gStep < dof) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    const int g = g0 + u * NT + tid;
-                    if (g >= dof) continue;
-                    const int xr = __ldg(T.xrow + g);
-                    const int si = orr ? __ldg(T.supIndex + g) : -1;
-                    int q0 = 0, q1 = 0;
-                    if (si >= 0) {
-                        q0 = __ldg(T.rptr + si);
-                        q1 = __ldg(T.rptr + si + 1);
-                    }
+                    const int g = g0 + tid + u * NT;
+                    xr[u] = g < dof ? __ldg(T.xrow + g) : -1;
+                    si[u] = g < dof ? __ldg(T.supIndex + g) : -1;
+                }
+            }
+            if (L.disp) {
+                double *od = L.disp + ((size_t)model * L.nLC + c0) * dof + g0 + tid;
+                for (int c = 0; c < nc; c++) {
+                    double d[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) d[u] = xr[u] >= 0 ? lds_f64(xsA + (unsigned)xr[u] * CS8 + (unsigned)c * 8u) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (g0 + tid + u * NT < dof) od[(size_t)c * dof + u * NT] = d[u];
+                }
+            }
+            if (orr) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (si[u] < 0) continue;
+                    const int g = g0 + tid + u * NT;
+                    const int q0 = __ldg(T.rptr + si[u]), q1 = __ldg(T.rptr + si[u] + 1);
                     for (int c = 0; c < nc; c += 4) {
-                        double acc[4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[j] = (si >= 0 && c + j < nc) ? -p[(size_t)(c + j) * dof + g] : 0.0;
-                        if (od) {
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if (c + j < nc) od[(size_t)(c + j) * dof + g] = xr >= 0 ? xs[xr * CS + c + j] : 0.0;
-                        }
-                        if (orr) {
-                            for (int q = q0; q < q1; q++) {
-                                const double kv = __ldg(ksf + q);
-                                const double *xc = xs + __ldg(T.rcol + q) * CS + c;
-#pragma unroll
-                                for (int j = 0; j < 4; j++)
-                                    if (c + j < nc) acc[j] = fma(kv, xc[j], acc[j]);
-                            }
+                        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                        for (int q = q0; q < q1; q++) {
+                            const double kv = __ldg(ksf + q);
+                            const unsigned xa = xsA + (unsigned)__ldg(T.rcol + q) * CS8 + (unsigned)c * 8u;
 #pragma unroll
                             for (int j = 0; j < 4; j++)
-                                if (c + j < nc) orr[(size_t)(c + j) * dof + g] = acc[j];
+                                if (c + j < nc) acc[j] = fma(kv, lds_f64(xa + 8u * j), acc[j]);
                         }
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (c + j < nc) atomicAdd(orr + (size_t)(c + j) * dof + g, acc[j]); // RED: no return value
                     }
                 }
             }
@@ -608,51 +727,36 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
                 const BeamGeom g = beam_geom(T, b);
                 const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
                 const uint32_t pm = T.pinMask[b];
-                int rows[6];
+                unsigned ra[6];
+                bool rv[6];
 #pragma unroll
-                for (int e = 0; e < 6; e++) rows[e] = __ldg(T.beamRows + b * 6 + e);
-                if (pm == 0) { // rigid ends: the matrix has five distinct values (feBeam2d.go:28-56)
-                    for (int c = cBeg; c < cEnd; c++) {
-                        double u[6];
+                for (int e = 0; e < 6; e++) {
+                    const int r = __ldg(T.beamRows + b * 6 + e);
+                    rv[e] = r >= 0;
+                    ra[e] = xsA + (unsigned)(r >= 0 ? r : 0) * CS8;
+                }
+                for (int c = cBeg; c < cEnd; c++) {
+                    double u[6], o[6];
 #pragma unroll
-                        for (int e = 0; e < 6; e++) u[e] = rows[e] >= 0 ? xs[rows[e] * CS + c] : 0.0;
-                        const double z0 = fma(g.s, u[1], g.c * u[0]), z1 = fma(g.c, u[1], -g.s * u[0]), z2 = u[2];
-                        const double z3 = fma(g.s, u[4], g.c * u[3]), z4 = fma(g.c, u[4], -g.s * u[3]), z5 = u[5];
-                        const double ax = cf.EFL * (z0 - z3);
-                        const double sh = fma(cf.EJL2, z2 + z5, cf.EJL3 * (z1 - z4));
-                        const double m0 = fma(cf.EJL, z5, fma(cf.EJL4, z2, cf.EJL2 * (z1 - z4)));
-                        const double m1 = fma(cf.EJL4, z5, fma(cf.EJL, z2, cf.EJL2 * (z1 - z4)));
-                        double *of = out + ((size_t)c * nB + b) * 6;
-                        if (vec16) { // 48-byte records: 16-byte aligned whenever the base pointer is
-                            double2 *o = reinterpret_cast<double2 *>(of);
-                            o[0] = make_double2(ax, sh);
-                            o[1] = make_double2(m0, -ax);
-                            o[2] = make_double2(-sh, m1);
-                        } else {
-                            of[0] = ax; of[1] = sh; of[2] = m0; of[3] = -ax; of[4] = -sh; of[5] = m1;
-                        }
+                    for (int e = 0; e < 6; e++) u[e] = rv[e] ? lds_f64(ra[e] + (unsigned)c * 8u) : 0.0;
+                    if (pm == 0) beam_forces_rigid(cf, g.c, g.s, u, o);
+                    else { // keep u/o of the common path in registers: the out-of-line call gets its own copies
+                        double uu[6], oo[6];
+#pragma unroll
+                        for (int e = 0; e < 6; e++) uu[e] = u[e];
+                        beam_forces_pinned(cf, pm, g.c, g.s, uu, oo);
+#pragma unroll
+                        for (int e = 0; e < 6; e++) o[e] = oo[e];
                     }
-                } else { // released ends: the condensed matrix is dense
-                    double k[36];
-                    stiff_beam2d(cf, pm, k);
-                    for (int c = cBeg; c < cEnd; c++) {
-                        double u[6], z[6];
+                    double *of = out + ((size_t)c * nB + b) * 6;
+                    if (vec16) { // 48-byte records: 16-byte aligned whenever the base pointer is
+                        double2 *o2 = reinterpret_cast<double2 *>(of);
+                        o2[0] = make_double2(o[0], o[1]);
+                        o2[1] = make_double2(o[2], o[3]);
+                        o2[2] = make_double2(o[4], o[5]);
+                    } else {
 #pragma unroll
-                        for (int e = 0; e < 6; e++) u[e] = rows[e] >= 0 ? xs[rows[e] * CS + c] : 0.0;
-                        z[0] = fma(g.s, u[1], g.c * u[0]);
-                        z[1] = fma(g.c, u[1], -g.s * u[0]);
-                        z[2] = u[2];
-                        z[3] = fma(g.s, u[4], g.c * u[3]);
-                        z[4] = fma(g.c, u[4], -g.s * u[3]);
-                        z[5] = u[5];
-                        double *o = out + ((size_t)c * nB + b) * 6;
-#pragma unroll
-                        for (int i = 0; i < 6; i++) {
-                            double acc = k[i * 6] * z[0];
-#pragma unroll
-                            for (int l = 1; l < 6; l++) acc = fma(k[i * 6 + l], z[l], acc);
-                            o[i] = acc;
-                        }
+                        for (int e = 0; e < 6; e++) of[e] = o[e];
                     }
                 }
             }
@@ -669,23 +773,362 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_solve_recover_tma: same pipeline, rows moved by the TMA unit (cp.async.bulk + mbarrier).
+//
+// A model's load block [nLC][dof] and its outputs are long contiguous rows, so every row crosses the
+// SM boundary as ONE bulk asynchronous copy: four load rows are always in flight into a shared-memory
+// ring without costing a register or an issue slot per element, results are staged row by row in the
+// same ring and leave with one bulk store each.  Preconditions (checked at launch, else the LDG/STG
+// kernel above runs): dof even and 16-byte aligned arrays (bulk copies move multiples of 16 bytes),
+// nB < 2 * blockDim (one beam per thread in registers, the rest through a small coefficient table).
+// ------------------------------------------------------------------------------------------------
+constexpr int TMA_DROWS = 4; // ring depth for rows of dof doubles (loads in, displacements out)
+constexpr int TMA_FROWS = 2; // ring depth for rows of nB*6 doubles (beam forces out)
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct TmaCfg {
+    int casesPerPass, cs;
+    int ringDoubles; // ring size in doubles: max(TMA_DROWS * dof, TMA_FROWS * nB * 6)
+    int nSM;
+};
+
+__global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover_tma(const DevTopo T, const StaticLaunch L, const TmaCfg cfg)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    __shared__ int s_failCase, s_flag;
+    __shared__ __align__(8) unsigned long long s_bar[TMA_DROWS];
+    const int model = blockIdx.x;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int dof = T.dof, nB = T.nB;
+    const int CS = cfg.cs;
+    double *Lv = smem_d + LV_PAD;                // [-LV_PAD, nSlots + LV_PAD) factor of this model
+    double *xs = smem_d + T.nSlots + 2 * LV_PAD; // [nPad][CS]
+    double *ring = xs + (((size_t)T.nPad * CS + 1) & ~(size_t)1); // 16-byte aligned
+    double *coefRest = ring + cfg.ringDoubles;   // [nRest][8] coefficients of the beams beyond blockDim
+    const unsigned ringA = (unsigned)__cvta_generic_to_shared(ring);
+    const unsigned barA = (unsigned)__cvta_generic_to_shared(s_bar);
+    const unsigned rowDB = (unsigned)dof * 8u, rowFB = (unsigned)nB * 48u;
+
+    if (tid == 0) {
+        s_failCase = 0x7fffffff;
+        s_flag = 0;
+        for (int i = 0; i < TMA_DROWS; i++) mbar_init(barA + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int stampTid = (((int)blockIdx.x / cfg.nSM) & 3) * 32;
+    STAMP(0);
+    // phase 0: factor of this model -> shared memory (strided gather from the interleaved workspace)
+    {
+        const double *w = L.W + model;
+        const size_t ld = (size_t)L.ld;
+        for (int s0 = 0; s0 < T.nSlots; s0 += NT * 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * NT + tid;
+                v[u] = s < T.nSlots ? w[(size_t)s * ld] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int s = s0 + u * NT + tid;
+                if (s < T.nSlots) Lv[s] = v[u];
+            }
+        }
+        for (int s = tid; s < LV_PAD; s += NT) Lv[T.nSlots + s] = Lv[s - LV_PAD] = 0.0;
+    }
+    const double *ksf = L.Ksf + (size_t)model * T.nnzR;
+    // per-thread DOF ownership (up to four DOFs) and beam ownership (one beam in registers)
+    int xr[4], si[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int g = tid + u * NT;
+        xr[u] = g < dof ? __ldg(T.xrow + g) : -1;
+        si[u] = g < dof ? __ldg(T.supIndex + g) : -1;
+    }
+    const double *sec = L.sections + (size_t)model * nB * 3;
+    const bool haveBeam = tid < nB;
+    BeamCoef cfB{};
+    double gcB = 0, gsB = 0;
+    uint32_t pmB = 0;
+    int rowsB[6] = {-1, -1, -1, -1, -1, -1};
+    if (haveBeam && L.forces) {
+        const BeamGeom g = beam_geom(T, tid);
+        cfB = beam_coef(sec[3 * tid], sec[3 * tid + 1], sec[3 * tid + 2], g.length);
+        gcB = g.c;
+        gsB = g.s;
+        pmB = T.pinMask[tid];
+#pragma unroll
+        for (int e = 0; e < 6; e++) rowsB[e] = __ldg(T.beamRows + tid * 6 + e);
+    }
+    const int nRest = nB > NT ? nB - NT : 0;
+    if (tid < nRest && L.forces) {
+        const int b = NT + tid;
+        const BeamGeom g = beam_geom(T, b);
+        const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
+        double *cr = coefRest + tid * 8;
+        cr[0] = cf.EFL; cr[1] = cf.EJL3; cr[2] = cf.EJL2; cr[3] = cf.EJL; cr[4] = cf.EJL4; cr[5] = g.c; cr[6] = g.s;
+    }
+    __syncthreads(); // barriers initialised, factor and coefficient table in place
+    const int solver = ((blockIdx.x / cfg.nSM) & 3) * 32; // co-resident CTAs put their solver warp on different SMSPs
+    unsigned rowsDone = 0; // rows that went through the load ring so far (mbarrier phase bookkeeping)
+
+    for (int c0 = 0; c0 < L.nLC; c0 += cfg.casesPerPass) {
+        const int nc = min(cfg.casesPerPass, L.nLC - c0);
+        const double *p = L.loads + ((size_t)model * L.nLC + c0) * dof;
+        double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof : nullptr;
+        // ---- phase 1: load rows through the ring -> xs; reaction rows start as -p (model.go:478) ----
+        if (tid == 0) {
+            for (int c = 0; c < min(TMA_DROWS, nc); c++) {
+                const unsigned s = (rowsDone + c) % TMA_DROWS;
+                mbar_expect_tx(barA + 8u * s, rowDB);
+                bulk_g2s(ringA + s * rowDB, p + (size_t)c * dof, rowDB, barA + 8u * s);
+            }
+        }
+        for (int c = 0; c < nc; c++) {
+            const unsigned rd = rowsDone + c, s = rd % TMA_DROWS;
+            mbar_wait(barA + 8u * s, (rd / TMA_DROWS) & 1u);
+            double *row = ring + (size_t)s * dof;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int g = tid + u * NT;
+                if (g >= dof) continue;
+                const double val = row[g];
+                if (!isfinite(val)) atomicMax(&s_flag, 1); // model.go:692-696
+                if (xr[u] >= 0) xs[xr[u] * CS + c] = val;
+                else if (xr[u] == -2 && val != 0.0) atomicMin(&s_failCase, c0 + c); // model.go:424-437
+                if (orr) row[g] = si[u] >= 0 ? -val : 0.0;
+            }
+            if (orr) fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                if (orr) {
+                    bulk_s2g(orr + (size_t)c * dof, ringA + s * rowDB, rowDB);
+                    bulk_commit();
+                }
+                if (c + TMA_DROWS < nc) { // refill this stage once the store has read it
+                    if (orr) bulk_wait_read<0>();
+                    mbar_expect_tx(barA + 8u * s, rowDB);
+                    bulk_g2s(ringA + s * rowDB, p + (size_t)(c + TMA_DROWS) * dof, rowDB, barA + 8u * s);
+                }
+            }
+        }
+        rowsDone += nc;
+        for (int idx = tid; idx < T.nDummy * nc; idx += NT) {
+            const int q = idx / nc, c = idx - q * nc;
+            xs[__ldg(T.dummyPos + q) * CS + c] = 0.0;
+        }
+        if (tid == 0 && orr) bulk_wait<0>(); // the -p rows are in memory before phase 3 adds to them
+        __syncthreads();
+        STAMP(1);
+
+        // ---- phase 2: L z = p, then L^T x = D^-1 z; one lane per load case walks the block op lists ----
+        if (tid >= solver && tid < solver + nc) {
+            substitute<true>(T.fwdOps, T.nFwdOps, (unsigned)__cvta_generic_to_shared(Lv), (unsigned)__cvta_generic_to_shared(xs), CS, tid - solver);
+            substitute<false>(T.bwdOps, T.nBwdOps, (unsigned)__cvta_generic_to_shared(Lv), (unsigned)__cvta_generic_to_shared(xs), CS, tid - solver);
+        }
+        STAMP(3);
+        __syncthreads();
+        STAMP(4);
+
+        // ---- phase 3a: reactions, model.go:470-489: one fire-and-forget reduction per supported entry ----
+        if (orr) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (si[u] < 0) continue;
+                const int g = tid + u * NT;
+                const int q0 = __ldg(T.rptr + si[u]), q1 = __ldg(T.rptr + si[u] + 1);
+                for (int c = 0; c < nc; c += 4) {
+                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                    for (int q = q0; q < q1; q++) {
+                        const double kv = __ldg(ksf + q);
+                        const double *xc = xs + __ldg(T.rcol + q) * CS + c;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (c + j < nc) acc[j] = fma(kv, xc[j], acc[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (c + j < nc) atomicAdd(orr + (size_t)(c + j) * dof + g, acc[j]); // RED: no return value
+                }
+            }
+        }
+        // ---- phase 3b: displacements (model.go:446-451), one bulk store per case row ----
+        if (L.disp) {
+            double *od = L.disp + ((size_t)model * L.nLC + c0) * dof;
+            for (int c = 0; c < nc; c++) {
+                const int s = c % TMA_DROWS;
+                if (tid == 0 && c >= TMA_DROWS) bulk_wait_read<TMA_DROWS - 1>();
+                __syncthreads();
+                double *row = ring + (size_t)s * dof;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int g = tid + u * NT;
+                    if (g < dof) row[g] = xr[u] >= 0 ? xs[xr[u] * CS + c] : 0.0;
+                }
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    bulk_s2g(od + (size_t)c * dof, ringA + s * rowDB, rowDB);
+                    bulk_commit();
+                }
+            }
+            if (tid == 0) bulk_wait_read<0>(); // the ring changes row size below
+        }
+        // ---- phase 3c: beam end forces s = k (T Zo), model.go:455-468; one bulk store per case row ----
+        if (L.forces) {
+            double *of = L.forces + ((size_t)model * L.nLC + c0) * nB * 6;
+            for (int c = 0; c < nc; c++) {
+                const int s = c % TMA_FROWS;
+                if (tid == 0 && c >= TMA_FROWS) bulk_wait_read<TMA_FROWS - 1>();
+                __syncthreads();
+                double *row = ring + (size_t)s * nB * 6;
+                if (haveBeam) {
+                    double u[6];
+#pragma unroll
+                    for (int e = 0; e < 6; e++) u[e] = rowsB[e] >= 0 ? xs[rowsB[e] * CS + c] : 0.0;
+                    double o[6];
+                    if (pmB == 0) beam_forces_rigid(cfB, gcB, gsB, u, o);
+                    else {
+                        double uu[6], oo[6];
+#pragma unroll
+                        for (int e = 0; e < 6; e++) uu[e] = u[e];
+                        beam_forces_pinned(cfB, pmB, gcB, gsB, uu, oo);
+#pragma unroll
+                        for (int e = 0; e < 6; e++) o[e] = oo[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 6; e++) row[tid * 6 + e] = o[e];
+                }
+                if (tid < nRest) {
+                    const int b = NT + tid;
+                    const double *cr = coefRest + tid * 8;
+                    BeamCoef cf;
+                    cf.EFL = cr[0]; cf.EJL3 = cr[1]; cf.EJL2 = cr[2]; cf.EJL = cr[3]; cf.EJL4 = cr[4];
+                    double u[6];
+#pragma unroll
+                    for (int e = 0; e < 6; e++) {
+                        const int r = __ldg(T.beamRows + b * 6 + e);
+                        u[e] = r >= 0 ? xs[r * CS + c] : 0.0;
+                    }
+                    const uint32_t pm = T.pinMask[b];
+                    double o[6];
+                    if (pm == 0) beam_forces_rigid(cf, cr[5], cr[6], u, o);
+                    else {
+                        double uu[6], oo[6];
+#pragma unroll
+                        for (int e = 0; e < 6; e++) uu[e] = u[e];
+                        beam_forces_pinned(cf, pm, cr[5], cr[6], uu, oo);
+#pragma unroll
+                        for (int e = 0; e < 6; e++) o[e] = oo[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 6; e++) row[b * 6 + e] = o[e];
+                }
+                fence_proxy_async();
+                __syncthreads();
+                if (tid == 0) {
+                    bulk_s2g(of + (size_t)c * nB * 6, ringA + (unsigned)s * rowFB, rowFB);
+                    bulk_commit();
+                }
+            }
+        }
+        if (tid == 0) bulk_wait_read<0>(); // ring and xs are reused by the next pass
+        __syncthreads();
+        STAMP(5);
+    }
+    if (tid == 0) {
+        bulk_wait<0>();
+        int st = L.status[model];
+        if (st == HDB_STATUS_OK && s_flag) st = HDB_STATUS_NONFINITE;
+        if (st == HDB_STATUS_OK && s_failCase != 0x7fffffff) st = HDB_STATUS_IGNORE_LOAD;
+        L.status[model] = st;
+        if (L.failCase) L.failCase[model] = (s_failCase != 0x7fffffff) ? s_failCase : -1;
+    }
+}
+
+static bool tma_eligible(const DevTopo &T, const StaticLaunch &L, int threads)
+{
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (T.dof % 2 != 0 || T.dof > 4 * threads || T.nB >= 2 * threads) return false;
+    if (!al16(L.loads) || !al16(L.disp) || !al16(L.forces) || !al16(L.react)) return false;
+    return true;
+}
+
 cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaStream_t st)
 {
-    int dev = 0, optin = 0;
+    int dev = 0, optin = 0, nSM = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
     SolveCfg cfg;
     size_t smem = 0;
     if (!solve_config(T, L.nLC, optin, cfg.casesPerPass, smem)) return cudaErrorInvalidConfiguration;
     cfg.cs = odd_stride(cfg.casesPerPass);
+    cfg.nSM = nSM;
+    // one thread per beam in the force phase when the model is small enough, whole warps
+    int threads = ((T.nB + 31) / 32) * 32;
+    if (threads < 128) threads = 128;
+    if (threads > SOL_MAX_THREADS) threads = SOL_MAX_THREADS;
+    static const bool useTma = std::getenv("HDB_USE_TMA") != nullptr; // experimental: slower than the LDG/STG kernel so far
+    if (useTma && tma_eligible(T, L, threads)) {
+        TmaCfg tc;
+        tc.casesPerPass = cfg.casesPerPass;
+        tc.cs = cfg.cs;
+        tc.nSM = nSM;
+        const size_t ring = std::max<size_t>((size_t)TMA_DROWS * T.dof, (size_t)TMA_FROWS * T.nB * 6);
+        tc.ringDoubles = (int)((ring + 1) & ~(size_t)1);
+        const int nRest = T.nB > threads ? T.nB - threads : 0;
+        const size_t xsD = (((size_t)T.nPad * cfg.cs + 1) & ~(size_t)1);
+        const size_t bytes = ((size_t)(T.nSlots + 2 * LV_PAD) + xsD + tc.ringDoubles + (size_t)nRest * 8) * sizeof(double);
+        if (bytes + 2048 <= (size_t)optin) {
+            if (bytes > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(k_solve_recover_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+                if (e != cudaSuccess) return e;
+            }
+            k_solve_recover_tma<<<L.nModels, threads, bytes, st>>>(T, L, tc);
+            return cudaGetLastError();
+        }
+    }
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_solve_recover, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    // one thread per beam in the force phase when the model is small enough, whole warps
-    int threads = ((T.nB + 31) / 32) * 32;
-    if (threads < 128) threads = 128;
-    if (threads > SOL_MAX_THREADS) threads = 256;
     k_solve_recover<<<L.nModels, threads, smem, st>>>(T, L, cfg);
     return cudaGetLastError();
 }
