@@ -74,8 +74,9 @@ struct hdb_topology {
     std::vector<cudaEvent_t> events;
     std::vector<int> evKind; // kernel kind of interval [2i, 2i+1]
     int lastKinds = 0;
-    // modal
-    ModalState *modal = nullptr;
+    // modal scratch (unit loads, their solutions, mass tables)
+    void *modalBuf = nullptr;
+    size_t modalBytes = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -336,7 +337,7 @@ void hdb_topology_destroy(hdb_topology *t)
         for (cudaStream_t st : {t->sIn, t->sK, t->sOut})
             if (st) cudaStreamDestroy(st);
         for (cudaEvent_t e : t->events) cudaEventDestroy(e);
-        modal_state_free(t->modal);
+        if (t->modalBuf) cudaFree(t->modalBuf);
     }
     delete t;
 }
@@ -777,34 +778,110 @@ int hdb_element_batch(hdb_topology *t, int32_t nModels, const double *sections, 
 int hdb_modal_mode_count(const hdb_topology *t, int32_t nMass, const int64_t *massN)
 {
     if (!t || nMass < 0 || (nMass > 0 && !massN)) return HDB_ERR_ARG;
-    std::vector<int32_t> rows;
-    return modal_mass_rows(t->S, nMass, massN, rows, nullptr);
+    std::vector<int32_t> dofs;
+    return modal_mass_rows(t->S, nMass, massN, dofs, nullptr);
 }
 
 int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nMass, const int64_t *massN,
                         const double *mass, int32_t maxModes, int32_t *nModes, double *hz, double *shapes,
                         int32_t *status, void *stream)
 {
-    if (!t || nModels < 0 || !sections || nMass < 0 || (nMass > 0 && (!massN || !mass)) || !nModes || !hz || !status)
+    if (!t || nModels < 0 || !sections || nMass < 0 || (nMass > 0 && (!massN || !mass)) || !nModes || !hz || !status ||
+        maxModes < 0)
         return HDB_ERR_ARG;
     int rc = ensure_device(t);
     if (rc != HDB_OK) return rc;
     if (nModels == 0) return HDB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
     prof_reset(t);
-    const int sb = std::min<int>(nModels, t->subBatch);
-    rc = ensure_workspace(t, (size_t)sb);
-    if (rc != HDB_OK) return rc;
-    ModalArgs A{};
-    A.nModels = nModels; A.sections = sections; A.nMass = nMass; A.massN = massN; A.mass = mass;
-    A.maxModes = maxModes; A.nModes = nModes; A.hz = hz; A.shapes = shapes; A.status = status;
-    A.W = t->W; A.Ksf = t->Ksf; A.keScratch = t->keScratch; A.ld = (int)t->wsModels; A.subBatch = sb;
-    A.smemOptin = t->smemOptin;
-    std::string detail;
-    int launches = 0;
-    rc = modal_enqueue(t->S, t->D, &t->modal, A, (cudaStream_t)stream, detail, launches);
-    count_launch(launches);
-    if (rc != HDB_OK) set_error_detail(detail);
-    return rc;
+    const Symbolic &S = t->S;
+    std::vector<int32_t> dofs;
+    std::vector<std::vector<int32_t>> massOf;
+    const int s = modal_mass_rows(S, nMass, massN, dofs, &massOf);
+    if (s < 0) {
+        set_error_detail("hdb_modal_batch: mass point index out of range");
+        return HDB_ERR_INPUT;
+    }
+    if (s == 0) { // empty mass list: H = 0, no results and no error (model.go:772-805)
+        CUDA_TRY(cudaMemsetAsync(nModes, 0, (size_t)nModels * sizeof(int32_t), st));
+        CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)nModels * sizeof(int32_t), st));
+        return HDB_OK;
+    }
+    if (maxModes < s) {
+        set_error_detail("hdb_modal_batch: maxModes is smaller than hdb_modal_mode_count()");
+        return HDB_ERR_SMALL_BUFFER;
+    }
+    if (s > modal_max_s(t->smemOptin)) {
+        set_error_detail("hdb_modal_batch: too many mass DOFs for the shared-memory resident eigen solver");
+        return HDB_ERR_UNSUPPORTED;
+    }
+    // mass-row tables (small; rebuilt per call)
+    std::vector<int32_t> mptr(1, 0), midx;
+    for (auto &l : massOf) {
+        midx.insert(midx.end(), l.begin(), l.end());
+        mptr.push_back((int32_t)midx.size());
+    }
+    const size_t per = (size_t)s * S.dof * sizeof(double);
+    int sbm = (int)std::max<size_t>(1, std::min<size_t>((size_t)nModels, ((size_t)768 << 20) / (2 * per)));
+    sbm = std::min(sbm, t->subBatch);
+    const size_t tabBytes = (dofs.size() + mptr.size() + std::max<size_t>(midx.size(), 1)) * sizeof(int32_t);
+    const size_t need = 2 * per * sbm + (size_t)sbm * s * sizeof(double) + tabBytes + 1024;
+    if (need > t->modalBytes) {
+        if (t->modalBuf) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            cudaFree(t->modalBuf);
+        }
+        t->modalBuf = nullptr;
+        t->modalBytes = 0;
+        CUDA_TRY(cudaMalloc(&t->modalBuf, need));
+        t->modalBytes = need;
+    }
+    char *base = (char *)t->modalBuf;
+    double *unitLoads = (double *)base;
+    double *sol = (double *)(base + per * sbm);
+    double *msqrt = (double *)(base + 2 * per * sbm);
+    int32_t *dMassDof = (int32_t *)(base + 2 * per * sbm + (size_t)sbm * s * sizeof(double));
+    int32_t *dMptr = dMassDof + dofs.size();
+    int32_t *dMidx = dMptr + mptr.size();
+    CUDA_TRY(cudaMemcpyAsync(dMassDof, dofs.data(), dofs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dMptr, mptr.data(), mptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (!midx.empty())
+        CUDA_TRY(cudaMemcpyAsync(dMidx, midx.data(), midx.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st)); // the host vectors above go out of scope
+
+    for (int m0 = 0; m0 < nModels; m0 += sbm) {
+        const int nm = std::min(sbm, nModels - m0);
+        ModalLaunch M{};
+        M.nModels = nm; M.s = s; M.dof = S.dof; M.nMass = nMass;
+        M.massDof = dMassDof; M.mptr = dMptr; M.midx = dMidx;
+        M.mass = mass + (size_t)m0 * nMass;
+        M.msqrt = msqrt; M.unitLoads = unitLoads; M.sol = sol;
+        M.maxModes = maxModes;
+        M.nModes = nModes + m0;
+        M.hz = hz + (size_t)m0 * maxModes;
+        M.shapes = shapes ? shapes + (size_t)m0 * maxModes * S.dof : nullptr;
+        M.status = status + m0;
+        {
+            ProfScope ps(t, KIND_MODAL0, st);
+            CUDA_TRY(launch_modal_loads(M, st));
+        }
+        count_launch(1);
+        // K^-1 applied to the s unit loads of every model: the LinearStatic kernels with s load cases
+        rc = static_enqueue(t, nm, sections + (size_t)m0 * S.nB * 3, s, unitLoads, sol, nullptr, nullptr, status + m0,
+                            nullptr, nullptr, st, true);
+        if (rc != HDB_OK) return rc;
+        {
+            ProfScope ps(t, KIND_MODAL0 + 1, st);
+            cudaError_t e = launch_modal_eigen(M, t->smemOptin, st);
+            if (e == cudaErrorInvalidConfiguration) {
+                set_error_detail("modal eigen kernel does not fit shared memory");
+                return HDB_ERR_UNSUPPORTED;
+            }
+            CUDA_TRY(e);
+        }
+        count_launch(1);
+    }
+    return HDB_OK;
 }
 
 int hdb_modal_batch(hdb_topology *t, int32_t nModels, const double *sections, int32_t nMass, const int64_t *massN,
@@ -816,6 +893,10 @@ int hdb_modal_batch(hdb_topology *t, int32_t nModels, const double *sections, in
     int rc = ensure_device(t);
     if (rc != HDB_OK) return rc;
     if (nModels == 0) return HDB_OK;
+    if (maxModes == 0 && hdb_modal_mode_count(t, nMass, massN) == 0) {
+        for (int i = 0; i < nModels; i++) nModes[i] = status[i] = 0;
+        return HDB_OK;
+    }
     if (is_device_ptr(sections)) {
         rc = hdb_modal_batch_dev(t, nModels, sections, nMass, massN, mass, maxModes, nModes, hz, shapes, status, nullptr);
         if (rc != HDB_OK) return rc;

@@ -10,7 +10,7 @@ namespace hdb {
 
 constexpr int BLK_HDR = 6;        // 1/d (3) + strictly lower part of the diagonal block (3)
 constexpr int BLK_STRIDE = 10;    // 9 values of an off block + 1 pad (keeps every block 16-byte aligned)
-constexpr int FACTOR_PREFETCH = 2; // block columns the factor kernel prefetches ahead
+constexpr int FACTOR_PREFETCH = 6; // block columns the factor kernel prefetches ahead
 
 // Result of the host symbolic phase.  All index arrays are int32 and identical for every model
 // of a batch (same topology, geometry, pins, supports).

@@ -1,4 +1,12 @@
 // modal.hpp — host interface of the batched Modal path (kernels in kernels_modal.cu).
+//
+// Reference: Modal (model.go:719-851) builds H = K^-1 M column by column and takes all eigenpairs of the
+// dense non-symmetric dof x dof H with gonum's Dgeev.  M is diagonal (lumped masses on X and Y of the
+// mass points, model.go:780-789), so the same spectrum comes from the symmetric s x s matrix
+//     B = M_S^1/2 (K_ff^-1)_SS M_S^1/2,   s = number of distinct free mass DOFs,
+// and the shape of mode k is K_ff^-1[:,S] M_S^1/2 y_k (zeros on eliminated DOFs) scaled to unit 2-norm
+// (SURVEY.md A.8).  Per model: s unit-load solves through the LinearStatic kernels, Householder
+// tridiagonalisation + implicit QL in shared memory, one dense FP64 contraction for the shapes.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -11,29 +19,30 @@
 
 namespace hdb {
 
-struct ModalState; // device copies of the mass-DOF lists of the last call, scratch matrices
+// distinct free mass DOFs (X and Y of every mass point that is not eliminated), ascending DOF;
+// rows = their global DOF numbers, massOf (optional) lists for every row the masses that add to it.
+int modal_mass_rows(const Symbolic &S, int nMass, const int64_t *massN, std::vector<int32_t> &dofs,
+                    std::vector<std::vector<int32_t>> *massOf);
 
-struct ModalArgs {
-    int nModels;
-    const double *sections; // device [nModels][nB][3]
-    int nMass;
-    const int64_t *massN;   // host [nMass]
-    const double *mass;     // device [nModels][nMass]
+struct ModalLaunch {
+    int nModels, s, dof, nMass;
+    const int32_t *massDof;   // device [s] global DOF of mass row i
+    const int32_t *mptr;      // device [s+1]
+    const int32_t *midx;      // device [mptr[s]] indices into the mass list
+    const double *mass;       // device [nModels][nMass] (newtons)
+    double *msqrt;            // device [nModels][s] sqrt(sum mass / Gravity)
+    double *unitLoads;        // device [nModels][s][dof]
+    const double *sol;        // device [nModels][s][dof] K^-1 applied to the unit loads (displacement layout)
     int maxModes;
-    int32_t *nModes;        // device [nModels]
-    double *hz;             // device [nModels][maxModes]
-    double *shapes;         // device [nModels][maxModes][dof] or NULL
-    int32_t *status;        // device [nModels]
-    double *W, *Ksf, *keScratch;
-    int ld, subBatch, smemOptin;
+    int32_t *nModes;          // device [nModels]
+    double *hz;               // device [nModels][maxModes]
+    double *shapes;           // device [nModels][maxModes][dof] or NULL
+    int32_t *status;          // device [nModels]
 };
 
-// distinct free mass DOFs (X and Y of every mass point that is not eliminated), as x rows,
-// ascending DOF; massOf (optional) lists for every row the indices of the masses that add to it.
-int modal_mass_rows(const Symbolic &S, int nMass, const int64_t *massN, std::vector<int32_t> &rows,
-                    std::vector<std::vector<int32_t>> *massOf);
-int modal_enqueue(const Symbolic &S, const DevTopo &D, ModalState **state, const ModalArgs &A, cudaStream_t st,
-                  std::string &detail, int &launches);
-void modal_state_free(ModalState *s);
+cudaError_t launch_modal_loads(const ModalLaunch &M, cudaStream_t st);
+// returns cudaErrorInvalidConfiguration when s is too large for the shared-memory resident eigen solver
+cudaError_t launch_modal_eigen(const ModalLaunch &M, int smemOptin, cudaStream_t st);
+int modal_max_s(int smemOptin);
 
 } // namespace hdb
