@@ -121,6 +121,67 @@ def cpu_port(fm, sections, loads, threads, literal=True):
     return dt
 
 
+def modal_main(args, rank, local_rank, world):
+    """Auxiliary line for BASELINE.json config 4: ModalCases on a batch of 1024 uniform_frame(64) models,
+    one modal case each, 130 modes per model (frequencies + shapes). Not the driver's headline metric."""
+    import torch
+    from hd_b200 import _lib, frames
+    from oracle import hd_oracle as oracle
+    N = 64 if args.bays == 128 else args.bays
+    M = 1024 if args.models_per_gpu == 8192 else args.models_per_gpu
+    fm = oracle.flatten_model(frames.uniform_frame(N))
+    sections = frames.uniform_frame_sections(N, rank * M, M)
+    massN, mass = frames.uniform_frame_masses(N, rank * M, M)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    topo = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports, device=local_rank)
+    s = topo.modal_mode_count(massN)
+    d_sec, d_mass = torch.from_numpy(sections).to(dev), torch.from_numpy(mass).to(dev)
+    d_n = torch.zeros((M,), dtype=torch.int32, device=dev)
+    d_hz = torch.zeros((M, s), dtype=torch.float64, device=dev)
+    d_sh = torch.zeros((M, s, fm.nP, 3), dtype=torch.float64, device=dev)
+    d_st = torch.zeros((M,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        topo.modal_batch_dev(M, d_sec, massN, d_mass, s, d_n, d_hz, d_sh, d_st, stream)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum().item()) == 0
+    topo.set_profiling(2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    kms = topo.last_kernel_ms()
+    nFree = topo.info.nFree
+    flops = 4 * nFree * 5 * s + 28 * s ** 3 / 3 + 2 * fm.dof * s * s + 3 * fm.dof * s  # SURVEY.md 8(d)
+    value = M * args.steps / (ms * 1e-3)
+    cpu = None
+    if not args.no_cpu:
+        threads = oracle.max_threads()
+        sample = args.cpu_sample or 2 * threads
+        t0 = time.perf_counter()
+        ost, _, _, _ = oracle.modal_batch(fm, sections[:sample], massN, mass[:sample], n_threads=threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample / dt, "unit": "modal solves/s", "cores": threads, "kind": "port",
+               "sample": f"first {sample} models, dense non-symmetric eigen solve of K^-1 M as the reference does"}
+    if rank == 0:
+        print(json.dumps({"metric": "modal solves/s (130 modes, uniform_frame(64))", "value": value, "unit": "modal solves/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": f"uniform_frame({N}) modal, {M} models per GPU, {s} modes each"},
+                          "kernel_ms_total": dict(zip(["k_assemble", "k_factor", "k_solve_recover", "k_modal_loads", "k_modal_eigen"], kms)),
+                          "fp64": {"algorithmic_mflop_per_solve": flops / 1e6, "achieved_tflops": value * flops / 1e12,
+                                   "peak_tflops": 36.86, "peak_source": "tools/fp64_microbench.cu on this pool's B200",
+                                   "frac": value * flops / 1e12 / 36.86},
+                          "cpu_baseline": cpu}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -131,6 +192,8 @@ def main():
     ap.add_argument("--bays", type=int, default=128)
     ap.add_argument("--cases", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=0, help="models in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--workload", default="static", choices=["static", "modal"],
+                    help="static = the headline LinearStatic batch (default); modal = BASELINE.json config 4 (auxiliary line)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -139,6 +202,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload == "modal":
+        return modal_main(args, rank, local_rank, world)
     N, nLC, M = args.bays, args.cases, args.models_per_gpu
 
     from hd_b200 import frames

@@ -1,0 +1,100 @@
+// Package hdb200 binds libhdb200.so (include/hdb200.h) for the hd package.
+//
+// NOT COMPILED IN THIS REPOSITORY'S IMAGE: there is no Go toolchain here (see DESIGN.md).  This is the
+// binding a maintainer of Konstantin8105/hd adds; it is written against the same header the C++ and
+// Python hosts use.  The reference keeps check.go, the text reports and its exported structs unchanged;
+// only the bodies of LinearStatic (model.go:358-605) and Modal (model.go:719-851) change: prepare/check in
+// Go -> flatten -> ONE cgo call per phase -> results copied into the Go result slices.
+package hdb200
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../hd_b200 -lhdb200 -Wl,-rpath,${SRCDIR}/../../hd_b200
+#include <stdlib.h>
+#include "hdb200.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"runtime"
+	"unsafe"
+)
+
+// Beam mirrors hd.BeamProp (model.go:58-77): identical memory layout, so []hd.BeamProp can be passed
+// to C without copying (all fields are pointer-free).
+type Beam struct {
+	N       [2]int
+	A, J, E float64
+}
+
+// Topology is the handle of the symbolic phase (hdb_topology_create).
+type Topology struct{ h *C.hdb_topology }
+
+func errOf(rc C.int, where string) error {
+	if rc >= 0 {
+		return nil
+	}
+	return fmt.Errorf("%s: %s (%s)", where, C.GoString(C.hdb_error_string(rc)), C.GoString(C.hdb_last_error_detail()))
+}
+
+func b2u(b [][6]bool) *C.uint8_t {
+	if len(b) == 0 {
+		return nil // all rigid, model.go:344-346
+	}
+	return (*C.uint8_t)(unsafe.Pointer(&b[0][0])) // Go bool is one byte, 0 or 1
+}
+
+// NewTopology replaces the structural half of getK / assemblyK (model.go:318-333, 607-681).
+func NewTopology(points [][2]float64, beams []Beam, pins [][6]bool, supports [][3]bool) (*Topology, error) {
+	t := &Topology{}
+	rc := C.hdb_topology_create(C.int32_t(len(points)), (*C.double)(unsafe.Pointer(&points[0][0])),
+		C.int32_t(len(beams)), (*C.hdb_beam)(unsafe.Pointer(&beams[0])), b2u(pins),
+		(*C.uint8_t)(unsafe.Pointer(&supports[0][0])), nil, &t.h)
+	if err := errOf(rc, "hdb_topology_create"); err != nil {
+		return nil, err
+	}
+	runtime.SetFinalizer(t, func(t *Topology) { t.Close() })
+	return t, nil
+}
+
+// Close releases the handle (explicit lifetime; the finalizer is only a safety net).
+func (t *Topology) Close() {
+	if t.h != nil {
+		C.hdb_topology_destroy(t.h)
+		t.h = nil
+	}
+}
+
+// StaticBatch is LinearStatic for nModels models sharing the topology (model.go:401-490).
+// sections [nModels][nB][3], loads [nModels][nLC][dof] (assemblyNodeLoad output); the result slices are
+// written in place: disp/react [nModels][nLC][nP][3], forces [nModels][nLC][nB][6].
+func (t *Topology) StaticBatch(nModels, nLC int, sections, loads, disp, forces, react []float64,
+	status, failCase []int32) error {
+	p := func(s []float64) *C.double {
+		if len(s) == 0 {
+			return nil
+		}
+		return (*C.double)(unsafe.Pointer(&s[0]))
+	}
+	rc := C.hdb_static_batch(t.h, C.int32_t(nModels), p(sections), C.int32_t(nLC), p(loads), p(disp), p(forces),
+		p(react), (*C.int32_t)(unsafe.Pointer(&status[0])), (*C.int32_t)(unsafe.Pointer(&failCase[0])))
+	runtime.KeepAlive(sections)
+	runtime.KeepAlive(loads)
+	return errOf(rc, "hdb_static_batch")
+}
+
+// ModalBatch is Modal for nModels models (model.go:719-851). massN is shared, mass [nModels][len(massN)].
+func (t *Topology) ModalBatch(nModels int, sections []float64, massN []int, mass []float64, maxModes int,
+	nModes []int32, hz, shapes []float64, status []int32) error {
+	rc := C.hdb_modal_batch(t.h, C.int32_t(nModels), (*C.double)(unsafe.Pointer(&sections[0])), C.int32_t(len(massN)),
+		(*C.int64_t)(unsafe.Pointer(&massN[0])), (*C.double)(unsafe.Pointer(&mass[0])), C.int32_t(maxModes),
+		(*C.int32_t)(unsafe.Pointer(&nModes[0])), (*C.double)(unsafe.Pointer(&hz[0])),
+		(*C.double)(unsafe.Pointer(&shapes[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
+	return errOf(rc, "hdb_modal_batch")
+}
+
+// ModeCount = number of distinct free mass DOFs = modes Modal returns.
+func (t *Topology) ModeCount(massN []int) int {
+	return int(C.hdb_modal_mode_count(t.h, C.int32_t(len(massN)), (*C.int64_t)(unsafe.Pointer(&massN[0]))))
+}

@@ -242,12 +242,16 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
                         c3 = c2;
                         c2 = c;
                         s2 = s;
-                        g = c * e[i];
+                        const double ei = e[i];
+                        g = c * ei;
                         h = c * p;
-                        r = hypot(p, e[i]);
+                        // the tridiagonal entries are O(lambda): no overflow / underflow guard needed, and the
+                        // scalar recurrence is the critical path of the whole kernel
+                        r = sqrt(fma(p, p, ei * ei));
+                        const double rinv = 1.0 / r;
                         e[i + 1] = s * r;
-                        s = e[i] / r;
-                        c = p / r;
+                        s = ei * rinv;
+                        c = p * rinv;
                         p = c * d[i] - s * g;
                         d[i + 1] = h + s * (c * g + s * d[i]);
                         cc[i] = c;
