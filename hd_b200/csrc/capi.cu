@@ -61,7 +61,10 @@ struct hdb_topology {
     DevTopo D{};
     std::vector<void *> devAllocs;
     // workspace of the device path
-    double *W = nullptr, *Ksf = nullptr, *keScratch = nullptr;
+    // two workspace sets: the assemble/factor stream prepares sub-batch i+1 while the solve stream works on i
+    double *Wbuf[2] = {nullptr, nullptr}, *Ksfbuf[2] = {nullptr, nullptr}, *keScratch = nullptr;
+    cudaStream_t prepStream = nullptr;
+    cudaEvent_t evFork = nullptr, evPrep[2] = {nullptr, nullptr}, evSolve[2] = {nullptr, nullptr}, evJoin = nullptr;
     long long *dbgClocks = nullptr; // HDB_DEBUG_CLOCKS=1: per-model phase stamps of k_solve_recover
     size_t wsModels = 0;
     int subBatch = 4096;
@@ -189,20 +192,35 @@ static int ensure_device(hdb_topology *t)
 
 static int ensure_workspace(hdb_topology *t, size_t models)
 {
+    if (!t->prepStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&t->prepStream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->evFork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&t->evJoin, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&t->evPrep[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&t->evSolve[i], cudaEventDisableTiming));
+        }
+    }
     if (models <= t->wsModels) return HDB_OK;
-    if (t->W) cudaFree(t->W);
-    if (t->Ksf) cudaFree(t->Ksf);
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; i++) {
+        if (t->Wbuf[i]) cudaFree(t->Wbuf[i]);
+        if (t->Ksfbuf[i]) cudaFree(t->Ksfbuf[i]);
+        t->Wbuf[i] = t->Ksfbuf[i] = nullptr;
+    }
     if (t->keScratch) cudaFree(t->keScratch);
-    t->W = t->Ksf = t->keScratch = nullptr;
+    t->keScratch = nullptr;
     t->wsModels = 0;
     const size_t ld = (models + 31) / 32 * 32;
     if (std::getenv("HDB_DEBUG_CLOCKS")) {
         if (t->dbgClocks) cudaFree(t->dbgClocks);
-        CUDA_TRY(cudaMalloc(&t->dbgClocks, ld * 8 * sizeof(long long)));
-        CUDA_TRY(cudaMemset(t->dbgClocks, 0, ld * 8 * sizeof(long long)));
+        CUDA_TRY(cudaMalloc(&t->dbgClocks, ld * 32 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(t->dbgClocks, 0, ld * 32 * sizeof(long long)));
     }
-    CUDA_TRY(cudaMalloc(&t->W, (size_t)t->S.nSlots * ld * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&t->Ksf, std::max<size_t>(1, models * (size_t)t->S.nnzR) * sizeof(double)));
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaMalloc(&t->Wbuf[i], (size_t)t->S.nSlots * ld * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&t->Ksfbuf[i], std::max<size_t>(1, models * (size_t)t->S.nnzR) * sizeof(double)));
+    }
     if (!assemble_fits_smem(t->D, t->smemOptin))
         CUDA_TRY(cudaMalloc(&t->keScratch, models * (size_t)t->S.nB * KE_LD * sizeof(double)));
     t->wsModels = ld;
@@ -325,8 +343,15 @@ void hdb_topology_destroy(hdb_topology *t)
         cudaSetDevice(t->device);
         cudaDeviceSynchronize();
         for (void *p : t->devAllocs) cudaFree(p);
-        if (t->W) cudaFree(t->W);
-        if (t->Ksf) cudaFree(t->Ksf);
+        for (int i = 0; i < 2; i++) {
+            if (t->Wbuf[i]) cudaFree(t->Wbuf[i]);
+            if (t->Ksfbuf[i]) cudaFree(t->Ksfbuf[i]);
+            if (t->evPrep[i]) cudaEventDestroy(t->evPrep[i]);
+            if (t->evSolve[i]) cudaEventDestroy(t->evSolve[i]);
+        }
+        if (t->evFork) cudaEventDestroy(t->evFork);
+        if (t->evJoin) cudaEventDestroy(t->evJoin);
+        if (t->prepStream) cudaStreamDestroy(t->prepStream);
         if (t->keScratch) cudaFree(t->keScratch);
         for (auto &c : t->chunk) {
             if (c.base) cudaFree(c.base);
@@ -519,8 +544,19 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
     const int sb = std::min<int>(nModels, t->subBatch);
     int rc = ensure_workspace(t, (size_t)sb);
     if (rc != HDB_OK) return rc;
-    for (int m0 = 0; m0 < nModels; m0 += sb) {
+    // Two-stage pipeline over sub-batches: assemble + factor of sub-batch i+1 run on the prep stream while
+    // the solve kernel of sub-batch i runs on the caller's stream (the factor kernel is a latency chain on
+    // a few warps per SM and hides completely behind the bandwidth-bound solve).  Two workspace sets.
+    const int nSub = (nModels + sb - 1) / sb;
+    const bool pipelined = solve && nSub > 1 && !t->keScratch && !t->dbgClocks;
+    cudaStream_t ps = pipelined ? t->prepStream : st;
+    if (pipelined) {
+        CUDA_TRY(cudaEventRecord(t->evFork, st));
+        CUDA_TRY(cudaStreamWaitEvent(ps, t->evFork, 0));
+    }
+    for (int i = 0, m0 = 0; m0 < nModels; m0 += sb, i++) {
         const int nm = std::min(sb, nModels - m0);
+        const int buf = pipelined ? (i & 1) : 0;
         StaticLaunch L{};
         L.nModels = nm;
         L.nLC = nLC;
@@ -532,25 +568,31 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
         L.react = react ? react + (size_t)m0 * nLC * S.dof : nullptr;
         L.status = status + m0;
         L.failCase = failCase ? failCase + m0 : nullptr;
-        L.W = t->W;
-        L.Ksf = t->Ksf;
+        L.W = t->Wbuf[buf];
+        L.Ksf = t->Ksfbuf[buf];
         L.kval = kval ? kval + (size_t)m0 * S.nnzK : nullptr;
         L.keScratch = t->keScratch;
         L.dbgClocks = t->dbgClocks;
+        if (pipelined && i >= 2) CUDA_TRY(cudaStreamWaitEvent(ps, t->evSolve[buf], 0)); // workspace set is free again
         {
-            ProfScope ps(t, KIND_ASSEMBLE, st);
-            CUDA_TRY(launch_assemble(t->D, L, st));
+            ProfScope pr(t, KIND_ASSEMBLE, ps);
+            CUDA_TRY(launch_assemble(t->D, L, ps));
         }
         count_launch(1);
         if (!solve) continue;
         {
-            ProfScope ps(t, KIND_FACTOR, st);
-            CUDA_TRY(launch_factor(t->D, L, st));
+            ProfScope pr(t, KIND_FACTOR, ps);
+            CUDA_TRY(launch_factor(t->D, L, ps));
+        }
+        if (pipelined) {
+            CUDA_TRY(cudaEventRecord(t->evPrep[buf], ps));
+            CUDA_TRY(cudaStreamWaitEvent(st, t->evPrep[buf], 0));
         }
         {
-            ProfScope ps(t, KIND_SOLVE, st);
+            ProfScope pr(t, KIND_SOLVE, st);
             CUDA_TRY(launch_solve_recover(t->D, L, st));
         }
+        if (pipelined) CUDA_TRY(cudaEventRecord(t->evSolve[buf], st));
         count_launch(2);
     }
     return HDB_OK;
@@ -561,13 +603,23 @@ static void debug_report_clocks(hdb_topology *t, int nModels)
     if (!t->dbgClocks) return;
     cudaDeviceSynchronize();
     const int n = std::min<int>(nModels, (int)t->wsModels);
-    std::vector<long long> h((size_t)n * 8);
+    std::vector<long long> h((size_t)n * 32);
     cudaMemcpy(h.data(), t->dbgClocks, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    double acc[5] = {0, 0, 0, 0, 0};
-    for (int m = 0; m < n; m++)
-        for (int i = 0; i < 5; i++) acc[i] += (double)(h[(size_t)m * 8 + i + 1] - h[(size_t)m * 8 + i]);
+    double acc[5] = {0, 0, 0, 0, 0}, warpEnd[8] = {0, 0, 0, 0, 0, 0, 0, 0}, warpMid[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < n; m++) {
+        for (int i = 0; i < 5; i++) acc[i] += (double)(h[(size_t)m * 32 + i + 1] - h[(size_t)m * 32 + i]);
+        for (int w = 0; w < 8; w++) {
+            warpMid[w] += (double)(h[(size_t)m * 32 + 8 + w] - h[(size_t)m * 32 + 4]);
+            warpEnd[w] += (double)(h[(size_t)m * 32 + 16 + w] - h[(size_t)m * 32 + 4]);
+        }
+    }
     std::fprintf(stderr, "[hdb] k_solve_recover cycles/model: load %.0f fwd %.0f bwd %.0f barrier %.0f recover %.0f\n",
                  acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n);
+    std::fprintf(stderr, "[hdb]   per-warp cycles from start of recovery to end of disp+react:");
+    for (int w = 0; w < 8; w++) std::fprintf(stderr, " %.0f", warpMid[w] / n);
+    std::fprintf(stderr, "\n[hdb]   per-warp cycles from start of recovery to end of forces:     ");
+    for (int w = 0; w < 8; w++) std::fprintf(stderr, " %.0f", warpEnd[w] / n);
+    std::fprintf(stderr, "\n");
 }
 
 int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *loads,

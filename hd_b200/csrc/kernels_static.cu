@@ -340,6 +340,7 @@ cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t 
 // k_solve_recover
 // ------------------------------------------------------------------------------------------------
 constexpr int SOL_MAX_THREADS = 256;
+constexpr int LOAD_CASES = 8; // load cases streamed together by the load phase: 4 DOFs x 8 cases = 32 loads in flight per thread
 constexpr int LV_PAD = 16; // the substitution reads 16 doubles around any slot: pad both ends of the factor
 
 struct SolveCfg {
@@ -350,9 +351,18 @@ struct SolveCfg {
 
 __host__ __device__ inline int odd_stride(int c) { return c | 1; }
 
+static int solve_threads(const DevTopo &T)
+{ // one thread per beam in the force phase when the model is small enough, whole warps
+    int threads = ((T.nB + 31) / 32) * 32;
+    if (threads < 128) threads = 128;
+    if (threads > SOL_MAX_THREADS) threads = SOL_MAX_THREADS;
+    return threads;
+}
+
 static size_t solve_smem_bytes(const DevTopo &T, int cp)
 {
-    return ((size_t)(T.nSlots + 2 * LV_PAD) + (size_t)T.nPad * odd_stride(cp)) * sizeof(double);
+    return ((size_t)(T.nSlots + 2 * LV_PAD) + (size_t)T.nPad * odd_stride(cp) + (SOL_MAX_THREADS / 32) * 32 * 7 + (size_t)(T.nB % solve_threads(T)) * 8) *
+           sizeof(double);
 }
 
 bool solve_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes)
@@ -563,6 +573,7 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
     const unsigned lvA = smA + LV_PAD * 8u;                       // [-LV_PAD, nSlots + LV_PAD) factor of this model
     const unsigned xsA = smA + (unsigned)(T.nSlots + 2 * LV_PAD) * 8u; // [nPad][CS]
     const unsigned CS8 = (unsigned)CS * 8u;
+    const unsigned fstA = xsA + (unsigned)T.nPad * CS8;              // per-warp 32 x 7 staging tiles of the force phase
 
     if (tid == 0) {
         s_failCase = 0x7fffffff;
@@ -570,7 +581,7 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
     }
 #define STAMP(i)                                                                              \
     do {                                                                                      \
-        if (L.dbgClocks && tid == stampTid) L.dbgClocks[(size_t)model * 8 + (i)] = clock64();  \
+        if (L.dbgClocks && tid == stampTid) L.dbgClocks[(size_t)model * 32 + (i)] = clock64();  \
     } while (0)
     const int stampTid = (((int)blockIdx.x / (cfg.nSM > 0 ? cfg.nSM : 148)) & 3) * 32;
     STAMP(0);
@@ -598,56 +609,68 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
         }
     }
     const double *ksf = L.Ksf + (size_t)model * T.nnzR;
-    int nSM = cfg.nSM > 0 ? cfg.nSM : 148;
+    const int nSM = cfg.nSM > 0 ? cfg.nSM : 148;
     const int solver = ((blockIdx.x / nSM) & 3) * 32; // co-resident CTAs put their solver warp on different SMSPs
-    // DOF ownership: a thread owns up to four DOFs; the index maps are read once
-    int xr[4], si[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-        const int g = tid + u * NT;
-        xr[u] = g < dof ? __ldg(T.xrow + g) : -1;
-        si[u] = g < dof ? __ldg(T.supIndex + g) : -1;
+    // beams beyond the last full round of the block: their coefficients go to a small shared table once,
+    // so that the force phase never recomputes an element inside its case loop
+    const int nMain = (nB / NT) * NT, nRest = nB - nMain;
+    const unsigned crA = fstA + (unsigned)(SOL_MAX_THREADS / 32) * (32u * 7u * 8u);
+    if (L.forces && tid < nRest) {
+        const int b = nMain + tid;
+        const double *sec = L.sections + (size_t)model * nB * 3;
+        const BeamGeom g = beam_geom(T, b);
+        const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
+        const unsigned a = crA + (unsigned)tid * 64u;
+        sts_f64(a, cf.EFL); sts_f64(a + 8, cf.EJL3); sts_f64(a + 16, cf.EJL2); sts_f64(a + 24, cf.EJL);
+        sts_f64(a + 32, cf.EJL4); sts_f64(a + 40, g.c); sts_f64(a + 48, g.s);
     }
-    const int gStep = NT * 4;
+    constexpr int LC = 4; // load cases handled together by one work item of the streaming phases
+    bool badLoad = false;
+    int failC = 0x7fffffff;
 
     for (int c0 = 0; c0 < L.nLC; c0 += cfg.casesPerPass) {
         const int nc = min(cfg.casesPerPass, L.nLC - c0);
         const double *p = L.loads + ((size_t)model * L.nLC + c0) * dof;
         double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof : nullptr;
+        const int nItems = ((nc + LC - 1) / LC) * dof; // item = (group of LC cases, DOF); DOF fastest: coalesced
         // phase 1: load cases -> xs (free rows), dummy rows = 0; model.go:692-696 and 424-437 checks.
-        // Cases stream four at a time: sixteen independent coalesced loads in flight per thread.  The
-        // reaction output starts here as -p on supported DOFs (model.go:478) and 0 elsewhere; phase 3 adds
-        // K[r,:] d to it with one fire-and-forget reduction per entry, so p is never read twice.
-        for (int g0 = 0; g0 < dof; g0 += gStep) {
-            if (g0 > 0) {
+        // Four items per thread are in flight (16 independent coalesced loads).  The reaction output starts
+        // here as -p on supported DOFs (model.go:478) and 0 elsewhere; phase 3 adds K[r,:] d to it with one
+        // fire-and-forget reduction per entry, so p is never read twice.
+        for (int it0 = 0; it0 < nItems; it0 += NT * 4) {
+            double v[4][LC];
+            int gi[4], ci[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int g = g0 + tid + u * NT;
-                    xr[u] = g < dof ? __ldg(T.xrow + g) : -1;
-                    si[u] = g < dof ? __ldg(T.supIndex + g) : -1;
-                }
+            for (int u = 0; u < 4; u++) {
+                const int it = it0 + u * NT + tid;
+                const int cg = it / dof;
+                gi[u] = it < nItems ? it - cg * dof : -1;
+                ci[u] = cg * LC;
+#pragma unroll
+                for (int j = 0; j < LC; j++)
+                    v[u][j] = (gi[u] >= 0 && ci[u] + j < nc) ? __ldcs(p + (size_t)(ci[u] + j) * dof + gi[u]) : 0.0;
             }
-            for (int c = 0; c < nc; c += 4) {
-                double v[4][4];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
+            for (int u = 0; u < 4; u++) {
+                if (gi[u] < 0) continue;
+                const int g = gi[u], c = ci[u];
+                const int xr = __ldg(T.xrow + g);
+                const bool sup = orr && __ldg(T.supIndex + g) >= 0;
+                const unsigned xb = xsA + (unsigned)(xr >= 0 ? xr : 0) * CS8 + (unsigned)c * 8u;
+                double *po = orr ? orr + (size_t)c * dof + g : nullptr;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int g = g0 + tid + u * NT;
-                        v[j][u] = (g < dof && c + j < nc) ? p[(size_t)(c + j) * dof + g] : 0.0;
-                    }
+                for (int j = 0; j < LC; j++) {
+                    if (c + j >= nc) break;
+                    const double val = v[u][j];
+                    badLoad |= !(fabs(val) <= 1.7976931348623157e308);
+                    if (xr >= 0) sts_f64(xb + 8u * j, val);
+                    if (po) po[(size_t)j * dof] = sup ? -val : 0.0;
+                }
+                if (xr == -2) {
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int g = g0 + tid + u * NT;
-                        if (!(g < dof && c + j < nc)) continue;
-                        const double val = v[j][u];
-                        if (!isfinite(val)) atomicMax(&s_flag, 1);
-                        if (xr[u] >= 0) sts_f64(xsA + (unsigned)xr[u] * CS8 + (unsigned)(c + j) * 8u, val);
-                        else if (xr[u] == -2 && val != 0.0) atomicMin(&s_failCase, c0 + c + j);
-                        if (orr) orr[(size_t)(c + j) * dof + g] = si[u] >= 0 ? -val : 0.0;
-                    }
+                    for (int j = 0; j < LC; j++)
+                        if (c + j < nc && v[u][j] != 0.0) failC = min(failC, c0 + c + j);
+                }
             }
         }
         for (int idx = tid; idx < T.nDummy * nc; idx += NT) {
@@ -667,63 +690,51 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
         __syncthreads();
         STAMP(4);
 
-        // phase 3a+b: displacements (model.go:446-451), written row by row (a case row is one contiguous
-        // run for the whole CTA), and reactions (model.go:470-489: columns ascending, eliminated columns
-        // carry d = 0) added to the -p rows of phase 1 with one reduction per supported entry.
-        for (int g0 = 0; g0 < dof; g0 += gStep) {
-            if (gStep < dof) {
+        // phase 3a+b: displacements (model.go:446-451) and reactions (model.go:470-489: columns ascending,
+        // eliminated columns carry d = 0) added to the -p rows of phase 1 with one reduction per supported entry.
+        if (L.disp || orr) {
+            double *od0 = L.disp ? L.disp + ((size_t)model * L.nLC + c0) * dof : nullptr;
+            for (int it = tid; it < nItems; it += NT) {
+                const int cg = it / dof, g = it - cg * dof, c = cg * LC;
+                const int xr = __ldg(T.xrow + g);
+                if (od0) {
+                    double *od = od0 + (size_t)c * dof + g;
+                    const unsigned xb = xsA + (unsigned)(xr >= 0 ? xr : 0) * CS8 + (unsigned)c * 8u;
+                    double d[LC];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int g = g0 + tid + u * NT;
-                    xr[u] = g < dof ? __ldg(T.xrow + g) : -1;
-                    si[u] = g < dof ? __ldg(T.supIndex + g) : -1;
+                    for (int j = 0; j < LC; j++) d[j] = (xr >= 0 && c + j < nc) ? lds_f64(xb + 8u * j) : 0.0;
+#pragma unroll
+                    for (int j = 0; j < LC; j++)
+                        if (c + j < nc) od[(size_t)j * dof] = d[j];
                 }
-            }
-            if (L.disp) {
-                double *od = L.disp + ((size_t)model * L.nLC + c0) * dof + g0 + tid;
-                for (int c = 0; c < nc; c++) {
-                    double d[4];
+                const int si = orr ? __ldg(T.supIndex + g) : -1;
+                if (si >= 0) {
+                    const int q0 = __ldg(T.rptr + si), q1 = __ldg(T.rptr + si + 1);
+                    double acc[LC];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) d[u] = xr[u] >= 0 ? lds_f64(xsA + (unsigned)xr[u] * CS8 + (unsigned)c * 8u) : 0.0;
+                    for (int j = 0; j < LC; j++) acc[j] = 0.0;
+                    for (int q = q0; q < q1; q++) {
+                        const double kv = __ldg(ksf + q);
+                        const unsigned xa = xsA + (unsigned)__ldg(T.rcol + q) * CS8 + (unsigned)c * 8u;
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (g0 + tid + u * NT < dof) od[(size_t)c * dof + u * NT] = d[u];
-                }
-            }
-            if (orr) {
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (si[u] < 0) continue;
-                    const int g = g0 + tid + u * NT;
-                    const int q0 = __ldg(T.rptr + si[u]), q1 = __ldg(T.rptr + si[u] + 1);
-                    for (int c = 0; c < nc; c += 4) {
-                        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                        for (int q = q0; q < q1; q++) {
-                            const double kv = __ldg(ksf + q);
-                            const unsigned xa = xsA + (unsigned)__ldg(T.rcol + q) * CS8 + (unsigned)c * 8u;
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if (c + j < nc) acc[j] = fma(kv, lds_f64(xa + 8u * j), acc[j]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (c + j < nc) atomicAdd(orr + (size_t)(c + j) * dof + g, acc[j]); // RED: no return value
+                        for (int j = 0; j < LC; j++)
+                            if (c + j < nc) acc[j] = fma(kv, lds_f64(xa + 8u * j), acc[j]);
                     }
+                    double *pr = orr + (size_t)c * dof + g;
+#pragma unroll
+                    for (int j = 0; j < LC; j++)
+                        if (c + j < nc) atomicAdd(pr + (size_t)j * dof, acc[j]); // RED: no return value
                 }
             }
         }
-        // phase 3c: beam end forces s = k (T Zo), model.go:455-468.  One thread per beam for all cases; the
-        // beams beyond the last full round of the block are spread case by case over the threads.
+        if (L.dbgClocks && (tid & 31) == 0 && (tid >> 5) < 8) L.dbgClocks[(size_t)model * 32 + 8 + (tid >> 5)] = clock64();
+        // phase 3c: beam end forces s = k (T Zo), model.go:455-468.  One thread per beam keeps the element
+        // coefficients in registers over all cases; the few beams beyond the last full round are spread case
+        // by case over the threads and take their coefficients from the shared table.
         if (L.forces) {
             double *out = L.forces + ((size_t)model * L.nLC + c0) * nB * 6;
-            const bool vec16 = (reinterpret_cast<uintptr_t>(L.forces) & 15) == 0;
             const double *sec = L.sections + (size_t)model * nB * 3;
-            const int nMain = (nB / NT) * NT, nRest = nB - nMain;
-            const int nItems = nMain + nRest * nc;
-            for (int it = tid; it < nItems; it += NT) {
-                int b, cBeg, cEnd;
-                if (it < nMain) { b = it; cBeg = 0; cEnd = nc; }
-                else { b = nMain + (it - nMain) / nc; cBeg = (it - nMain) % nc; cEnd = cBeg + 1; }
+            for (int b = tid; b < nMain; b += NT) {
                 const BeamGeom g = beam_geom(T, b);
                 const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
                 const uint32_t pm = T.pinMask[b];
@@ -735,7 +746,9 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
                     rv[e] = r >= 0;
                     ra[e] = xsA + (unsigned)(r >= 0 ? r : 0) * CS8;
                 }
-                for (int c = cBeg; c < cEnd; c++) {
+                const unsigned wb = fstA + (unsigned)(tid >> 5) * (32u * 7u * 8u);
+                const unsigned lane = tid & 31;
+                for (int c = 0; c < nc; c++) {
                     double u[6], o[6];
 #pragma unroll
                     for (int e = 0; e < 6; e++) u[e] = rv[e] ? lds_f64(ra[e] + (unsigned)c * 8u) : 0.0;
@@ -748,22 +761,56 @@ __global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevT
 #pragma unroll
                         for (int e = 0; e < 6; e++) o[e] = oo[e];
                     }
-                    double *of = out + ((size_t)c * nB + b) * 6;
-                    if (vec16) { // 48-byte records: 16-byte aligned whenever the base pointer is
-                        double2 *o2 = reinterpret_cast<double2 *>(of);
-                        o2[0] = make_double2(o[0], o[1]);
-                        o2[1] = make_double2(o[2], o[3]);
-                        o2[2] = make_double2(o[4], o[5]);
-                    } else {
+                    // a full warp holds 32 consecutive beams = 192 consecutive doubles of the output row:
+                    // transpose through shared memory so that every store instruction writes one contiguous
+                    // 256-byte run (full sectors) instead of 16-byte pieces 48 bytes apart
+                    __syncwarp();
 #pragma unroll
-                        for (int e = 0; e < 6; e++) of[e] = o[e];
+                    for (int e = 0; e < 6; e++) sts_f64(wb + (lane * 7u + e) * 8u, o[e]);
+                    __syncwarp();
+                    double *ow = out + ((size_t)c * nB + (b - (int)lane)) * 6;
+#pragma unroll
+                    for (int e = 0; e < 6; e++) {
+                        const unsigned q = e * 32u + lane;
+                        ow[q] = lds_f64(wb + ((q / 6u) * 7u + q % 6u) * 8u);
                     }
                 }
             }
+            for (int it = tid; it < nRest * nc; it += NT) {
+                const int r = it / nc, c = it - r * nc, b = nMain + r;
+                const unsigned a = crA + (unsigned)r * 64u;
+                BeamCoef cf;
+                cf.EFL = lds_f64(a); cf.EJL3 = lds_f64(a + 8); cf.EJL2 = lds_f64(a + 16); cf.EJL = lds_f64(a + 24);
+                cf.EJL4 = lds_f64(a + 32);
+                const double gc = lds_f64(a + 40), gs = lds_f64(a + 48);
+                const uint32_t pm = T.pinMask[b];
+                double u[6], o[6];
+#pragma unroll
+                for (int e = 0; e < 6; e++) {
+                    const int row = __ldg(T.beamRows + b * 6 + e);
+                    u[e] = row >= 0 ? lds_f64(xsA + (unsigned)row * CS8 + (unsigned)c * 8u) : 0.0;
+                }
+                if (pm == 0) beam_forces_rigid(cf, gc, gs, u, o);
+                else {
+                    double uu[6], oo[6];
+#pragma unroll
+                    for (int e = 0; e < 6; e++) uu[e] = u[e];
+                    beam_forces_pinned(cf, pm, gc, gs, uu, oo);
+#pragma unroll
+                    for (int e = 0; e < 6; e++) o[e] = oo[e];
+                }
+                double *of = out + ((size_t)c * nB + b) * 6;
+#pragma unroll
+                for (int e = 0; e < 6; e++) of[e] = o[e];
+            }
         }
+        if (L.dbgClocks && (tid & 31) == 0 && (tid >> 5) < 8) L.dbgClocks[(size_t)model * 32 + 16 + (tid >> 5)] = clock64();
         __syncthreads(); // xs is reused by the next pass
         STAMP(5);
     }
+    if (badLoad) atomicMax(&s_flag, 1);
+    if (failC != 0x7fffffff) atomicMin(&s_failCase, failC);
+    __syncthreads();
     if (tid == 0) {
         int st = L.status[model];
         if (st == HDB_STATUS_OK && s_flag) st = HDB_STATUS_NONFINITE;
@@ -1101,10 +1148,7 @@ cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaSt
     if (!solve_config(T, L.nLC, optin, cfg.casesPerPass, smem)) return cudaErrorInvalidConfiguration;
     cfg.cs = odd_stride(cfg.casesPerPass);
     cfg.nSM = nSM;
-    // one thread per beam in the force phase when the model is small enough, whole warps
-    int threads = ((T.nB + 31) / 32) * 32;
-    if (threads < 128) threads = 128;
-    if (threads > SOL_MAX_THREADS) threads = SOL_MAX_THREADS;
+    const int threads = solve_threads(T);
     static const bool useTma = std::getenv("HDB_USE_TMA") != nullptr; // experimental: slower than the LDG/STG kernel so far
     if (useTma && tma_eligible(T, L, threads)) {
         TmaCfg tc;

@@ -5,7 +5,7 @@ os.environ["HDB_DEBUG_CLOCKS"] = "1"
 import numpy as np, torch
 from hd_b200 import _lib, frames
 from oracle import hd_oracle as oracle
-N, M, nLC = 128, 4096, 20
+N, M, nLC = 128, int(os.environ.get("PROBE_M", "4096")), 20
 fm = oracle.flatten_model(frames.uniform_frame(N))
 sec = frames.uniform_frame_sections(N, 0, M); loads = frames.uniform_frame_loads(N, 0, M)
 t = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports)
