@@ -117,7 +117,7 @@ static int ensure_device(hdb_topology *t)
     DevTopo &D = t->D;
     D.nP = S.nP; D.nB = S.nB; D.dof = S.dof; D.nFree = S.nFree; D.nBlk = S.nBlk; D.nPad = S.nPad; D.nSlots = S.nSlots;
     D.nSup = S.nSup; D.nnzR = S.nnzR; D.nnzK = S.nnzK; D.nDummy = (int)S.dummyPos.size(); D.maxBlkCount = S.maxBlkCount;
-    D.winNeed = S.winNeed; D.nFwdOps = (int)S.fwdOps.size() / 2; D.nBwdOps = (int)S.bwdOps.size() / 2;
+    D.winNeed = S.winNeed; D.nFwdOps = (int)S.fwdOps.size() / 4; D.nBwdOps = (int)S.bwdOps.size() / 4;
     // gather codes -> padded shared-memory indices
     auto pad = [](const std::vector<int32_t> &src) {
         std::vector<int32_t> o(src.size());
@@ -172,12 +172,13 @@ static int ensure_device(hdb_topology *t)
         const int32_t *f = nullptr, *b = nullptr;
         if ((rc = upload(t, S.fwdOps, &f)) != HDB_OK) return rc;
         if ((rc = upload(t, S.bwdOps, &b)) != HDB_OK) return rc;
-        D.fwdOps = reinterpret_cast<const int2 *>(f);
-        D.bwdOps = reinterpret_cast<const int2 *>(b);
+        D.fwdOps = reinterpret_cast<const int4 *>(f);
+        D.bwdOps = reinterpret_cast<const int4 *>(b);
     }
     UP(S.xrow, xrow);
     UP(S.beamRows, beamRows);
     UP(S.supIndex, supIndex);
+    UP(S.supDofs, supDofs);
     UP(S.rptr, rptr);
     UP(S.rcol, rcol);
     UP(S.dummyPos, dummyPos);
@@ -602,23 +603,24 @@ static void debug_report_clocks(hdb_topology *t, int nModels)
 {
     if (!t->dbgClocks) return;
     cudaDeviceSynchronize();
-    const int n = std::min<int>(nModels, (int)t->wsModels);
+    const int n = std::min<int>(std::min<int>(nModels, (int)t->wsModels), t->smCount);
     std::vector<long long> h((size_t)n * 32);
     cudaMemcpy(h.data(), t->dbgClocks, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    double acc[5] = {0, 0, 0, 0, 0}, warpEnd[8] = {0, 0, 0, 0, 0, 0, 0, 0}, warpMid[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int m = 0; m < n; m++) {
-        for (int i = 0; i < 5; i++) acc[i] += (double)(h[(size_t)m * 32 + i + 1] - h[(size_t)m * 32 + i]);
-        for (int w = 0; w < 8; w++) {
-            warpMid[w] += (double)(h[(size_t)m * 32 + 8 + w] - h[(size_t)m * 32 + 4]);
-            warpEnd[w] += (double)(h[(size_t)m * 32 + 16 + w] - h[(size_t)m * 32 + 4]);
-        }
+    double blk = 0, sol = 0, models = 0, ph[16] = {};
+    for (int b = 0; b < n; b++) {
+        const long long *d = h.data() + (size_t)b * 32;
+        blk += (double)d[0];
+        sol += (double)d[1];
+        models += (double)d[2];
+        for (int k = 0; k < 16; k++) ph[k] += (double)d[8 + k];
     }
-    std::fprintf(stderr, "[hdb] k_solve_recover cycles/model: load %.0f fwd %.0f bwd %.0f barrier %.0f recover %.0f\n",
-                 acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n);
-    std::fprintf(stderr, "[hdb]   per-warp cycles from start of recovery to end of disp+react:");
-    for (int w = 0; w < 8; w++) std::fprintf(stderr, " %.0f", warpMid[w] / n);
-    std::fprintf(stderr, "\n[hdb]   per-warp cycles from start of recovery to end of forces:     ");
-    for (int w = 0; w < 8; w++) std::fprintf(stderr, " %.0f", warpEnd[w] / n);
+    if (models <= 0) return;
+    std::fprintf(stderr, "[hdb] k_solve_pipe cycles/model (last launch, %d blocks): block %.0f | solver warp %.0f | streaming warp 1:\n", n,
+                 blk / models, sol / models);
+    static const char *names[11] = {"Ksf->smem", "beam coef", "disp", "(barrier)", "react", "forces", "(barrier)", "factor gather issue",
+                                    "load cases", "(barrier)", "status"};
+    std::fprintf(stderr, "[hdb]  ");
+    for (int k = 0; k < 11; k++) std::fprintf(stderr, " %s %.0f |", names[k], ph[k] / models);
     std::fprintf(stderr, "\n");
 }
 

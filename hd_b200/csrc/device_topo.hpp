@@ -7,16 +7,20 @@
 
 namespace hdb {
 
-// substitution op list (one warp walks it, one lane per load case); see build_solve_ops()
-enum : int { OP_PULL = 0, OP_DIAG = 1, OP_FUSED = 2 };
-constexpr int OPF_FIRST = 1 << 27; // first op of a block: reset the accumulator
-constexpr int OPF_PREV = 1 << 26;  // source block is the block finished just before (values are in registers)
-constexpr int OP_KIND_SHIFT = 28;
-constexpr int OP_BLK_MASK = (1 << 26) - 1;
+// substitution op lists (one warp walks them, one lane per load case; built at the end of build_symbolic):
+// runs of int4 records, each run led by a header {2 * count, 0, kind, 0}; an op is {slot of the off block L_IJ,
+// header slot of the target block, tgt | src << 14 | flags, 0} and means acc(tgt) -= L x(src) resp. L^T x(src)
+enum : int { RUN_GENERIC = 0, RUN_CHAIN = 1 };
+constexpr int OPF_FIRST = 1 << 28;   // first op of a target block: the accumulator starts from its right-hand side
+constexpr int OPF_PREV = 1 << 29;    // source block is the block stored by the op just before (values are in registers)
+constexpr int OPF_LAST = 1 << 30;    // last op of a target block: finish with the diagonal block and store x(tgt)
+constexpr int OPF_NOPULL = (int)(1u << 31); // block without off blocks in this direction
+constexpr int OP_BLK_MASK = (1 << 14) - 1;
+constexpr int OP_SRC_SHIFT = 14;
 
 struct DevTopo {
     int nP, nB, dof, nFree, nBlk, nPad, nSlots, nSup, nnzR, nnzK, nDummy, maxBlkCount, winNeed;
-    int nFwdOps, nBwdOps;
+    int nFwdOps, nBwdOps; // records incl. run headers and terminators
     // geometry / topology (shared by every model of a batch)
     const double *points;      // [nP][2]
     const int32_t *beamN;      // [nB][2]
@@ -30,12 +34,12 @@ struct DevTopo {
     // block factorization schedule
     const int32_t *BLp, *BLi, *colOff, *blkSlot, *pairPtr, *pairTgt, *needUpto;
     const int4 *colDesc;       // [nBlk] {first slot, off-block count, prefetch bound, first Schur target}
-    // substitution op lists: int2 {slot, blk | flags | kind << 28}
-    const int2 *fwdOps, *bwdOps;
+    const int4 *fwdOps, *bwdOps; // substitution op lists
     // recovery
     const int32_t *xrow;       // [dof]
     const int32_t *beamRows;   // [nB*6]
     const int32_t *supIndex;   // [dof]
+    const int32_t *supDofs;    // [nSup] supported DOFs ascending
     const int32_t *rptr, *rcol;
     const int32_t *dummyPos;   // [nDummy]
 };

@@ -8,7 +8,7 @@
 
 namespace hdb {
 
-constexpr int BLK_HDR = 6;        // 1/d (3) + strictly lower part of the diagonal block (3)
+constexpr int BLK_HDR = 6;        // 1/d (3) + strictly lower part of the inverse of the unit diagonal block (3)
 constexpr int BLK_STRIDE = 10;    // 9 values of an off block + 1 pad (keeps every block 16-byte aligned)
 constexpr int FACTOR_PREFETCH = 6; // block columns the factor kernel prefetches ahead
 
@@ -74,8 +74,8 @@ struct Symbolic {
     std::vector<int32_t> needUpto;  // [nBlk] slots [0, needUpto[J]) must be resident to eliminate column J
     int winNeed = 0;                // shared-memory window (slots) the factor kernel needs incl. prefetch
     // forward substitution: row block I pulls from (J, slot) ascending J
-    std::vector<int32_t> fwdPtr, fwdJ, fwdSlot;
-    // substitution op lists walked by the solve kernel: pairs {slot, blk | flags | kind << 28}
+    std::vector<int32_t> fwdPtr, fwdJ, fwdSlot, fwdQ;
+    // substitution op lists walked by the solve kernel: records {slot of L_IJ, header slot of tgt, tgt | src << 14 | flags, 0}
     std::vector<int32_t> fwdOps, bwdOps;
     // DOF -> x row (padded position) for free DOFs, -1 supported/eliminated, -2 ignore (load must be zero)
     std::vector<int32_t> xrow;      // [dof]

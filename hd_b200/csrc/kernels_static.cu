@@ -230,8 +230,10 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
         d2 = fma(-l21, u21, fma(-l20, a20, d2));
         if (d2 == 0.0 || !isfinite(d2)) bad = true;
         const double inv2 = __drcp_rn(d2);
+        // header for the solve kernel: 1/d and the strictly lower part of V = Ldiag^-1 (both substitutions then
+        // finish a block with independent multiply-adds instead of a dependent chain)
         WIN(base + 0) = inv0; WIN(base + 1) = inv1; WIN(base + 2) = inv2;
-        WIN(base + 3) = l10;  WIN(base + 4) = l20;  WIN(base + 5) = l21;
+        WIN(base + 3) = -l10; WIN(base + 4) = fma(l10, l21, -l20); WIN(base + 5) = -l21;
         const int nb = d.y;
         if (nb == 1) {
             // ---- the banded case: one off block; its values and the Schur update stay in registers ----
@@ -337,32 +339,60 @@ cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_solve_recover
+// k_solve_pipe: load cases -> substitution -> displacements, reactions, beam forces (model.go:421-491)
+//
+// One persistent block per SM works through its models as a three-stage software pipeline over two
+// shared-memory buffers.  In iteration i
+//   * the solver warp runs the two triangular solves of model i-1: a sequential chain of 3x3 block ops,
+//     one lane per load case.  It has SM sub-partition 0 to itself (warps 4, 8, 12 only take part in the
+//     block-wide barrier): shared-memory loads that queue behind the global traffic of other warps in the
+//     same sub-partition made the chain 2.5x slower;
+//   * the streaming warps (sub-partitions 1-3) first turn model i-2's solution into its three outputs, then
+//     pull model i in: factor and load cases,
+// so the memory system always has twelve warps of loads or stores in flight while the chain runs.
+//
+// Shared memory of one buffer: the factor of the model [nSlots] (reused for the beam coefficients and the
+// reaction block once the solve is over), and xs[nBlk][cases][3] (a block's three unknowns of one load
+// case are adjacent, the lane stride of 24 bytes is bank-conflict free).  Integer topology tables (op
+// lists, DOF info, beam rows, reaction rows) are staged once per block.
 // ------------------------------------------------------------------------------------------------
-constexpr int SOL_MAX_THREADS = 256;
-constexpr int LOAD_CASES = 8; // load cases streamed together by the load phase: 4 DOFs x 8 cases = 32 loads in flight per thread
-constexpr int LV_PAD = 16; // the substitution reads 16 doubles around any slot: pad both ends of the factor
+constexpr int PIPE_THREADS = 512; // warp 0 = solver, warps 4, 8, 12 idle, the other twelve stream
+constexpr int LC = 4;             // load cases handled together by one work item of the streaming stages
+constexpr int NS = PIPE_THREADS / 32 / 4 * 3 * 32; // streaming threads: the warps outside SM sub-partition 0
+constexpr int LOAD_U = 14;        // loads in flight per streaming thread in the load stage
+constexpr unsigned FST_BYTES = 32u * 7u * 8u; // per-warp 32 x 7 staging tile of the force stage
 
 struct SolveCfg {
     int casesPerPass; // <= 32
-    int cs;           // row stride of xs in doubles (odd)
-    int nSM;
+    int nPass;        // passes over the load cases of a model (1 unless shared memory is short)
+    int lvmDoubles;   // one factor/table buffer
+    int xsDoubles;    // one xs buffer
+    int expNoGather;  // experiment (HDB_EXP_NOGATHER): skip the factor gather, results are wrong
 };
 
-__host__ __device__ inline int odd_stride(int c) { return c | 1; }
+// one block of xs = [cases][3] doubles, padded to an odd count: threads that read the same component of
+// consecutive blocks (reactions, beam forces) then fall into different banks
+__host__ __device__ inline int xs_block_doubles(int cp) { return (3 * cp) | 1; }
 
-static int solve_threads(const DevTopo &T)
-{ // one thread per beam in the force phase when the model is small enough, whole warps
-    int threads = ((T.nB + 31) / 32) * 32;
-    if (threads < 128) threads = 128;
-    if (threads > SOL_MAX_THREADS) threads = SOL_MAX_THREADS;
-    return threads;
+static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+static size_t pipe_idx_bytes(const DevTopo &T)
+{
+    return (size_t)(T.nFwdOps + T.nBwdOps) * 16 +
+           align16(((size_t)T.dof + (size_t)6 * T.nB + (size_t)2 * T.nSup + 1 + (size_t)T.nnzR) * 4) +
+           (size_t)(NS / 32) * FST_BYTES + 32;
+}
+
+static size_t pipe_lvm_doubles(const DevTopo &T)
+{
+    // solve: factor of the model; recovery: beam coefficients + reaction block K[sup, free] of the model
+    size_t d = std::max<size_t>((size_t)T.nSlots, (size_t)T.nB * 8 + (size_t)T.nnzR);
+    return (d + 1) & ~(size_t)1;
 }
 
 static size_t solve_smem_bytes(const DevTopo &T, int cp)
 {
-    return ((size_t)(T.nSlots + 2 * LV_PAD) + (size_t)T.nPad * odd_stride(cp) + (SOL_MAX_THREADS / 32) * 32 * 7 + (size_t)(T.nB % solve_threads(T)) * 8) *
-           sizeof(double);
+    return pipe_idx_bytes(T) + 2 * (pipe_lvm_doubles(T) + (size_t)T.nBlk * xs_block_doubles(cp)) * sizeof(double);
 }
 
 bool solve_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes)
@@ -380,18 +410,6 @@ bool solve_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, s
     return false;
 }
 
-// Block substitution, one lane per load case.  The warp walks an op list (device_topo.hpp): OP_PULL
-// accumulates s += L_IJ z_J for one off block, OP_DIAG finishes a block with its diagonal part, OP_FUSED
-// does both for the common banded case (single pull from the block finished just before, whose values
-// are still in registers).  The 16 doubles around rec.x are laid out per pass so that every register
-// index is static:
-//   forward : [off block 9 + pad | 1/d0 1/d1 1/d2 l10 l20 l21]   (OP_DIAG points 10 before its header)
-//   backward: [1/d0 1/d1 1/d2 l10 l20 l21 | off block 9 + pad]   (OP_PULL points 6 before its block)
-// A single warp is issue-bound here (about one instruction every two cycles), so the loop is written
-// for instruction count: 32-bit shared-window addresses with immediate offsets, 16-byte value loads, a
-// two-op unrolled body without register rotation.  Software pipeline: the loads of op k+1 are issued in
-// the middle of op k, right after its off-block values have been consumed, so their latency hides
-// behind the diagonal solve chain.
 __device__ __forceinline__ double lds_f64(unsigned a)
 {
     double v;
@@ -413,117 +431,6 @@ __device__ __forceinline__ void lds_v2o(unsigned a, double &x, double &y)
 __device__ __forceinline__ void sts_f64(unsigned a, double v)
 {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
-}
-
-template <bool FWD>
-__device__ __noinline__ void substitute(const int2 *__restrict__ ops, const int nOps, const unsigned lvA, const unsigned xsA,
-                                        const int CS, const int c)
-{
-    if (nOps <= 0) return;
-    const unsigned xA = xsA + (unsigned)c * 8u;
-    const unsigned CS8 = (unsigned)CS * 8u, CS24 = 3u * CS8;
-    double h0 = 0, h1 = 0, h2 = 0; // the block finished last
-    double s0 = 0, s1 = 0, s2 = 0; // pulled sum of the block in progress
-    // values of the current op that its first stage consumes; reloaded in the middle of the op
-    double L00, L01, L02, L10, L11, L12, L20, L21, L22, p0, p1, p2, i0 = 0, i1 = 0, i2 = 0;
-    unsigned xa;
-#define SUB_LOAD_MID(REC)                                                          \
-    do {                                                                           \
-        const unsigned a_ = lvA + (unsigned)(REC).x * 8u;                          \
-        if (FWD) {                                                                 \
-            lds_v2o<0>(a_, L00, L01);                                              \
-            lds_v2o<16>(a_, L02, L10);                                             \
-            lds_v2o<32>(a_, L11, L12);                                             \
-            lds_v2o<48>(a_, L20, L21);                                             \
-            L22 = lds_f64o<64>(a_);                                                \
-        } else {                                                                   \
-            lds_v2o<0>(a_, i0, i1);                                                \
-            i2 = lds_f64o<16>(a_);                                                 \
-            lds_v2o<48>(a_, L00, L01);                                             \
-            lds_v2o<64>(a_, L02, L10);                                             \
-            lds_v2o<80>(a_, L11, L12);                                             \
-            lds_v2o<96>(a_, L20, L21);                                             \
-            L22 = lds_f64o<112>(a_);                                               \
-        }                                                                          \
-        xa = xA + (unsigned)((REC).y & OP_BLK_MASK) * CS24;                        \
-        p0 = lds_f64(xa);                                                          \
-        p1 = lds_f64(xa + CS8);                                                    \
-        p2 = lds_f64(xa + 2u * CS8);                                               \
-    } while (0)
-
-    int2 rec = __ldg(ops), recN = __ldg(ops + min(1, nOps - 1));
-    SUB_LOAD_MID(rec);
-    for (int k = 0; k < nOps; k++) {
-        const int2 recNN = __ldg(ops + min(k + 2, nOps - 1));
-        const int kind = (unsigned)rec.y >> OP_KIND_SHIFT;
-        // diagonal-stage values of this op: needed only after the first stage, so their latency is hidden
-        double l10, l20, l21;
-        {
-            const unsigned a = lvA + (unsigned)rec.x * 8u;
-            if (FWD) {
-                l10 = lds_f64o<104>(a);
-                lds_v2o<112>(a, l20, l21);
-            } else {
-                l10 = lds_f64o<24>(a);
-                lds_v2o<32>(a, l20, l21);
-            }
-        }
-        // ---- stage 1: off block ----
-        double t0, t1, t2; // right-hand side of the diagonal stage
-        if (kind == OP_FUSED) { // source = block finished just before (registers), fresh accumulator
-            if (FWD) {
-                t0 = fma(-L02, h2, fma(-L01, h1, fma(-L00, h0, p0)));
-                t1 = fma(-L12, h2, fma(-L11, h1, fma(-L10, h0, p1)));
-                t2 = fma(-L22, h2, fma(-L21, h1, fma(-L20, h0, p2)));
-            } else {
-                t0 = fma(-L20, h2, fma(-L10, h1, fma(-L00, h0, p0 * i0)));
-                t1 = fma(-L21, h2, fma(-L11, h1, fma(-L01, h0, p1 * i1)));
-                t2 = fma(-L22, h2, fma(-L12, h1, fma(-L02, h0, p2 * i2)));
-            }
-        } else if (kind == OP_PULL) {
-            if (rec.y & OPF_FIRST) s0 = s1 = s2 = 0.0;
-            double z0 = h0, z1 = h1, z2 = h2;
-            if (!(rec.y & OPF_PREV)) { z0 = p0; z1 = p1; z2 = p2; }
-            if (FWD) {
-                s0 = fma(L02, z2, fma(L01, z1, fma(L00, z0, s0)));
-                s1 = fma(L12, z2, fma(L11, z1, fma(L10, z0, s1)));
-                s2 = fma(L22, z2, fma(L21, z1, fma(L20, z0, s2)));
-            } else {
-                s0 = fma(L20, z2, fma(L10, z1, fma(L00, z0, s0)));
-                s1 = fma(L21, z2, fma(L11, z1, fma(L01, z0, s1)));
-                s2 = fma(L22, z2, fma(L12, z1, fma(L02, z0, s2)));
-            }
-            t0 = t1 = t2 = 0.0;
-        } else { // OP_DIAG
-            if (rec.y & OPF_FIRST) s0 = s1 = s2 = 0.0;
-            if (FWD) { t0 = p0 - s0; t1 = p1 - s1; t2 = p2 - s2; }
-            else { t0 = fma(p0, i0, -s0); t1 = fma(p1, i1, -s1); t2 = fma(p2, i2, -s2); }
-        }
-        const unsigned xaCur = xa;
-        // ---- the first-stage values are dead: reload them for the next op; the loads complete behind
-        //      the diagonal chain below ----
-        if (k + 1 < nOps) SUB_LOAD_MID(recN);
-        // ---- stage 2: diagonal block ----
-        if (kind != OP_PULL) {
-            double r0, r1, r2;
-            if (FWD) { // unit lower solve; the D scaling is applied by the backward pass
-                r0 = t0;
-                r1 = fma(-l10, r0, t1);
-                r2 = fma(-l21, r1, fma(-l20, r0, t2));
-            } else { // unit upper (transposed) solve
-                r2 = t2;
-                r1 = fma(-l21, r2, t1);
-                r0 = fma(-l10, r1, fma(-l20, r2, t0));
-            }
-            sts_f64(xaCur, r0);
-            sts_f64(xaCur + CS8, r1);
-            sts_f64(xaCur + 2u * CS8, r2);
-            h0 = r0; h1 = r1; h2 = r2;
-        }
-        rec = recN;
-        recN = recNN;
-    }
-#undef SUB_LOAD_MID
 }
 
 __device__ __forceinline__ void beam_forces_rigid(const BeamCoef &cf, const double gc, const double gs, const double *u,
@@ -558,583 +465,498 @@ __device__ __noinline__ void beam_forces_pinned(const BeamCoef &cf, const uint32
     }
 }
 
-__global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover(const DevTopo T, const StaticLaunch L, const SolveCfg cfg)
+
+__device__ __forceinline__ int4 lds_op(unsigned a)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(unsigned a)
+{
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void bar_stream(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
+
+// ---- the sequential part: one lane per load case walks the op runs (device_topo.hpp) -----------------
+// A block column of the factor in shared memory: header [1/d0 1/d1 1/d2 v10 v20 v21], off blocks L_IJ
+// row-major (+ 1 pad).  All table loads are warp-uniform 16-byte loads; the loads of op k+1 are issued
+// before the result of op k is stored.
+//
+// CHAIN run, forward: z(tgt) = V_tgt (p(tgt) - L z(src)), src = target of the op before
+__device__ __forceinline__ void chain_fwd(const unsigned pos, const int n, const unsigned lvA, const unsigned xA, const unsigned BS)
+{
+    int4 r = lds_op(pos), rN = lds_op(pos + 16u);
+    double h0, h1, h2;
+    {
+        const unsigned sa = xA + (unsigned)((r.z >> OP_SRC_SHIFT) & OP_BLK_MASK) * BS;
+        h0 = lds_f64o<0>(sa); h1 = lds_f64o<8>(sa); h2 = lds_f64o<16>(sa);
+    }
+    double m00, m01, m02, m10, m11, m12, m20, m21, m22, i2, v10, v20, v21, q0, q1, q2;
+    unsigned ta;
+#define CHAIN_LOAD(REC)                                                  \
+    do {                                                                 \
+        const unsigned a_ = lvA + (unsigned)(REC).x * 8u;                \
+        const unsigned h_ = lvA + (unsigned)(REC).y * 8u;                \
+        ta = xA + (unsigned)((REC).z & OP_BLK_MASK) * BS;                \
+        lds_v2o<0>(a_, m00, m01);                                        \
+        lds_v2o<16>(a_, m02, m10);                                       \
+        lds_v2o<32>(a_, m11, m12);                                       \
+        lds_v2o<48>(a_, m20, m21);                                       \
+        m22 = lds_f64o<64>(a_);                                          \
+        lds_v2o<16>(h_, i2, v10);                                        \
+        lds_v2o<32>(h_, v20, v21);                                       \
+        q0 = lds_f64o<0>(ta); q1 = lds_f64o<8>(ta); q2 = lds_f64o<16>(ta); \
+    } while (0)
+    CHAIN_LOAD(r);
+    for (int k = 0; k < n; k++) {
+        const int4 rNN = lds_op(pos + 16u * (unsigned)(k + 2)); // may run past the run: never used then
+        const double a0 = fma(-m02, h2, fma(-m01, h1, fma(-m00, h0, q0)));
+        const double a1 = fma(-m12, h2, fma(-m11, h1, fma(-m10, h0, q1)));
+        const double a2 = fma(-m22, h2, fma(-m21, h1, fma(-m20, h0, q2)));
+        const double z1 = fma(v10, a0, a1), z2 = fma(v21, a1, fma(v20, a0, a2));
+        const unsigned tc = ta;
+        CHAIN_LOAD(rN); // past the end of the run this reads a run header or the terminator: aligned, in range, unused
+        sts_f64(tc, a0); sts_f64(tc + 8u, z1); sts_f64(tc + 16u, z2);
+        h0 = a0; h1 = z1; h2 = z2;
+        rN = rNN;
+    }
+    (void)i2;
+#undef CHAIN_LOAD
+}
+
+// CHAIN run, backward: x(tgt) = V_tgt^T (D^-1 z(tgt) - L^T x(src))
+__device__ __forceinline__ void chain_bwd(const unsigned pos, const int n, const unsigned lvA, const unsigned xA, const unsigned BS)
+{
+    int4 r = lds_op(pos), rN = lds_op(pos + 16u);
+    double h0, h1, h2;
+    {
+        const unsigned sa = xA + (unsigned)((r.z >> OP_SRC_SHIFT) & OP_BLK_MASK) * BS;
+        h0 = lds_f64o<0>(sa); h1 = lds_f64o<8>(sa); h2 = lds_f64o<16>(sa);
+    }
+    double m00, m01, m02, m10, m11, m12, m20, m21, m22, i0, i1, i2, v10, v20, v21, z0, z1, z2;
+    unsigned ta;
+#define CHAIN_LOAD(REC)                                                  \
+    do {                                                                 \
+        const unsigned a_ = lvA + (unsigned)(REC).x * 8u;                \
+        const unsigned h_ = lvA + (unsigned)(REC).y * 8u;                \
+        ta = xA + (unsigned)((REC).z & OP_BLK_MASK) * BS;                \
+        lds_v2o<0>(a_, m00, m01);                                        \
+        lds_v2o<16>(a_, m02, m10);                                       \
+        lds_v2o<32>(a_, m11, m12);                                       \
+        lds_v2o<48>(a_, m20, m21);                                       \
+        m22 = lds_f64o<64>(a_);                                          \
+        lds_v2o<0>(h_, i0, i1);                                          \
+        lds_v2o<16>(h_, i2, v10);                                        \
+        lds_v2o<32>(h_, v20, v21);                                       \
+        z0 = lds_f64o<0>(ta); z1 = lds_f64o<8>(ta); z2 = lds_f64o<16>(ta); \
+    } while (0)
+    CHAIN_LOAD(r);
+    for (int k = 0; k < n; k++) {
+        const int4 rNN = lds_op(pos + 16u * (unsigned)(k + 2));
+        // L^T: column j of the off block against x(src)
+        const double a0 = fma(-m20, h2, fma(-m10, h1, fma(-m00, h0, z0 * i0)));
+        const double a1 = fma(-m21, h2, fma(-m11, h1, fma(-m01, h0, z1 * i1)));
+        const double a2 = fma(-m22, h2, fma(-m12, h1, fma(-m02, h0, z2 * i2)));
+        const double x1 = fma(v21, a2, a1), x0 = fma(v20, a2, fma(v10, a1, a0));
+        const unsigned tc = ta;
+        CHAIN_LOAD(rN);
+        sts_f64(tc, x0); sts_f64(tc + 8u, x1); sts_f64(tc + 16u, a2);
+        h0 = x0; h1 = x1; h2 = a2;
+        rN = rNN;
+    }
+#undef CHAIN_LOAD
+}
+
+// GENERIC run: per-op flags (blocks with several off blocks, blocks without any)
+template <bool FWD>
+__device__ __noinline__ void generic_run(const unsigned pos, const int n, const unsigned lvA, const unsigned xA, const unsigned BS)
+{
+    double h0 = 0, h1 = 0, h2 = 0, a0 = 0, a1 = 0, a2 = 0;
+    for (int k = 0; k < n; k++) {
+        const int4 r = lds_op(pos + 16u * (unsigned)k);
+        const int y = r.z;
+        const unsigned a_ = lvA + (unsigned)r.x * 8u, h_ = lvA + (unsigned)r.y * 8u;
+        const unsigned ta = xA + (unsigned)(y & OP_BLK_MASK) * BS;
+        if (y & OPF_FIRST) {
+            a0 = lds_f64o<0>(ta); a1 = lds_f64o<8>(ta); a2 = lds_f64o<16>(ta);
+            if (!FWD) { a0 *= lds_f64o<0>(h_); a1 *= lds_f64o<8>(h_); a2 *= lds_f64o<16>(h_); }
+        }
+        if (!(y & OPF_NOPULL)) {
+            double z0 = h0, z1 = h1, z2 = h2;
+            if (!(y & OPF_PREV)) {
+                const unsigned sa = xA + (unsigned)((y >> OP_SRC_SHIFT) & OP_BLK_MASK) * BS;
+                z0 = lds_f64o<0>(sa); z1 = lds_f64o<8>(sa); z2 = lds_f64o<16>(sa);
+            }
+            double m00, m01, m02, m10, m11, m12, m20, m21, m22;
+            lds_v2o<0>(a_, m00, m01);
+            lds_v2o<16>(a_, m02, m10);
+            lds_v2o<32>(a_, m11, m12);
+            lds_v2o<48>(a_, m20, m21);
+            m22 = lds_f64o<64>(a_);
+            if (FWD) {
+                a0 = fma(-m02, z2, fma(-m01, z1, fma(-m00, z0, a0)));
+                a1 = fma(-m12, z2, fma(-m11, z1, fma(-m10, z0, a1)));
+                a2 = fma(-m22, z2, fma(-m21, z1, fma(-m20, z0, a2)));
+            } else {
+                a0 = fma(-m20, z2, fma(-m10, z1, fma(-m00, z0, a0)));
+                a1 = fma(-m21, z2, fma(-m11, z1, fma(-m01, z0, a1)));
+                a2 = fma(-m22, z2, fma(-m12, z1, fma(-m02, z0, a2)));
+            }
+        }
+        if (y & OPF_LAST) {
+            const double v10 = lds_f64o<24>(h_), v20 = lds_f64o<32>(h_), v21 = lds_f64o<40>(h_);
+            if (FWD) { h0 = a0; h1 = fma(v10, a0, a1); h2 = fma(v21, a1, fma(v20, a0, a2)); }
+            else { h2 = a2; h1 = fma(v21, a2, a1); h0 = fma(v20, a2, fma(v10, a1, a0)); }
+            sts_f64(ta, h0); sts_f64(ta + 8u, h1); sts_f64(ta + 16u, h2);
+        }
+    }
+}
+
+template <bool FWD>
+__device__ __forceinline__ void walk_ops(unsigned pos, const unsigned lvA, const unsigned xA, const unsigned BS)
+{
+    for (;;) {
+        const int4 hdr = lds_op(pos);
+        const int n = hdr.x >> 1;
+        if (n == 0) break;
+        pos += 16u;
+        if (hdr.z == RUN_CHAIN) {
+            if (FWD) chain_fwd(pos, n, lvA, xA, BS);
+            else chain_bwd(pos, n, lvA, xA, BS);
+        } else generic_run<FWD>(pos, n, lvA, xA, BS);
+        pos += 16u * (unsigned)n;
+    }
+}
+
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T, const StaticLaunch L, const SolveCfg cfg)
 {
     extern __shared__ __align__(16) double smem_d[];
-    __shared__ int s_failCase, s_flag;
-    const int model = blockIdx.x;
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const int dof = T.dof, nB = T.nB;
-    const int CS = cfg.cs;
+    __shared__ int s_fail[2], s_flag[2];
+    const int tid = threadIdx.x;
+    // The solver warp keeps its scheduler (SM sub-partition 0 = warps 0, 4, 8, ...) to itself: its shared-memory
+    // loads would otherwise queue behind the global loads and stores of streaming warps in the same
+    // instruction queue.  Warps 4, 8, 12 only take part in the block-wide barriers.
+    const int warp = tid >> 5;
+    const bool streamer = (warp & 3) != 0;
+    const int st = (warp - (warp >> 2) - 1) * 32 + (tid & 31); // streaming thread index
+    const int dof = T.dof, nB = T.nB, CSP = cfg.casesPerPass;
     // Shared memory is addressed through 32-bit shared-window addresses and explicit ld/st.shared: generic
     // pointers into dynamic shared memory make the compiler re-derive the window base (S2R SR_CgaCtaId, an
     // XU-pipe instruction) inside every loop, which saturated the XU pipe in the first version of this kernel.
     const unsigned smA = (unsigned)__cvta_generic_to_shared(smem_d);
-    const unsigned lvA = smA + LV_PAD * 8u;                       // [-LV_PAD, nSlots + LV_PAD) factor of this model
-    const unsigned xsA = smA + (unsigned)(T.nSlots + 2 * LV_PAD) * 8u; // [nPad][CS]
-    const unsigned CS8 = (unsigned)CS * 8u;
-    const unsigned fstA = xsA + (unsigned)T.nPad * CS8;              // per-warp 32 x 7 staging tiles of the force phase
+    const unsigned opsA = smA; // forward list, backward list
+    const unsigned xbA = opsA + (unsigned)(T.nFwdOps + T.nBwdOps) * 16u;                   // [dof] DOF info, see below
+    const unsigned bbA = xbA + (unsigned)dof * 4u;                                         // [nB*6] xs byte offset or -1
+    const unsigned rpA = bbA + (unsigned)nB * 24u;                                         // [nSup+1]
+    const unsigned rcA = rpA + (unsigned)(T.nSup + 1) * 4u;                                // [nnzR] xs byte offset
+    const unsigned sdA = rcA + (unsigned)T.nnzR * 4u;                                      // [nSup] supported DOFs
+    const unsigned fst0 = (sdA + (unsigned)T.nSup * 4u + 15u) & ~15u;                      // staging tiles, one per streaming warp
+    const unsigned lvm0 = fst0 + (unsigned)(NS / 32) * FST_BYTES;
+    const unsigned lvmBytes = (unsigned)cfg.lvmDoubles * 8u, xsBytes = (unsigned)cfg.xsDoubles * 8u;
+    const unsigned xs0 = lvm0 + 2u * lvmBytes;
+    const unsigned BS = 8u * (unsigned)xs_block_doubles(CSP); // bytes of one block of xs: [cases][3] (+ pad)
 
-    if (tid == 0) {
-        s_failCase = 0x7fffffff;
-        s_flag = 0;
+    // ---- once per block: integer tables -> shared memory ----
+    auto xoff = [&](int r) { return r >= 0 ? (int)((unsigned)(r / 3) * BS + (unsigned)(r % 3) * 8u) : r; };
+    for (int k = tid; k < T.nFwdOps + T.nBwdOps; k += blockDim.x) {
+        const int4 r = k < T.nFwdOps ? __ldg(T.fwdOps + k) : __ldg(T.bwdOps + (k - T.nFwdOps));
+        asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(opsA + 16u * k), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
     }
-#define STAMP(i)                                                                              \
-    do {                                                                                      \
-        if (L.dbgClocks && tid == stampTid) L.dbgClocks[(size_t)model * 32 + (i)] = clock64();  \
+    // DOF info: xs byte offset (a multiple of 8) for a free DOF, else negative; bit 0 = supported, bit 1 = ignored
+    // (no stiffness: its load must be zero, model.go:424-437)
+    for (int g = tid; g < dof; g += blockDim.x) {
+        const int xr = __ldg(T.xrow + g);
+        sts_s32(xbA + 4u * g, (xr >= 0 ? xoff(xr) : (int)0x80000000) | (__ldg(T.supIndex + g) >= 0 ? 1 : 0) | (xr == -2 ? 2 : 0));
+    }
+    for (int k = tid; k < nB * 6; k += blockDim.x) sts_s32(bbA + 4u * k, xoff(__ldg(T.beamRows + k)));
+    for (int k = tid; k <= T.nSup; k += blockDim.x) sts_s32(rpA + 4u * k, __ldg(T.rptr + k));
+    for (int k = tid; k < T.nnzR; k += blockDim.x) sts_s32(rcA + 4u * k, xoff(__ldg(T.rcol + k)));
+    for (int k = tid; k < T.nSup; k += blockDim.x) sts_s32(sdA + 4u * k, __ldg(T.supDofs + k));
+    if (tid < 2) {
+        s_fail[tid] = 0x7fffffff;
+        s_flag[tid] = 0;
+    }
+    __syncthreads();
+
+    const int nMy = (L.nModels - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x; // models of this block
+    const int nIt = nMy * cfg.nPass;
+    long long tSolve = 0, tAll = L.dbgClocks ? clock64() : 0;
+    long long tPh[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // streaming sub-phases (HDB_DEBUG_CLOCKS)
+#define TICK(k)                                  \
+    do {                                         \
+        if (L.dbgClocks) {                       \
+            const long long t1_ = clock64();     \
+            tPh[k] += t1_ - t0;                  \
+            t0 = t1_;                            \
+        }                                        \
     } while (0)
-    const int stampTid = (((int)blockIdx.x / (cfg.nSM > 0 ? cfg.nSM : 148)) & 3) * 32;
-    STAMP(0);
-    // phase 0: factor of this model -> shared memory (strided gather from the interleaved workspace);
-    // eight independent loads in flight per thread
-    {
-        const double *w = L.W + model;
-        const size_t ld = (size_t)L.ld;
-        for (int s0 = 0; s0 < T.nSlots; s0 += NT * 8) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int s = s0 + u * NT + tid;
-                v[u] = s < T.nSlots ? w[(size_t)s * ld] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int s = s0 + u * NT + tid;
-                if (s < T.nSlots) sts_f64(lvA + (unsigned)s * 8u, v[u]);
-            }
-        }
-        for (int s = tid; s < LV_PAD; s += NT) {
-            sts_f64(lvA + (unsigned)(T.nSlots + s) * 8u, 0.0);
-            sts_f64(lvA - (unsigned)(LV_PAD - s) * 8u, 0.0);
-        }
-    }
-    const double *ksf = L.Ksf + (size_t)model * T.nnzR;
-    const int nSM = cfg.nSM > 0 ? cfg.nSM : 148;
-    const int solver = ((blockIdx.x / nSM) & 3) * 32; // co-resident CTAs put their solver warp on different SMSPs
-    // beams beyond the last full round of the block: their coefficients go to a small shared table once,
-    // so that the force phase never recomputes an element inside its case loop
-    const int nMain = (nB / NT) * NT, nRest = nB - nMain;
-    const unsigned crA = fstA + (unsigned)(SOL_MAX_THREADS / 32) * (32u * 7u * 8u);
-    if (L.forces && tid < nRest) {
-        const int b = nMain + tid;
-        const double *sec = L.sections + (size_t)model * nB * 3;
-        const BeamGeom g = beam_geom(T, b);
-        const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
-        const unsigned a = crA + (unsigned)tid * 64u;
-        sts_f64(a, cf.EFL); sts_f64(a + 8, cf.EJL3); sts_f64(a + 16, cf.EJL2); sts_f64(a + 24, cf.EJL);
-        sts_f64(a + 32, cf.EJL4); sts_f64(a + 40, g.c); sts_f64(a + 48, g.s);
-    }
-    constexpr int LC = 4; // load cases handled together by one work item of the streaming phases
-    bool badLoad = false;
-    int failC = 0x7fffffff;
 
-    for (int c0 = 0; c0 < L.nLC; c0 += cfg.casesPerPass) {
-        const int nc = min(cfg.casesPerPass, L.nLC - c0);
-        const double *p = L.loads + ((size_t)model * L.nLC + c0) * dof;
-        double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof : nullptr;
-        const int nItems = ((nc + LC - 1) / LC) * dof; // item = (group of LC cases, DOF); DOF fastest: coalesced
-        // phase 1: load cases -> xs (free rows), dummy rows = 0; model.go:692-696 and 424-437 checks.
-        // Four items per thread are in flight (16 independent coalesced loads).  The reaction output starts
-        // here as -p on supported DOFs (model.go:478) and 0 elsewhere; phase 3 adds K[r,:] d to it with one
-        // fire-and-forget reduction per entry, so p is never read twice.
-        for (int it0 = 0; it0 < nItems; it0 += NT * 4) {
-            double v[4][LC];
-            int gi[4], ci[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int it = it0 + u * NT + tid;
-                const int cg = it / dof;
-                gi[u] = it < nItems ? it - cg * dof : -1;
-                ci[u] = cg * LC;
-#pragma unroll
-                for (int j = 0; j < LC; j++)
-                    v[u][j] = (gi[u] >= 0 && ci[u] + j < nc) ? __ldcs(p + (size_t)(ci[u] + j) * dof + gi[u]) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (gi[u] < 0) continue;
-                const int g = gi[u], c = ci[u];
-                const int xr = __ldg(T.xrow + g);
-                const bool sup = orr && __ldg(T.supIndex + g) >= 0;
-                const unsigned xb = xsA + (unsigned)(xr >= 0 ? xr : 0) * CS8 + (unsigned)c * 8u;
-                double *po = orr ? orr + (size_t)c * dof + g : nullptr;
-#pragma unroll
-                for (int j = 0; j < LC; j++) {
-                    if (c + j >= nc) break;
-                    const double val = v[u][j];
-                    badLoad |= !(fabs(val) <= 1.7976931348623157e308);
-                    if (xr >= 0) sts_f64(xb + 8u * j, val);
-                    if (po) po[(size_t)j * dof] = sup ? -val : 0.0;
-                }
-                if (xr == -2) {
-#pragma unroll
-                    for (int j = 0; j < LC; j++)
-                        if (c + j < nc && v[u][j] != 0.0) failC = min(failC, c0 + c + j);
+    for (int i = 0; i < nIt + 2; i++) {
+        if (tid < 32) {
+            // ================= solver warp: item i-1 =================
+            if (i >= 1 && i <= nIt) {
+                const int it = i - 1, pass = it % cfg.nPass;
+                const int nc = min(CSP, L.nLC - pass * CSP);
+                const unsigned buf = (unsigned)(it & 1);
+                if (tid < nc) {
+                    const long long t0 = L.dbgClocks ? clock64() : 0;
+                    const unsigned tabA = lvm0 + buf * lvmBytes, xA = xs0 + buf * xsBytes + (unsigned)tid * 24u;
+                    walk_ops<true>(opsA, tabA, xA, BS);
+                    walk_ops<false>(opsA + 16u * (unsigned)T.nFwdOps, tabA, xA, BS);
+                    if (L.dbgClocks) tSolve += clock64() - t0;
                 }
             }
-        }
-        for (int idx = tid; idx < T.nDummy * nc; idx += NT) {
-            const int q = idx / nc, c = idx - q * nc;
-            sts_f64(xsA + (unsigned)__ldg(T.dummyPos + q) * CS8 + (unsigned)c * 8u, 0.0);
-        }
-        __syncthreads();
-        STAMP(1);
-
-        // phase 2: L z = p, then L^T x = D^-1 z; one lane per load case walks the block op lists
-        if (tid >= solver && tid < solver + nc) {
-            substitute<true>(T.fwdOps, T.nFwdOps, lvA, xsA, CS, tid - solver);
-            STAMP(2);
-            substitute<false>(T.bwdOps, T.nBwdOps, lvA, xsA, CS, tid - solver);
-        }
-        STAMP(3);
-        __syncthreads();
-        STAMP(4);
-
-        // phase 3a+b: displacements (model.go:446-451) and reactions (model.go:470-489: columns ascending,
-        // eliminated columns carry d = 0) added to the -p rows of phase 1 with one reduction per supported entry.
-        if (L.disp || orr) {
-            double *od0 = L.disp ? L.disp + ((size_t)model * L.nLC + c0) * dof : nullptr;
-            for (int it = tid; it < nItems; it += NT) {
-                const int cg = it / dof, g = it - cg * dof, c = cg * LC;
-                const int xr = __ldg(T.xrow + g);
-                if (od0) {
-                    double *od = od0 + (size_t)c * dof + g;
-                    const unsigned xb = xsA + (unsigned)(xr >= 0 ? xr : 0) * CS8 + (unsigned)c * 8u;
-                    double d[LC];
+        } else if (streamer) {
+            // ================= streaming warps =================
+            const unsigned buf = (unsigned)(i & 1);
+            const unsigned lvB = lvm0 + buf * lvmBytes, xsB = xs0 + buf * xsBytes;
+            long long t0 = L.dbgClocks ? clock64() : 0;
+            if (i >= 2) {
+                // ---------- recover item i-2: displacements, reactions, beam forces ----------
+                const int it = i - 2, pass = it % cfg.nPass;
+                const int model = (int)blockIdx.x + (it / cfg.nPass) * (int)gridDim.x;
+                const int c0 = pass * CSP, nc = min(CSP, L.nLC - c0);
+                const int nGroups = (nc + LC - 1) / LC;
+                double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof : nullptr;
+                const unsigned ksA = lvB + (unsigned)nB * 64u;
+                // the factor buffer is dead once the solve is over: it takes the beam coefficients and the
+                // reaction block K[sup, free] of the model (one coalesced read instead of a dependent global
+                // load per entry)
+                if (orr) {
+                    const double *ksf = L.Ksf + (size_t)model * T.nnzR;
+                    for (int q0 = 0; q0 < T.nnzR; q0 += NS * 4) {
+                        double v[4];
 #pragma unroll
-                    for (int j = 0; j < LC; j++) d[j] = (xr >= 0 && c + j < nc) ? lds_f64(xb + 8u * j) : 0.0;
+                        for (int u = 0; u < 4; u++) {
+                            const int q = q0 + u * NS + st;
+                            v[u] = q < T.nnzR ? __ldcs(ksf + q) : 0.0;
+                        }
 #pragma unroll
-                    for (int j = 0; j < LC; j++)
-                        if (c + j < nc) od[(size_t)j * dof] = d[j];
+                        for (int u = 0; u < 4; u++) {
+                            const int q = q0 + u * NS + st;
+                            if (q < T.nnzR) sts_f64(ksA + 8u * q, v[u]);
+                        }
+                    }
                 }
-                const int si = orr ? __ldg(T.supIndex + g) : -1;
-                if (si >= 0) {
-                    const int q0 = __ldg(T.rptr + si), q1 = __ldg(T.rptr + si + 1);
-                    double acc[LC];
+                TICK(0);
+                if (L.forces) {
+                    const double *sec = L.sections + (size_t)model * nB * 3;
+                    for (int b = st; b < nB; b += NS) {
+                        const BeamGeom g = beam_geom(T, b);
+                        const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
+                        const unsigned a = lvB + (unsigned)b * 8u, cs = (unsigned)nB * 8u; // component-major: conflict-free
+                        sts_f64(a, cf.EFL); sts_f64(a + cs, cf.EJL3); sts_f64(a + 2u * cs, cf.EJL2); sts_f64(a + 3u * cs, cf.EJL);
+                        sts_f64(a + 4u * cs, cf.EJL4); sts_f64(a + 5u * cs, g.c); sts_f64(a + 6u * cs, g.s);
+                        sts_s32(lvB + 7u * cs + (unsigned)b * 4u, (int)T.pinMask[b]);
+                    }
+                }
+                TICK(1);
+                // displacements (model.go:446-451): the [cases][dof] block of a model is one contiguous run, walked
+                // with a constant stride so that every store is base + immediate; (DOF, case) follow incrementally
+                if (L.disp) {
+                    double *ob = L.disp + ((size_t)model * L.nLC + c0) * dof + st;
+                    const int nFlat = nc * dof;
+                    int g = st % dof;
+                    unsigned cOff = (unsigned)(st / dof) * 24u;
+                    for (int f0 = 0; f0 < nFlat; f0 += NS * 4) {
 #pragma unroll
-                    for (int j = 0; j < LC; j++) acc[j] = 0.0;
-                    for (int q = q0; q < q1; q++) {
-                        const double kv = __ldg(ksf + q);
-                        const unsigned xa = xsA + (unsigned)__ldg(T.rcol + q) * CS8 + (unsigned)c * 8u;
+                        for (int u = 0; u < 4; u++) {
+                            if (f0 + u * NS + st < nFlat) {
+                                const int info = lds_s32(xbA + 4u * g);
+                                __stcs(ob + f0 + u * NS, info >= 0 ? lds_f64(xsB + (unsigned)info + cOff) : 0.0);
+                            }
+                            g += NS % dof; // NS, dof: g advances by NS per step
+                            cOff += (unsigned)(NS / dof) * 24u;
+                            if (g >= dof) { g -= dof; cOff += 24u; }
+                        }
+                    }
+                }
+                TICK(2);
+                bar_stream(NS); // coefficient table and reaction block complete
+                TICK(3);
+                // reactions (model.go:470-489: columns ascending, eliminated columns carry d = 0) added to the -p
+                // rows of the load stage with one reduction per entry; item = (group of LC cases, supported DOF)
+                if (orr) {
+                    const int nItems = nGroups * T.nSup;
+                    for (int w = st; w < nItems; w += NS) {
+                        const int cg = w / T.nSup, si = w - cg * T.nSup, c = cg * LC;
+                        const int q0 = lds_s32(rpA + 4u * si), q1 = lds_s32(rpA + 4u * si + 4u);
+                        double acc[LC];
+#pragma unroll
+                        for (int j = 0; j < LC; j++) acc[j] = 0.0;
+                        for (int q = q0; q < q1; q++) {
+                            const double kv = lds_f64(ksA + 8u * q);
+                            const unsigned xa = xsB + (unsigned)lds_s32(rcA + 4u * q) + (unsigned)c * 24u;
+#pragma unroll
+                            for (int j = 0; j < LC; j++)
+                                if (c + j < nc) acc[j] = fma(kv, lds_f64(xa + 24u * j), acc[j]);
+                        }
+                        double *pr = orr + (size_t)c * dof + lds_s32(sdA + 4u * si);
 #pragma unroll
                         for (int j = 0; j < LC; j++)
-                            if (c + j < nc) acc[j] = fma(kv, lds_f64(xa + 8u * j), acc[j]);
-                    }
-                    double *pr = orr + (size_t)c * dof + g;
-#pragma unroll
-                    for (int j = 0; j < LC; j++)
-                        if (c + j < nc) atomicAdd(pr + (size_t)j * dof, acc[j]); // RED: no return value
-                }
-            }
-        }
-        if (L.dbgClocks && (tid & 31) == 0 && (tid >> 5) < 8) L.dbgClocks[(size_t)model * 32 + 8 + (tid >> 5)] = clock64();
-        // phase 3c: beam end forces s = k (T Zo), model.go:455-468.  One thread per beam keeps the element
-        // coefficients in registers over all cases; the few beams beyond the last full round are spread case
-        // by case over the threads and take their coefficients from the shared table.
-        if (L.forces) {
-            double *out = L.forces + ((size_t)model * L.nLC + c0) * nB * 6;
-            const double *sec = L.sections + (size_t)model * nB * 3;
-            for (int b = tid; b < nMain; b += NT) {
-                const BeamGeom g = beam_geom(T, b);
-                const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
-                const uint32_t pm = T.pinMask[b];
-                unsigned ra[6];
-                bool rv[6];
-#pragma unroll
-                for (int e = 0; e < 6; e++) {
-                    const int r = __ldg(T.beamRows + b * 6 + e);
-                    rv[e] = r >= 0;
-                    ra[e] = xsA + (unsigned)(r >= 0 ? r : 0) * CS8;
-                }
-                const unsigned wb = fstA + (unsigned)(tid >> 5) * (32u * 7u * 8u);
-                const unsigned lane = tid & 31;
-                for (int c = 0; c < nc; c++) {
-                    double u[6], o[6];
-#pragma unroll
-                    for (int e = 0; e < 6; e++) u[e] = rv[e] ? lds_f64(ra[e] + (unsigned)c * 8u) : 0.0;
-                    if (pm == 0) beam_forces_rigid(cf, g.c, g.s, u, o);
-                    else { // keep u/o of the common path in registers: the out-of-line call gets its own copies
-                        double uu[6], oo[6];
-#pragma unroll
-                        for (int e = 0; e < 6; e++) uu[e] = u[e];
-                        beam_forces_pinned(cf, pm, g.c, g.s, uu, oo);
-#pragma unroll
-                        for (int e = 0; e < 6; e++) o[e] = oo[e];
-                    }
-                    // a full warp holds 32 consecutive beams = 192 consecutive doubles of the output row:
-                    // transpose through shared memory so that every store instruction writes one contiguous
-                    // 256-byte run (full sectors) instead of 16-byte pieces 48 bytes apart
-                    __syncwarp();
-#pragma unroll
-                    for (int e = 0; e < 6; e++) sts_f64(wb + (lane * 7u + e) * 8u, o[e]);
-                    __syncwarp();
-                    double *ow = out + ((size_t)c * nB + (b - (int)lane)) * 6;
-#pragma unroll
-                    for (int e = 0; e < 6; e++) {
-                        const unsigned q = e * 32u + lane;
-                        ow[q] = lds_f64(wb + ((q / 6u) * 7u + q % 6u) * 8u);
+                            if (c + j < nc) atomicAdd(pr + (size_t)j * dof, acc[j]); // RED: no return value
                     }
                 }
-            }
-            for (int it = tid; it < nRest * nc; it += NT) {
-                const int r = it / nc, c = it - r * nc, b = nMain + r;
-                const unsigned a = crA + (unsigned)r * 64u;
-                BeamCoef cf;
-                cf.EFL = lds_f64(a); cf.EJL3 = lds_f64(a + 8); cf.EJL2 = lds_f64(a + 16); cf.EJL = lds_f64(a + 24);
-                cf.EJL4 = lds_f64(a + 32);
-                const double gc = lds_f64(a + 40), gs = lds_f64(a + 48);
-                const uint32_t pm = T.pinMask[b];
-                double u[6], o[6];
+                TICK(4);
+                // beam end forces s = k (T Zo), model.go:455-468.  Unit of work of a warp = (32 consecutive beams,
+                // group of LC cases); the 192 results of one case go through the warp's staging tile so that every
+                // store instruction writes one contiguous 256-byte run instead of 8-byte pieces 48 bytes apart.
+                if (L.forces) {
+                    double *out = L.forces + ((size_t)model * L.nLC + c0) * nB * 6;
+                    const int nBG = (nB + 31) / 32, sw = st >> 5, nSW = NS >> 5;
+                    const unsigned lane = (unsigned)tid & 31u;
+                    const unsigned wb = fst0 + (unsigned)sw * FST_BYTES;
+                    for (int w = sw; w < nGroups * nBG; w += nSW) {
+                        const int cg = w / nBG, bg = w - cg * nBG, c = cg * LC;
+                        const int b = bg * 32 + (int)lane;
+                        const bool live = b < nB;
+                        const int nOut = min(32, nB - bg * 32) * 6; // doubles this warp writes per case
+                        const unsigned a = lvB + (unsigned)(live ? b : 0) * 8u, cs = (unsigned)nB * 8u;
+                        BeamCoef cf;
+                        cf.EFL = lds_f64(a); cf.EJL3 = lds_f64(a + cs); cf.EJL2 = lds_f64(a + 2u * cs); cf.EJL = lds_f64(a + 3u * cs);
+                        cf.EJL4 = lds_f64(a + 4u * cs);
+                        const double gc = lds_f64(a + 5u * cs), gs = lds_f64(a + 6u * cs);
+                        const uint32_t pm = live ? (uint32_t)lds_s32(lvB + 7u * cs + (unsigned)b * 4u) : 0u;
+                        unsigned ra[6];
+                        bool rv[6];
 #pragma unroll
-                for (int e = 0; e < 6; e++) {
-                    const int row = __ldg(T.beamRows + b * 6 + e);
-                    u[e] = row >= 0 ? lds_f64(xsA + (unsigned)row * CS8 + (unsigned)c * 8u) : 0.0;
+                        for (int e = 0; e < 6; e++) {
+                            const int r = live ? lds_s32(bbA + 4u * (unsigned)(b * 6 + e)) : -1;
+                            rv[e] = r >= 0;
+                            ra[e] = xsB + (unsigned)(r >= 0 ? r : 0) + (unsigned)c * 24u;
+                        }
+                        double *ow = out + ((size_t)c * nB + bg * 32) * 6;
+#pragma unroll
+                        for (int j = 0; j < LC; j++) {
+                            if (c + j >= nc) break;
+                            double u[6], o[6];
+#pragma unroll
+                            for (int e = 0; e < 6; e++) u[e] = rv[e] ? lds_f64(ra[e] + 24u * j) : 0.0;
+                            if (pm == 0) beam_forces_rigid(cf, gc, gs, u, o);
+                            else { // keep u/o of the common path in registers: the out-of-line call gets its own copies
+                                double uu[6], oo[6];
+#pragma unroll
+                                for (int e = 0; e < 6; e++) uu[e] = u[e];
+                                beam_forces_pinned(cf, pm, gc, gs, uu, oo);
+#pragma unroll
+                                for (int e = 0; e < 6; e++) o[e] = oo[e];
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int e = 0; e < 6; e++) sts_f64(wb + (lane * 7u + e) * 8u, o[e]);
+                            __syncwarp();
+                            double *oj = ow + (size_t)j * nB * 6;
+#pragma unroll
+                            for (int e = 0; e < 6; e++) {
+                                const unsigned q = e * 32u + lane;
+                                if ((int)q < nOut) __stcs(oj + q, lds_f64(wb + ((q / 6u) * 7u + q % 6u) * 8u));
+                            }
+                        }
+                    }
                 }
-                if (pm == 0) beam_forces_rigid(cf, gc, gs, u, o);
-                else {
-                    double uu[6], oo[6];
+                TICK(5);
+                bar_stream(NS); // every reader of this buffer is done: the load stage may overwrite it
+                TICK(6);
+            }
+            if (i < nIt) {
+                // ---------- load item i: factor, load cases, tables ----------
+                const int it = i, pass = it % cfg.nPass;
+                const int model = (int)blockIdx.x + (it / cfg.nPass) * (int)gridDim.x;
+                const int c0 = pass * CSP, nc = min(CSP, L.nLC - c0);
+                const int nGroups = (nc + LC - 1) / LC;
+                // factor of this model (strided gather from the interleaved workspace): the first eight slots of
+                // every thread stay in flight across the load-case loop below
+                const double *wf = L.W + model;
+                const size_t ld = (size_t)L.ld;
+                double fv[8];
 #pragma unroll
-                    for (int e = 0; e < 6; e++) uu[e] = u[e];
-                    beam_forces_pinned(cf, pm, gc, gs, uu, oo);
-#pragma unroll
-                    for (int e = 0; e < 6; e++) o[e] = oo[e];
+                for (int u = 0; u < 8; u++) {
+                    const int s = u * NS + st;
+                    fv[u] = (s < T.nSlots && !cfg.expNoGather) ? wf[(size_t)s * ld] : 1.0;
                 }
-                double *of = out + ((size_t)c * nB + b) * 6;
+                TICK(7);
+                // load cases -> xs (free rows), dummy rows = 0; checks of model.go:692-696 and 424-437.  The
+                // [cases][dof] block is one contiguous run walked with a constant stride: LOAD_U independent
+                // base + immediate loads per thread are in flight.  The reaction output starts here as -p on
+                // supported DOFs (model.go:478) and 0 elsewhere, so p is never read twice.
+                const double *pb = L.loads + ((size_t)model * L.nLC + c0) * dof + st;
+                double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof + st : nullptr;
+                const int nFlat = nc * dof;
+                bool badLoad = false;
+                int failC = 0x7fffffff;
+                {
+                    int g = st % dof;
+                    unsigned cOff = (unsigned)(st / dof) * 24u;
+                    for (int f0 = 0; f0 < nFlat; f0 += NS * LOAD_U) {
+                        double v[LOAD_U];
+                        const bool full = f0 + NS * LOAD_U <= nFlat;
+                        if (full) {
 #pragma unroll
-                for (int e = 0; e < 6; e++) of[e] = o[e];
-            }
-        }
-        if (L.dbgClocks && (tid & 31) == 0 && (tid >> 5) < 8) L.dbgClocks[(size_t)model * 32 + 16 + (tid >> 5)] = clock64();
-        __syncthreads(); // xs is reused by the next pass
-        STAMP(5);
-    }
-    if (badLoad) atomicMax(&s_flag, 1);
-    if (failC != 0x7fffffff) atomicMin(&s_failCase, failC);
-    __syncthreads();
-    if (tid == 0) {
-        int st = L.status[model];
-        if (st == HDB_STATUS_OK && s_flag) st = HDB_STATUS_NONFINITE;
-        if (st == HDB_STATUS_OK && s_failCase != 0x7fffffff) st = HDB_STATUS_IGNORE_LOAD;
-        L.status[model] = st;
-        if (L.failCase) L.failCase[model] = (s_failCase != 0x7fffffff) ? s_failCase : -1;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_solve_recover_tma: same pipeline, rows moved by the TMA unit (cp.async.bulk + mbarrier).
-//
-// A model's load block [nLC][dof] and its outputs are long contiguous rows, so every row crosses the
-// SM boundary as ONE bulk asynchronous copy: four load rows are always in flight into a shared-memory
-// ring without costing a register or an issue slot per element, results are staged row by row in the
-// same ring and leave with one bulk store each.  Preconditions (checked at launch, else the LDG/STG
-// kernel above runs): dof even and 16-byte aligned arrays (bulk copies move multiples of 16 bytes),
-// nB < 2 * blockDim (one beam per thread in registers, the rest through a small coefficient table).
-// ------------------------------------------------------------------------------------------------
-constexpr int TMA_DROWS = 4; // ring depth for rows of dof doubles (loads in, displacements out)
-constexpr int TMA_FROWS = 2; // ring depth for rows of nB*6 doubles (beam forces out)
-
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-struct TmaCfg {
-    int casesPerPass, cs;
-    int ringDoubles; // ring size in doubles: max(TMA_DROWS * dof, TMA_FROWS * nB * 6)
-    int nSM;
-};
-
-__global__ void __launch_bounds__(SOL_MAX_THREADS, 2) k_solve_recover_tma(const DevTopo T, const StaticLaunch L, const TmaCfg cfg)
-{
-    extern __shared__ __align__(16) double smem_d[];
-    __shared__ int s_failCase, s_flag;
-    __shared__ __align__(8) unsigned long long s_bar[TMA_DROWS];
-    const int model = blockIdx.x;
-    const int tid = threadIdx.x, NT = blockDim.x;
-    const int dof = T.dof, nB = T.nB;
-    const int CS = cfg.cs;
-    double *Lv = smem_d + LV_PAD;                // [-LV_PAD, nSlots + LV_PAD) factor of this model
-    double *xs = smem_d + T.nSlots + 2 * LV_PAD; // [nPad][CS]
-    double *ring = xs + (((size_t)T.nPad * CS + 1) & ~(size_t)1); // 16-byte aligned
-    double *coefRest = ring + cfg.ringDoubles;   // [nRest][8] coefficients of the beams beyond blockDim
-    const unsigned ringA = (unsigned)__cvta_generic_to_shared(ring);
-    const unsigned barA = (unsigned)__cvta_generic_to_shared(s_bar);
-    const unsigned rowDB = (unsigned)dof * 8u, rowFB = (unsigned)nB * 48u;
-
-    if (tid == 0) {
-        s_failCase = 0x7fffffff;
-        s_flag = 0;
-        for (int i = 0; i < TMA_DROWS; i++) mbar_init(barA + 8u * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    const int stampTid = (((int)blockIdx.x / cfg.nSM) & 3) * 32;
-    STAMP(0);
-    // phase 0: factor of this model -> shared memory (strided gather from the interleaved workspace)
-    {
-        const double *w = L.W + model;
-        const size_t ld = (size_t)L.ld;
-        for (int s0 = 0; s0 < T.nSlots; s0 += NT * 8) {
-            double v[8];
+                            for (int u = 0; u < LOAD_U; u++) v[u] = __ldcs(pb + f0 + u * NS);
+                        } else {
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int s = s0 + u * NT + tid;
-                v[u] = s < T.nSlots ? w[(size_t)s * ld] : 0.0;
-            }
+                            for (int u = 0; u < LOAD_U; u++) v[u] = f0 + u * NS + st < nFlat ? __ldcs(pb + f0 + u * NS) : 0.0;
+                        }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int s = s0 + u * NT + tid;
-                if (s < T.nSlots) Lv[s] = v[u];
-            }
-        }
-        for (int s = tid; s < LV_PAD; s += NT) Lv[T.nSlots + s] = Lv[s - LV_PAD] = 0.0;
-    }
-    const double *ksf = L.Ksf + (size_t)model * T.nnzR;
-    // per-thread DOF ownership (up to four DOFs) and beam ownership (one beam in registers)
-    int xr[4], si[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-        const int g = tid + u * NT;
-        xr[u] = g < dof ? __ldg(T.xrow + g) : -1;
-        si[u] = g < dof ? __ldg(T.supIndex + g) : -1;
-    }
-    const double *sec = L.sections + (size_t)model * nB * 3;
-    const bool haveBeam = tid < nB;
-    BeamCoef cfB{};
-    double gcB = 0, gsB = 0;
-    uint32_t pmB = 0;
-    int rowsB[6] = {-1, -1, -1, -1, -1, -1};
-    if (haveBeam && L.forces) {
-        const BeamGeom g = beam_geom(T, tid);
-        cfB = beam_coef(sec[3 * tid], sec[3 * tid + 1], sec[3 * tid + 2], g.length);
-        gcB = g.c;
-        gsB = g.s;
-        pmB = T.pinMask[tid];
-#pragma unroll
-        for (int e = 0; e < 6; e++) rowsB[e] = __ldg(T.beamRows + tid * 6 + e);
-    }
-    const int nRest = nB > NT ? nB - NT : 0;
-    if (tid < nRest && L.forces) {
-        const int b = NT + tid;
-        const BeamGeom g = beam_geom(T, b);
-        const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
-        double *cr = coefRest + tid * 8;
-        cr[0] = cf.EFL; cr[1] = cf.EJL3; cr[2] = cf.EJL2; cr[3] = cf.EJL; cr[4] = cf.EJL4; cr[5] = g.c; cr[6] = g.s;
-    }
-    __syncthreads(); // barriers initialised, factor and coefficient table in place
-    const int solver = ((blockIdx.x / cfg.nSM) & 3) * 32; // co-resident CTAs put their solver warp on different SMSPs
-    unsigned rowsDone = 0; // rows that went through the load ring so far (mbarrier phase bookkeeping)
-
-    for (int c0 = 0; c0 < L.nLC; c0 += cfg.casesPerPass) {
-        const int nc = min(cfg.casesPerPass, L.nLC - c0);
-        const double *p = L.loads + ((size_t)model * L.nLC + c0) * dof;
-        double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof : nullptr;
-        // ---- phase 1: load rows through the ring -> xs; reaction rows start as -p (model.go:478) ----
-        if (tid == 0) {
-            for (int c = 0; c < min(TMA_DROWS, nc); c++) {
-                const unsigned s = (rowsDone + c) % TMA_DROWS;
-                mbar_expect_tx(barA + 8u * s, rowDB);
-                bulk_g2s(ringA + s * rowDB, p + (size_t)c * dof, rowDB, barA + 8u * s);
-            }
-        }
-        for (int c = 0; c < nc; c++) {
-            const unsigned rd = rowsDone + c, s = rd % TMA_DROWS;
-            mbar_wait(barA + 8u * s, (rd / TMA_DROWS) & 1u);
-            double *row = ring + (size_t)s * dof;
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int g = tid + u * NT;
-                if (g >= dof) continue;
-                const double val = row[g];
-                if (!isfinite(val)) atomicMax(&s_flag, 1); // model.go:692-696
-                if (xr[u] >= 0) xs[xr[u] * CS + c] = val;
-                else if (xr[u] == -2 && val != 0.0) atomicMin(&s_failCase, c0 + c); // model.go:424-437
-                if (orr) row[g] = si[u] >= 0 ? -val : 0.0;
-            }
-            if (orr) fence_proxy_async();
-            __syncthreads();
-            if (tid == 0) {
-                if (orr) {
-                    bulk_s2g(orr + (size_t)c * dof, ringA + s * rowDB, rowDB);
-                    bulk_commit();
+                        for (int u = 0; u < LOAD_U; u++) {
+                            if (full || f0 + u * NS + st < nFlat) {
+                                const int info = lds_s32(xbA + 4u * g);
+                                const double val = v[u];
+                                badLoad |= !(fabs(val) <= 1.7976931348623157e308);
+                                if (info >= 0) sts_f64(xsB + (unsigned)info + cOff, val);
+                                if (orr) orr[f0 + u * NS] = (info & 1) ? -val : 0.0;
+                                if ((info & 2) && val != 0.0) failC = min(failC, c0 + (int)(cOff / 24u));
+                            }
+                            g += NS % dof;
+                            cOff += (unsigned)(NS / dof) * 24u;
+                            if (g >= dof) { g -= dof; cOff += 24u; }
+                        }
+                    }
                 }
-                if (c + TMA_DROWS < nc) { // refill this stage once the store has read it
-                    if (orr) bulk_wait_read<0>();
-                    mbar_expect_tx(barA + 8u * s, rowDB);
-                    bulk_g2s(ringA + s * rowDB, p + (size_t)(c + TMA_DROWS) * dof, rowDB, barA + 8u * s);
+                for (int idx = st; idx < T.nDummy * nc; idx += NS) {
+                    const int q = idx / nc, c = idx - q * nc;
+                    const int r = __ldg(T.dummyPos + q);
+                    sts_f64(xsB + (unsigned)(r / 3) * BS + (unsigned)(r % 3) * 8u + (unsigned)c * 24u, 0.0);
                 }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int s = u * NS + st;
+                    if (s < T.nSlots) sts_f64(lvB + (unsigned)s * 8u, fv[u]);
+                }
+                for (int s = 8 * NS + st; s < T.nSlots; s += NS) sts_f64(lvB + (unsigned)s * 8u, wf[(size_t)s * ld]);
+                if (badLoad) atomicMax(&s_flag[buf], 1);
+                if (failC != 0x7fffffff) atomicMin(&s_fail[buf], failC);
+                TICK(8);
+                bar_stream(NS);
+                TICK(9);
+                if (st == 0) { // status of this pass (model.go:424-437); passes of a model arrive in order
+                    int s = L.status[model];
+                    const int fc = s_fail[buf];
+                    if (s_flag[buf] && (s == HDB_STATUS_OK || s == HDB_STATUS_IGNORE_LOAD)) s = HDB_STATUS_NONFINITE;
+                    else if (s == HDB_STATUS_OK && fc != 0x7fffffff) s = HDB_STATUS_IGNORE_LOAD;
+                    L.status[model] = s;
+                    if (L.failCase) {
+                        const int old = pass == 0 ? -1 : L.failCase[model];
+                        L.failCase[model] = old >= 0 ? old : (fc != 0x7fffffff ? fc : -1);
+                    }
+                    s_fail[buf] = 0x7fffffff;
+                    s_flag[buf] = 0;
+                }
+                TICK(10);
             }
         }
-        rowsDone += nc;
-        for (int idx = tid; idx < T.nDummy * nc; idx += NT) {
-            const int q = idx / nc, c = idx - q * nc;
-            xs[__ldg(T.dummyPos + q) * CS + c] = 0.0;
-        }
-        if (tid == 0 && orr) bulk_wait<0>(); // the -p rows are in memory before phase 3 adds to them
         __syncthreads();
-        STAMP(1);
-
-        // ---- phase 2: L z = p, then L^T x = D^-1 z; one lane per load case walks the block op lists ----
-        if (tid >= solver && tid < solver + nc) {
-            substitute<true>(T.fwdOps, T.nFwdOps, (unsigned)__cvta_generic_to_shared(Lv), (unsigned)__cvta_generic_to_shared(xs), CS, tid - solver);
-            substitute<false>(T.bwdOps, T.nBwdOps, (unsigned)__cvta_generic_to_shared(Lv), (unsigned)__cvta_generic_to_shared(xs), CS, tid - solver);
-        }
-        STAMP(3);
-        __syncthreads();
-        STAMP(4);
-
-        // ---- phase 3a: reactions, model.go:470-489: one fire-and-forget reduction per supported entry ----
-        if (orr) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (si[u] < 0) continue;
-                const int g = tid + u * NT;
-                const int q0 = __ldg(T.rptr + si[u]), q1 = __ldg(T.rptr + si[u] + 1);
-                for (int c = 0; c < nc; c += 4) {
-                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                    for (int q = q0; q < q1; q++) {
-                        const double kv = __ldg(ksf + q);
-                        const double *xc = xs + __ldg(T.rcol + q) * CS + c;
-#pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (c + j < nc) acc[j] = fma(kv, xc[j], acc[j]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (c + j < nc) atomicAdd(orr + (size_t)(c + j) * dof + g, acc[j]); // RED: no return value
-                }
-            }
-        }
-        // ---- phase 3b: displacements (model.go:446-451), one bulk store per case row ----
-        if (L.disp) {
-            double *od = L.disp + ((size_t)model * L.nLC + c0) * dof;
-            for (int c = 0; c < nc; c++) {
-                const int s = c % TMA_DROWS;
-                if (tid == 0 && c >= TMA_DROWS) bulk_wait_read<TMA_DROWS - 1>();
-                __syncthreads();
-                double *row = ring + (size_t)s * dof;
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int g = tid + u * NT;
-                    if (g < dof) row[g] = xr[u] >= 0 ? xs[xr[u] * CS + c] : 0.0;
-                }
-                fence_proxy_async();
-                __syncthreads();
-                if (tid == 0) {
-                    bulk_s2g(od + (size_t)c * dof, ringA + s * rowDB, rowDB);
-                    bulk_commit();
-                }
-            }
-            if (tid == 0) bulk_wait_read<0>(); // the ring changes row size below
-        }
-        // ---- phase 3c: beam end forces s = k (T Zo), model.go:455-468; one bulk store per case row ----
-        if (L.forces) {
-            double *of = L.forces + ((size_t)model * L.nLC + c0) * nB * 6;
-            for (int c = 0; c < nc; c++) {
-                const int s = c % TMA_FROWS;
-                if (tid == 0 && c >= TMA_FROWS) bulk_wait_read<TMA_FROWS - 1>();
-                __syncthreads();
-                double *row = ring + (size_t)s * nB * 6;
-                if (haveBeam) {
-                    double u[6];
-#pragma unroll
-                    for (int e = 0; e < 6; e++) u[e] = rowsB[e] >= 0 ? xs[rowsB[e] * CS + c] : 0.0;
-                    double o[6];
-                    if (pmB == 0) beam_forces_rigid(cfB, gcB, gsB, u, o);
-                    else {
-                        double uu[6], oo[6];
-#pragma unroll
-                        for (int e = 0; e < 6; e++) uu[e] = u[e];
-                        beam_forces_pinned(cfB, pmB, gcB, gsB, uu, oo);
-#pragma unroll
-                        for (int e = 0; e < 6; e++) o[e] = oo[e];
-                    }
-#pragma unroll
-                    for (int e = 0; e < 6; e++) row[tid * 6 + e] = o[e];
-                }
-                if (tid < nRest) {
-                    const int b = NT + tid;
-                    const double *cr = coefRest + tid * 8;
-                    BeamCoef cf;
-                    cf.EFL = cr[0]; cf.EJL3 = cr[1]; cf.EJL2 = cr[2]; cf.EJL = cr[3]; cf.EJL4 = cr[4];
-                    double u[6];
-#pragma unroll
-                    for (int e = 0; e < 6; e++) {
-                        const int r = __ldg(T.beamRows + b * 6 + e);
-                        u[e] = r >= 0 ? xs[r * CS + c] : 0.0;
-                    }
-                    const uint32_t pm = T.pinMask[b];
-                    double o[6];
-                    if (pm == 0) beam_forces_rigid(cf, cr[5], cr[6], u, o);
-                    else {
-                        double uu[6], oo[6];
-#pragma unroll
-                        for (int e = 0; e < 6; e++) uu[e] = u[e];
-                        beam_forces_pinned(cf, pm, cr[5], cr[6], uu, oo);
-#pragma unroll
-                        for (int e = 0; e < 6; e++) o[e] = oo[e];
-                    }
-#pragma unroll
-                    for (int e = 0; e < 6; e++) row[b * 6 + e] = o[e];
-                }
-                fence_proxy_async();
-                __syncthreads();
-                if (tid == 0) {
-                    bulk_s2g(of + (size_t)c * nB * 6, ringA + (unsigned)s * rowFB, rowFB);
-                    bulk_commit();
-                }
-            }
-        }
-        if (tid == 0) bulk_wait_read<0>(); // ring and xs are reused by the next pass
-        __syncthreads();
-        STAMP(5);
     }
-    if (tid == 0) {
-        bulk_wait<0>();
-        int st = L.status[model];
-        if (st == HDB_STATUS_OK && s_flag) st = HDB_STATUS_NONFINITE;
-        if (st == HDB_STATUS_OK && s_failCase != 0x7fffffff) st = HDB_STATUS_IGNORE_LOAD;
-        L.status[model] = st;
-        if (L.failCase) L.failCase[model] = (s_failCase != 0x7fffffff) ? s_failCase : -1;
+    if (L.dbgClocks) {
+        long long *d = L.dbgClocks + (size_t)blockIdx.x * 32;
+        if (tid == 0) { d[0] = clock64() - tAll; d[1] = tSolve; d[2] = nMy; }
+        if (tid == 32) // streaming warp 1
+            for (int k = 0; k < 16; k++) d[8 + k] = tPh[k];
     }
-}
-
-static bool tma_eligible(const DevTopo &T, const StaticLaunch &L, int threads)
-{
-    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    if (T.dof % 2 != 0 || T.dof > 4 * threads || T.nB >= 2 * threads) return false;
-    if (!al16(L.loads) || !al16(L.disp) || !al16(L.forces) || !al16(L.react)) return false;
-    return true;
 }
 
 cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaStream_t st)
@@ -1146,34 +968,18 @@ cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaSt
     SolveCfg cfg;
     size_t smem = 0;
     if (!solve_config(T, L.nLC, optin, cfg.casesPerPass, smem)) return cudaErrorInvalidConfiguration;
-    cfg.cs = odd_stride(cfg.casesPerPass);
-    cfg.nSM = nSM;
-    const int threads = solve_threads(T);
-    static const bool useTma = std::getenv("HDB_USE_TMA") != nullptr; // experimental: slower than the LDG/STG kernel so far
-    if (useTma && tma_eligible(T, L, threads)) {
-        TmaCfg tc;
-        tc.casesPerPass = cfg.casesPerPass;
-        tc.cs = cfg.cs;
-        tc.nSM = nSM;
-        const size_t ring = std::max<size_t>((size_t)TMA_DROWS * T.dof, (size_t)TMA_FROWS * T.nB * 6);
-        tc.ringDoubles = (int)((ring + 1) & ~(size_t)1);
-        const int nRest = T.nB > threads ? T.nB - threads : 0;
-        const size_t xsD = (((size_t)T.nPad * cfg.cs + 1) & ~(size_t)1);
-        const size_t bytes = ((size_t)(T.nSlots + 2 * LV_PAD) + xsD + tc.ringDoubles + (size_t)nRest * 8) * sizeof(double);
-        if (bytes + 2048 <= (size_t)optin) {
-            if (bytes > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(k_solve_recover_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-                if (e != cudaSuccess) return e;
-            }
-            k_solve_recover_tma<<<L.nModels, threads, bytes, st>>>(T, L, tc);
-            return cudaGetLastError();
-        }
-    }
+    cfg.nPass = (L.nLC + cfg.casesPerPass - 1) / cfg.casesPerPass;
+    if (cfg.nPass < 1) cfg.nPass = 1;
+    cfg.lvmDoubles = (int)pipe_lvm_doubles(T);
+    cfg.expNoGather = std::getenv("HDB_EXP_NOGATHER") != nullptr;
+    cfg.xsDoubles = T.nBlk * xs_block_doubles(cfg.casesPerPass);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_solve_recover, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_solve_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_solve_recover<<<L.nModels, threads, smem, st>>>(T, L, cfg);
+    const int grid = L.nModels < nSM ? L.nModels : nSM;
+    if (L.dbgClocks) std::fprintf(stderr, "[hdb] k_solve_pipe: %d blocks, %zu bytes of shared memory, %d cases per pass\n", grid, smem, cfg.casesPerPass);
+    k_solve_pipe<<<grid, PIPE_THREADS, smem, st>>>(T, L, cfg);
     return cudaGetLastError();
 }
 

@@ -565,6 +565,7 @@ int build_symbolic(int32_t nP, const double *points, int32_t nB, const hdb_beam 
     for (int I = 0; I < nBlk; I++) S.fwdPtr[I + 1] += S.fwdPtr[I];
     S.fwdJ.resize(nOff);
     S.fwdSlot.resize(nOff);
+    S.fwdQ.resize(nOff);
     {
         std::vector<int32_t> w(S.fwdPtr.begin(), S.fwdPtr.end() - 1);
         for (int J = 0; J < nBlk; J++) // ascending J inside every row
@@ -572,35 +573,65 @@ int build_symbolic(int32_t nP, const double *points, int32_t nB, const hdb_beam 
                 const int e = w[S.BLi[q]]++;
                 S.fwdJ[e] = J;
                 S.fwdSlot[e] = S.blkSlot[q];
+                S.fwdQ[e] = q;
             }
     }
 
-    // ---- substitution op lists (see device_topo.hpp): {slot, blk | flags | kind << 28} ----
-    auto rec = [](std::vector<int32_t> &v, int slot, int blk, int flags, int kind) {
-        v.push_back(slot);
-        v.push_back(blk | flags | (kind << 28));
+    // ---- substitution op lists (see device_topo.hpp) ----
+    // The factor kernel leaves every block column as header [1/d0 1/d1 1/d2 | v10 v20 v21] (V = Ldiag^-1) plus
+    // its off blocks L_IJ.  One op of the solver warp is acc(tgt) -= L x(src) (forward) or L^T x(src)
+    // (backward) on 3-vectors, with flags FIRST (acc starts from the right-hand side of tgt, scaled by D^-1 in
+    // the backward pass), LAST (x(tgt) = V acc resp. V^T acc is stored), PREV (src is the block stored by the
+    // op just before: still in registers) and NOPULL (block without off blocks in this direction).
+    // Ops are grouped into runs, each led by a header record {2 * count, 0, kind, 0}.  A CHAIN run is a
+    // sequence of ops that each make up a whole target block (FIRST and LAST) and pull from the target of the
+    // op before (the first one from any finished block): the common banded case, walked by a branch-free
+    // loop.  All other ops form GENERIC runs with per-op flags; PREV is relative to the run.
+    if (nBlk >= (1 << 14)) {
+        detail = "too many node blocks for the substitution op encoding";
+        return HDB_ERR_ARG;
+    }
+    const int FFIRST = 1 << 28, FPREV = 1 << 29, FLAST = 1 << 30, FNOPULL = (int)(1u << 31);
+    struct Op { int slot, src, tgt, flags; };
+    auto segment = [&](const std::vector<Op> &ops, std::vector<int32_t> &out) {
+        out.clear();
+        auto eligible = [&](const Op &o) { return (o.flags & FFIRST) && (o.flags & FLAST) && !(o.flags & FNOPULL); };
+        size_t k = 0;
+        while (k < ops.size()) {
+            size_t e = k + 1;
+            const bool chain = eligible(ops[k]);
+            if (chain) while (e < ops.size() && eligible(ops[e]) && ops[e].src == ops[e - 1].tgt) e++;
+            else while (e < ops.size() && !eligible(ops[e])) e++;
+            // header: an even first field and small other fields, because the chain loop's one-op-ahead prefetch
+            // may read (never use) a header as if it were an op
+            out.insert(out.end(), {(int32_t)(2 * (e - k)), 0, chain ? 1 : 0, 0});
+            int lastDone = -1;
+            for (size_t i = k; i < e; i++) {
+                int f = ops[i].flags;
+                if (!chain && !(f & FNOPULL) && ops[i].src == lastDone) f |= FPREV;
+                out.insert(out.end(), {ops[i].slot, S.colOff[ops[i].tgt], ops[i].tgt | (ops[i].src << 14) | f, 0});
+                if (f & FLAST) lastDone = ops[i].tgt;
+            }
+            k = e;
+        }
+        // two zero records end the list: a zero header stops the walk, and the prefetch may read past a run
+        out.insert(out.end(), 8, 0);
     };
-    const int KPULL = 0, KDIAG = 1, KFUSED = 2, FFIRST = 1 << 27, FPREV = 1 << 26;
-    for (int I = 0; I < nBlk; I++) { // forward: values laid out [off block 10 | header 6] from rec.slot
+    std::vector<Op> fo, bo;
+    for (int I = 0; I < nBlk; I++) {
         const int e0 = S.fwdPtr[I], e1 = S.fwdPtr[I + 1];
-        if (e1 - e0 == 1 && S.fwdJ[e0] == I - 1 && S.fwdSlot[e0] + BLK_STRIDE == S.colOff[I]) {
-            rec(S.fwdOps, S.fwdSlot[e0], I, FFIRST | FPREV, KFUSED);
-            continue;
-        }
+        if (e0 == e1) fo.push_back({S.colOff[I] + BLK_HDR, 0, I, FFIRST | FLAST | FNOPULL});
         for (int e = e0; e < e1; e++)
-            rec(S.fwdOps, S.fwdSlot[e], S.fwdJ[e], (e == e0 ? FFIRST : 0) | (S.fwdJ[e] == I - 1 ? FPREV : 0), KPULL);
-        rec(S.fwdOps, S.colOff[I] - BLK_STRIDE, I, (e0 == e1 ? FFIRST : 0), KDIAG);
+            fo.push_back({S.fwdSlot[e], S.fwdJ[e], I, (e == e0 ? FFIRST : 0) | (e == e1 - 1 ? FLAST : 0)});
     }
-    for (int J = nBlk - 1; J >= 0; J--) { // backward: [header 6 | off block 10] from rec.slot
+    for (int J = nBlk - 1; J >= 0; J--) {
         const int q0 = S.BLp[J], q1 = S.BLp[J + 1];
-        if (q1 - q0 == 1 && S.BLi[q0] == J + 1) {
-            rec(S.bwdOps, S.colOff[J], J, FFIRST | FPREV, KFUSED);
-            continue;
-        }
+        if (q0 == q1) bo.push_back({S.colOff[J] + BLK_HDR, 0, J, FFIRST | FLAST | FNOPULL});
         for (int q = q0; q < q1; q++)
-            rec(S.bwdOps, S.blkSlot[q] - BLK_HDR, S.BLi[q], (q == q0 ? FFIRST : 0) | (S.BLi[q] == J + 1 ? FPREV : 0), KPULL);
-        rec(S.bwdOps, S.colOff[J], J, (q0 == q1 ? FFIRST : 0), KDIAG);
+            bo.push_back({S.blkSlot[q], S.BLi[q], J, (q == q0 ? FFIRST : 0) | (q == q1 - 1 ? FLAST : 0)});
     }
+    segment(fo, S.fwdOps);
+    segment(bo, S.bwdOps);
     return HDB_OK;
 }
 

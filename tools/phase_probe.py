@@ -1,7 +1,8 @@
 """Phase-time probe of k_solve_recover (HDB_DEBUG_CLOCKS=1): which outputs cost what."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["HDB_DEBUG_CLOCKS"] = "1"
+if not os.environ.get("PROBE_NOCLK"):
+    os.environ["HDB_DEBUG_CLOCKS"] = "1"
 import numpy as np, torch
 from hd_b200 import _lib, frames
 from oracle import hd_oracle as oracle
