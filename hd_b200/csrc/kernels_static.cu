@@ -359,15 +359,15 @@ cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t 
 constexpr int PIPE_THREADS = 512; // warp 0 = solver, warps 4, 8, 12 idle, the other twelve stream
 constexpr int LC = 4;             // load cases handled together by one work item of the streaming stages
 constexpr int NS = PIPE_THREADS / 32 / 4 * 3 * 32; // streaming threads: the warps outside SM sub-partition 0
-constexpr int LOAD_U = 14;        // loads in flight per streaming thread in the load stage
-constexpr unsigned FST_BYTES = 32u * 7u * 8u; // per-warp 32 x 7 staging tile of the force stage
+constexpr int LOAD_U = 7;         // 16-byte loads in flight per streaming thread in the load stage
+constexpr unsigned FST_BYTES = 32u * 6u * 8u; // per-warp 32 x 6 staging tile of the force stage
 
 struct SolveCfg {
     int casesPerPass; // <= 32
     int nPass;        // passes over the load cases of a model (1 unless shared memory is short)
     int lvmDoubles;   // one factor/table buffer
     int xsDoubles;    // one xs buffer
-    int expNoGather;  // experiment (HDB_EXP_NOGATHER): skip the factor gather, results are wrong
+    int vec2;         // load and output arrays are 16-byte aligned and dof is even: 16-byte global accesses
 };
 
 // one block of xs = [cases][3] doubles, padded to an odd count: threads that read the same component of
@@ -379,14 +379,14 @@ static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 static size_t pipe_idx_bytes(const DevTopo &T)
 {
     return (size_t)(T.nFwdOps + T.nBwdOps) * 16 +
-           align16(((size_t)T.dof + (size_t)6 * T.nB + (size_t)2 * T.nSup + 1 + (size_t)T.nnzR) * 4) +
+           align16(((size_t)T.dof + (size_t)6 * T.nB + (size_t)2 * T.nSup + 1 + (size_t)T.nnzR + (size_t)T.nB) * 4) + (size_t)T.nB * 24 +
            (size_t)(NS / 32) * FST_BYTES + 32;
 }
 
 static size_t pipe_lvm_doubles(const DevTopo &T)
 {
     // solve: factor of the model; recovery: beam coefficients + reaction block K[sup, free] of the model
-    size_t d = std::max<size_t>((size_t)T.nSlots, (size_t)T.nB * 8 + (size_t)T.nnzR);
+    size_t d = std::max<size_t>((size_t)T.nSlots, (size_t)T.nB * 5 + (size_t)T.nnzR);
     return (d + 1) & ~(size_t)1;
 }
 
@@ -654,7 +654,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
     const unsigned rpA = bbA + (unsigned)nB * 24u;                                         // [nSup+1]
     const unsigned rcA = rpA + (unsigned)(T.nSup + 1) * 4u;                                // [nnzR] xs byte offset
     const unsigned sdA = rcA + (unsigned)T.nnzR * 4u;                                      // [nSup] supported DOFs
-    const unsigned fst0 = (sdA + (unsigned)T.nSup * 4u + 15u) & ~15u;                      // staging tiles, one per streaming warp
+    const unsigned pmA = sdA + (unsigned)T.nSup * 4u;                                      // [nB] pin masks
+    const unsigned gmA = (pmA + (unsigned)nB * 4u + 15u) & ~15u;                           // [3][nB] beam cos, sin, length
+    const unsigned fst0 = (gmA + (unsigned)nB * 24u + 15u) & ~15u;                         // staging tiles, one per streaming warp
     const unsigned lvm0 = fst0 + (unsigned)(NS / 32) * FST_BYTES;
     const unsigned lvmBytes = (unsigned)cfg.lvmDoubles * 8u, xsBytes = (unsigned)cfg.xsDoubles * 8u;
     const unsigned xs0 = lvm0 + 2u * lvmBytes;
@@ -676,6 +678,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
     for (int k = tid; k <= T.nSup; k += blockDim.x) sts_s32(rpA + 4u * k, __ldg(T.rptr + k));
     for (int k = tid; k < T.nnzR; k += blockDim.x) sts_s32(rcA + 4u * k, xoff(__ldg(T.rcol + k)));
     for (int k = tid; k < T.nSup; k += blockDim.x) sts_s32(sdA + 4u * k, __ldg(T.supDofs + k));
+    for (int b = tid; b < nB; b += blockDim.x) { // geometry is shared by all models: once per block
+        const BeamGeom g = beam_geom(T, b);
+        sts_f64(gmA + (unsigned)b * 8u, g.c);
+        sts_f64(gmA + (unsigned)(nB + b) * 8u, g.s);
+        sts_f64(gmA + (unsigned)(2 * nB + b) * 8u, g.length);
+        sts_s32(pmA + 4u * b, (int)T.pinMask[b]);
+    }
     if (tid < 2) {
         s_fail[tid] = 0x7fffffff;
         s_flag[tid] = 0;
@@ -722,8 +731,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 const int c0 = pass * CSP, nc = min(CSP, L.nLC - c0);
                 const int nGroups = (nc + LC - 1) / LC;
                 double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof : nullptr;
-                const unsigned ksA = lvB + (unsigned)nB * 64u;
-                // the factor buffer is dead once the solve is over: it takes the beam coefficients and the
+                const unsigned cs = (unsigned)nB * 8u, ksA = lvB + 5u * cs;
+                // the factor buffer is dead once the solve is over: it takes the beam coefficients [5][nB] and the
                 // reaction block K[sup, free] of the model (one coalesced read instead of a dependent global
                 // load per entry)
                 if (orr) {
@@ -746,31 +755,41 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 if (L.forces) {
                     const double *sec = L.sections + (size_t)model * nB * 3;
                     for (int b = st; b < nB; b += NS) {
-                        const BeamGeom g = beam_geom(T, b);
-                        const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
-                        const unsigned a = lvB + (unsigned)b * 8u, cs = (unsigned)nB * 8u; // component-major: conflict-free
+                        const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], lds_f64(gmA + (unsigned)(2 * nB + b) * 8u));
+                        const unsigned a = lvB + (unsigned)b * 8u; // component-major: conflict-free
                         sts_f64(a, cf.EFL); sts_f64(a + cs, cf.EJL3); sts_f64(a + 2u * cs, cf.EJL2); sts_f64(a + 3u * cs, cf.EJL);
-                        sts_f64(a + 4u * cs, cf.EJL4); sts_f64(a + 5u * cs, g.c); sts_f64(a + 6u * cs, g.s);
-                        sts_s32(lvB + 7u * cs + (unsigned)b * 4u, (int)T.pinMask[b]);
+                        sts_f64(a + 4u * cs, cf.EJL4);
                     }
                 }
                 TICK(1);
                 // displacements (model.go:446-451): the [cases][dof] block of a model is one contiguous run, walked
-                // with a constant stride so that every store is base + immediate; (DOF, case) follow incrementally
+                // in pairs with a constant stride so that every store is base + immediate; (DOF, case) follow
+                // incrementally
                 if (L.disp) {
-                    double *ob = L.disp + ((size_t)model * L.nLC + c0) * dof + st;
+                    double *ob = L.disp + ((size_t)model * L.nLC + c0) * dof + 2 * st;
                     const int nFlat = nc * dof;
-                    int g = st % dof;
-                    unsigned cOff = (unsigned)(st / dof) * 24u;
-                    for (int f0 = 0; f0 < nFlat; f0 += NS * 4) {
+                    int g = (2 * st) % dof;
+                    unsigned cOff = (unsigned)((2 * st) / dof) * 24u;
+                    for (int f0 = 0; f0 < nFlat; f0 += 2 * NS * 4) {
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
-                            if (f0 + u * NS + st < nFlat) {
-                                const int info = lds_s32(xbA + 4u * g);
-                                __stcs(ob + f0 + u * NS, info >= 0 ? lds_f64(xsB + (unsigned)info + cOff) : 0.0);
+                            const int f = f0 + 2 * (u * NS + st);
+                            if (f < nFlat) {
+                                int g1 = g + 1;
+                                unsigned c1 = cOff;
+                                if (g1 == dof) { g1 = 0; c1 += 24u; }
+                                const int i0 = lds_s32(xbA + 4u * g), i1 = lds_s32(xbA + 4u * g1);
+                                const double d0 = i0 >= 0 ? lds_f64(xsB + (unsigned)i0 + cOff) : 0.0;
+                                const double d1 = i1 >= 0 ? lds_f64(xsB + (unsigned)i1 + c1) : 0.0;
+                                double *o = ob + f0 + 2 * u * NS;
+                                if (cfg.vec2) __stcs(reinterpret_cast<double2 *>(o), make_double2(d0, d1));
+                                else {
+                                    __stcs(o, d0);
+                                    if (f + 1 < nFlat) __stcs(o + 1, d1);
+                                }
                             }
-                            g += NS % dof; // NS, dof: g advances by NS per step
-                            cOff += (unsigned)(NS / dof) * 24u;
+                            g += (2 * NS) % dof;
+                            cOff += (unsigned)((2 * NS) / dof) * 24u;
                             if (g >= dof) { g -= dof; cOff += 24u; }
                         }
                     }
@@ -804,7 +823,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 TICK(4);
                 // beam end forces s = k (T Zo), model.go:455-468.  Unit of work of a warp = (32 consecutive beams,
                 // group of LC cases); the 192 results of one case go through the warp's staging tile so that every
-                // store instruction writes one contiguous 256-byte run instead of 8-byte pieces 48 bytes apart.
+                // store instruction writes one contiguous run (512 bytes) instead of 8-byte pieces 48 bytes apart.
                 if (L.forces) {
                     double *out = L.forces + ((size_t)model * L.nLC + c0) * nB * 6;
                     const int nBG = (nB + 31) / 32, sw = st >> 5, nSW = NS >> 5;
@@ -815,12 +834,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                         const int b = bg * 32 + (int)lane;
                         const bool live = b < nB;
                         const int nOut = min(32, nB - bg * 32) * 6; // doubles this warp writes per case
-                        const unsigned a = lvB + (unsigned)(live ? b : 0) * 8u, cs = (unsigned)nB * 8u;
+                        const unsigned a = lvB + (unsigned)(live ? b : 0) * 8u;
                         BeamCoef cf;
                         cf.EFL = lds_f64(a); cf.EJL3 = lds_f64(a + cs); cf.EJL2 = lds_f64(a + 2u * cs); cf.EJL = lds_f64(a + 3u * cs);
                         cf.EJL4 = lds_f64(a + 4u * cs);
-                        const double gc = lds_f64(a + 5u * cs), gs = lds_f64(a + 6u * cs);
-                        const uint32_t pm = live ? (uint32_t)lds_s32(lvB + 7u * cs + (unsigned)b * 4u) : 0u;
+                        const unsigned ga = gmA + (unsigned)(live ? b : 0) * 8u;
+                        const double gc = lds_f64(ga), gs = lds_f64(ga + cs);
+                        const uint32_t pm = live ? (uint32_t)lds_s32(pmA + 4u * b) : 0u;
                         unsigned ra[6];
                         bool rv[6];
 #pragma unroll
@@ -847,13 +867,19 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                             }
                             __syncwarp();
 #pragma unroll
-                            for (int e = 0; e < 6; e++) sts_f64(wb + (lane * 7u + e) * 8u, o[e]);
+                            for (int e = 0; e < 6; e += 2)
+                                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(wb + (lane * 6u + e) * 8u), "d"(o[e]), "d"(o[e + 1]) : "memory");
                             __syncwarp();
                             double *oj = ow + (size_t)j * nB * 6;
 #pragma unroll
-                            for (int e = 0; e < 6; e++) {
-                                const unsigned q = e * 32u + lane;
-                                if ((int)q < nOut) __stcs(oj + q, lds_f64(wb + ((q / 6u) * 7u + q % 6u) * 8u));
+                            for (int e = 0; e < 3; e++) {
+                                const unsigned q = 2u * (e * 32u + lane); // doubles q, q+1 of the 192
+                                if ((int)q < nOut) {
+                                    double x, y;
+                                    lds_v2o<0>(wb + q * 8u, x, y);
+                                    if (cfg.vec2) __stcs(reinterpret_cast<double2 *>(oj + q), make_double2(x, y));
+                                    else { __stcs(oj + q, x); __stcs(oj + q + 1, y); }
+                                }
                             }
                         }
                     }
@@ -863,11 +889,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 TICK(6);
             }
             if (i < nIt) {
-                // ---------- load item i: factor, load cases, tables ----------
+                // ---------- load item i: factor, load cases ----------
                 const int it = i, pass = it % cfg.nPass;
                 const int model = (int)blockIdx.x + (it / cfg.nPass) * (int)gridDim.x;
                 const int c0 = pass * CSP, nc = min(CSP, L.nLC - c0);
-                const int nGroups = (nc + LC - 1) / LC;
+                const int sOld = st == 0 ? L.status[model] : 0; // needed at the end of the stage only
                 // factor of this model (strided gather from the interleaved workspace): the first eight slots of
                 // every thread stay in flight across the load-case loop below
                 const double *wf = L.W + model;
@@ -876,43 +902,63 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     const int s = u * NS + st;
-                    fv[u] = (s < T.nSlots && !cfg.expNoGather) ? wf[(size_t)s * ld] : 1.0;
+                    fv[u] = s < T.nSlots ? wf[(size_t)s * ld] : 0.0;
                 }
                 TICK(7);
                 // load cases -> xs (free rows), dummy rows = 0; checks of model.go:692-696 and 424-437.  The
-                // [cases][dof] block is one contiguous run walked with a constant stride: LOAD_U independent
-                // base + immediate loads per thread are in flight.  The reaction output starts here as -p on
-                // supported DOFs (model.go:478) and 0 elsewhere, so p is never read twice.
-                const double *pb = L.loads + ((size_t)model * L.nLC + c0) * dof + st;
-                double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof + st : nullptr;
+                // [cases][dof] block is one contiguous run walked in pairs with a constant stride: LOAD_U
+                // independent base + immediate 16-byte loads per thread are in flight.  The reaction output
+                // starts here as -p on supported DOFs (model.go:478) and 0 elsewhere, so p is never read twice.
+                const double *pb = L.loads + ((size_t)model * L.nLC + c0) * dof + 2 * st;
+                double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof + 2 * st : nullptr;
                 const int nFlat = nc * dof;
                 bool badLoad = false;
                 int failC = 0x7fffffff;
                 {
-                    int g = st % dof;
-                    unsigned cOff = (unsigned)(st / dof) * 24u;
-                    for (int f0 = 0; f0 < nFlat; f0 += NS * LOAD_U) {
-                        double v[LOAD_U];
-                        const bool full = f0 + NS * LOAD_U <= nFlat;
-                        if (full) {
+                    int g = (2 * st) % dof;
+                    unsigned cOff = (unsigned)((2 * st) / dof) * 24u;
+                    for (int f0 = 0; f0 < nFlat; f0 += 2 * NS * LOAD_U) {
+                        double2 v[LOAD_U];
+                        if (cfg.vec2 && f0 + 2 * NS * LOAD_U <= nFlat) {
 #pragma unroll
-                            for (int u = 0; u < LOAD_U; u++) v[u] = __ldcs(pb + f0 + u * NS);
+                            for (int u = 0; u < LOAD_U; u++) v[u] = __ldcs(reinterpret_cast<const double2 *>(pb + f0 + 2 * u * NS));
                         } else {
 #pragma unroll
-                            for (int u = 0; u < LOAD_U; u++) v[u] = f0 + u * NS + st < nFlat ? __ldcs(pb + f0 + u * NS) : 0.0;
+                            for (int u = 0; u < LOAD_U; u++) {
+                                const int f = f0 + 2 * (u * NS + st);
+                                if (cfg.vec2) v[u] = f < nFlat ? __ldcs(reinterpret_cast<const double2 *>(pb + f0 + 2 * u * NS)) : make_double2(0.0, 0.0);
+                                else {
+                                    v[u].x = f < nFlat ? __ldcs(pb + f0 + 2 * u * NS) : 0.0;
+                                    v[u].y = f + 1 < nFlat ? __ldcs(pb + f0 + 2 * u * NS + 1) : 0.0;
+                                }
+                            }
                         }
 #pragma unroll
                         for (int u = 0; u < LOAD_U; u++) {
-                            if (full || f0 + u * NS + st < nFlat) {
-                                const int info = lds_s32(xbA + 4u * g);
-                                const double val = v[u];
-                                badLoad |= !(fabs(val) <= 1.7976931348623157e308);
-                                if (info >= 0) sts_f64(xsB + (unsigned)info + cOff, val);
-                                if (orr) orr[f0 + u * NS] = (info & 1) ? -val : 0.0;
-                                if ((info & 2) && val != 0.0) failC = min(failC, c0 + (int)(cOff / 24u));
+                            const int f = f0 + 2 * (u * NS + st);
+                            if (f < nFlat) {
+                                int g1 = g + 1;
+                                unsigned c1 = cOff;
+                                if (g1 == dof) { g1 = 0; c1 += 24u; }
+                                const int i0 = lds_s32(xbA + 4u * g), i1 = f + 1 < nFlat ? lds_s32(xbA + 4u * g1) : (int)0x80000000;
+                                const double v0 = v[u].x, v1 = v[u].y;
+                                badLoad |= !(fabs(v0) <= 1.7976931348623157e308) | !(fabs(v1) <= 1.7976931348623157e308);
+                                if (i0 >= 0) sts_f64(xsB + (unsigned)i0 + cOff, v0);
+                                if (i1 >= 0) sts_f64(xsB + (unsigned)i1 + c1, v1);
+                                if (orr) {
+                                    const double r0 = (i0 & 1) ? -v0 : 0.0, r1 = (i1 & 1) ? -v1 : 0.0;
+                                    double *o = orr + f0 + 2 * u * NS;
+                                    if (cfg.vec2) *reinterpret_cast<double2 *>(o) = make_double2(r0, r1);
+                                    else {
+                                        o[0] = r0;
+                                        if (f + 1 < nFlat) o[1] = r1;
+                                    }
+                                }
+                                if (((i0 & 2) && v0 != 0.0)) failC = min(failC, c0 + (int)(cOff / 24u));
+                                if (((i1 & 2) && v1 != 0.0)) failC = min(failC, c0 + (int)(c1 / 24u));
                             }
-                            g += NS % dof;
-                            cOff += (unsigned)(NS / dof) * 24u;
+                            g += (2 * NS) % dof;
+                            cOff += (unsigned)((2 * NS) / dof) * 24u;
                             if (g >= dof) { g -= dof; cOff += 24u; }
                         }
                     }
@@ -934,11 +980,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 bar_stream(NS);
                 TICK(9);
                 if (st == 0) { // status of this pass (model.go:424-437); passes of a model arrive in order
-                    int s = L.status[model];
+                    int s = sOld;
                     const int fc = s_fail[buf];
                     if (s_flag[buf] && (s == HDB_STATUS_OK || s == HDB_STATUS_IGNORE_LOAD)) s = HDB_STATUS_NONFINITE;
                     else if (s == HDB_STATUS_OK && fc != 0x7fffffff) s = HDB_STATUS_IGNORE_LOAD;
-                    L.status[model] = s;
+                    if (s != sOld) L.status[model] = s;
                     if (L.failCase) {
                         const int old = pass == 0 ? -1 : L.failCase[model];
                         L.failCase[model] = old >= 0 ? old : (fc != 0x7fffffff ? fc : -1);
@@ -971,7 +1017,10 @@ cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaSt
     cfg.nPass = (L.nLC + cfg.casesPerPass - 1) / cfg.casesPerPass;
     if (cfg.nPass < 1) cfg.nPass = 1;
     cfg.lvmDoubles = (int)pipe_lvm_doubles(T);
-    cfg.expNoGather = std::getenv("HDB_EXP_NOGATHER") != nullptr;
+    {
+        auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        cfg.vec2 = (T.dof % 2 == 0) && al16(L.loads) && al16(L.disp) && al16(L.react) && al16(L.forces);
+    }
     cfg.xsDoubles = T.nBlk * xs_block_doubles(cfg.casesPerPass);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_solve_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
