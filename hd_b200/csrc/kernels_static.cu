@@ -632,6 +632,7 @@ __device__ __forceinline__ void walk_ops(unsigned pos, const unsigned lvA, const
     }
 }
 
+template <bool DBG> // DBG: per-phase cycle counters (HDB_DEBUG_CLOCKS); a separate instantiation keeps them out of the product's registers
 __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T, const StaticLaunch L, const SolveCfg cfg)
 {
     extern __shared__ __align__(16) double smem_d[];
@@ -693,11 +694,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
 
     const int nMy = (L.nModels - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x; // models of this block
     const int nIt = nMy * cfg.nPass;
-    long long tSolve = 0, tAll = L.dbgClocks ? clock64() : 0;
-    long long tPh[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // streaming sub-phases (HDB_DEBUG_CLOCKS)
+    long long tSolve = 0, tAll = DBG ? clock64() : 0;
+    long long tPh[DBG ? 16 : 1] = {0}; // streaming sub-phases
 #define TICK(k)                                  \
     do {                                         \
-        if (L.dbgClocks) {                       \
+        if (DBG) {                               \
             const long long t1_ = clock64();     \
             tPh[k] += t1_ - t0;                  \
             t0 = t1_;                            \
@@ -712,18 +713,18 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 const int nc = min(CSP, L.nLC - pass * CSP);
                 const unsigned buf = (unsigned)(it & 1);
                 if (tid < nc) {
-                    const long long t0 = L.dbgClocks ? clock64() : 0;
+                    const long long t0 = DBG ? clock64() : 0;
                     const unsigned tabA = lvm0 + buf * lvmBytes, xA = xs0 + buf * xsBytes + (unsigned)tid * 24u;
                     walk_ops<true>(opsA, tabA, xA, BS);
                     walk_ops<false>(opsA + 16u * (unsigned)T.nFwdOps, tabA, xA, BS);
-                    if (L.dbgClocks) tSolve += clock64() - t0;
+                    if (DBG) tSolve += clock64() - t0;
                 }
             }
         } else if (streamer) {
             // ================= streaming warps =================
             const unsigned buf = (unsigned)(i & 1);
             const unsigned lvB = lvm0 + buf * lvmBytes, xsB = xs0 + buf * xsBytes;
-            long long t0 = L.dbgClocks ? clock64() : 0;
+            long long t0 = DBG ? clock64() : 0;
             if (i >= 2) {
                 // ---------- recover item i-2: displacements, reactions, beam forces ----------
                 const int it = i - 2, pass = it % cfg.nPass;
@@ -850,17 +851,22 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                             ra[e] = xsB + (unsigned)(r >= 0 ? r : 0) + (unsigned)c * 24u;
                         }
                         double *ow = out + ((size_t)c * nB + bg * 32) * 6;
+                        // released ends are rare: a warp with any takes the out-of-line general element for all its
+                        // lanes, so that the rigid path never touches the local arrays that call needs
+                        const bool anyPin = __any_sync(0xffffffffu, pm != 0u);
 #pragma unroll
                         for (int j = 0; j < LC; j++) {
                             if (c + j >= nc) break;
-                            double u[6], o[6];
+                            double o[6];
+                            if (!anyPin) {
+                                double u[6];
 #pragma unroll
-                            for (int e = 0; e < 6; e++) u[e] = rv[e] ? lds_f64(ra[e] + 24u * j) : 0.0;
-                            if (pm == 0) beam_forces_rigid(cf, gc, gs, u, o);
-                            else { // keep u/o of the common path in registers: the out-of-line call gets its own copies
+                                for (int e = 0; e < 6; e++) u[e] = rv[e] ? lds_f64(ra[e] + 24u * j) : 0.0;
+                                beam_forces_rigid(cf, gc, gs, u, o);
+                            } else {
                                 double uu[6], oo[6];
 #pragma unroll
-                                for (int e = 0; e < 6; e++) uu[e] = u[e];
+                                for (int e = 0; e < 6; e++) uu[e] = rv[e] ? lds_f64(ra[e] + 24u * j) : 0.0;
                                 beam_forces_pinned(cf, pm, gc, gs, uu, oo);
 #pragma unroll
                                 for (int e = 0; e < 6; e++) o[e] = oo[e];
@@ -997,7 +1003,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
         }
         __syncthreads();
     }
-    if (L.dbgClocks) {
+    if (DBG) {
         long long *d = L.dbgClocks + (size_t)blockIdx.x * 32;
         if (tid == 0) { d[0] = clock64() - tAll; d[1] = tSolve; d[2] = nMy; }
         if (tid == 32) // streaming warp 1
@@ -1022,13 +1028,14 @@ cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaSt
         cfg.vec2 = (T.dof % 2 == 0) && al16(L.loads) && al16(L.disp) && al16(L.react) && al16(L.forces);
     }
     cfg.xsDoubles = T.nBlk * xs_block_doubles(cfg.casesPerPass);
+    auto kern = L.dbgClocks ? k_solve_pipe<true> : k_solve_pipe<false>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_solve_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const int grid = L.nModels < nSM ? L.nModels : nSM;
     if (L.dbgClocks) std::fprintf(stderr, "[hdb] k_solve_pipe: %d blocks, %zu bytes of shared memory, %d cases per pass\n", grid, smem, cfg.casesPerPass);
-    k_solve_pipe<<<grid, PIPE_THREADS, smem, st>>>(T, L, cfg);
+    kern<<<grid, PIPE_THREADS, smem, st>>>(T, L, cfg);
     return cudaGetLastError();
 }
 
