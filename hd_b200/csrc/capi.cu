@@ -62,7 +62,7 @@ struct hdb_topology {
     std::vector<void *> devAllocs;
     // workspace of the device path
     // two workspace sets: the assemble/factor stream prepares sub-batch i+1 while the solve stream works on i
-    double *Wbuf[2] = {nullptr, nullptr}, *Ksfbuf[2] = {nullptr, nullptr}, *keScratch = nullptr;
+    double *Wbuf[2] = {nullptr, nullptr}, *Lmbuf[2] = {nullptr, nullptr}, *Ksfbuf[2] = {nullptr, nullptr}, *keScratch = nullptr;
     cudaStream_t prepStream = nullptr;
     cudaEvent_t evFork = nullptr, evPrep[2] = {nullptr, nullptr}, evSolve[2] = {nullptr, nullptr}, evJoin = nullptr;
     long long *dbgClocks = nullptr; // HDB_DEBUG_CLOCKS=1: per-model phase stamps of k_solve_recover
@@ -206,8 +206,9 @@ static int ensure_workspace(hdb_topology *t, size_t models)
     CUDA_TRY(cudaDeviceSynchronize());
     for (int i = 0; i < 2; i++) {
         if (t->Wbuf[i]) cudaFree(t->Wbuf[i]);
+        if (t->Lmbuf[i]) cudaFree(t->Lmbuf[i]);
         if (t->Ksfbuf[i]) cudaFree(t->Ksfbuf[i]);
-        t->Wbuf[i] = t->Ksfbuf[i] = nullptr;
+        t->Wbuf[i] = t->Lmbuf[i] = t->Ksfbuf[i] = nullptr;
     }
     if (t->keScratch) cudaFree(t->keScratch);
     t->keScratch = nullptr;
@@ -220,6 +221,7 @@ static int ensure_workspace(hdb_topology *t, size_t models)
     }
     for (int i = 0; i < 2; i++) {
         CUDA_TRY(cudaMalloc(&t->Wbuf[i], (size_t)t->S.nSlots * ld * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&t->Lmbuf[i], (size_t)t->S.nSlots * ld * sizeof(double)));
         CUDA_TRY(cudaMalloc(&t->Ksfbuf[i], std::max<size_t>(1, models * (size_t)t->S.nnzR) * sizeof(double)));
     }
     if (!assemble_fits_smem(t->D, t->smemOptin))
@@ -346,6 +348,7 @@ void hdb_topology_destroy(hdb_topology *t)
         for (void *p : t->devAllocs) cudaFree(p);
         for (int i = 0; i < 2; i++) {
             if (t->Wbuf[i]) cudaFree(t->Wbuf[i]);
+            if (t->Lmbuf[i]) cudaFree(t->Lmbuf[i]);
             if (t->Ksfbuf[i]) cudaFree(t->Ksfbuf[i]);
             if (t->evPrep[i]) cudaEventDestroy(t->evPrep[i]);
             if (t->evSolve[i]) cudaEventDestroy(t->evSolve[i]);
@@ -570,6 +573,7 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
         L.status = status + m0;
         L.failCase = failCase ? failCase + m0 : nullptr;
         L.W = t->Wbuf[buf];
+        L.Lm = t->Lmbuf[buf];
         L.Ksf = t->Ksfbuf[buf];
         L.kval = kval ? kval + (size_t)m0 * S.nnzK : nullptr;
         L.keScratch = t->keScratch;

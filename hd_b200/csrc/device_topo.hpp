@@ -52,7 +52,8 @@ struct StaticLaunch {
     const double *loads;       // [nModels][nLC][dof]
     double *disp, *forces, *react; // outputs, any may be NULL
     int32_t *status, *failCase;    // failCase may be NULL
-    double *W;                 // [nSlots][ld] factor workspace, interleaved over models
+    double *W;                 // [nSlots][ld] factor workspace, interleaved over models (assembly -> factorization)
+    double *Lm;                // [ld][nSlots] finished factor, model-major (factorization -> solve)
     double *Ksf;               // [nModels][nnzR]
     double *kval;              // [nModels][nnzK] or NULL
     double *keScratch;         // [nModels][nB*KE_LD] or NULL (NULL = element matrices live in shared memory)

@@ -304,10 +304,13 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
                 }
             }
         }
-        // ---- block column J is final: stream it out ----
-        if (WS) {
+        // ---- block column J is final: stream it out, model-major.  The solve kernel reads a model's factor as
+        //      one contiguous run; the 8-byte pieces written here complete their sectors in L2 within a few
+        //      iterations, and this kernel (one warp per 32 models) is nowhere near a store-bandwidth limit ----
+        {
             const int end = base + BLK_HDR + BLK_STRIDE * nb;
-            for (int s2 = base; s2 < end; s2++) wg[(size_t)s2 * ld] = WIN(s2);
+            double *lm = L.Lm + (size_t)model * T.nSlots;
+            for (int s2 = base; s2 < end; s2++) lm[s2] = WIN(s2);
         }
     }
 #undef WIN
@@ -900,15 +903,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 const int model = (int)blockIdx.x + (it / cfg.nPass) * (int)gridDim.x;
                 const int c0 = pass * CSP, nc = min(CSP, L.nLC - c0);
                 const int sOld = st == 0 ? L.status[model] : 0; // needed at the end of the stage only
-                // factor of this model (strided gather from the interleaved workspace): the first eight slots of
-                // every thread stay in flight across the load-case loop below
-                const double *wf = L.W + model;
-                const size_t ld = (size_t)L.ld;
-                double fv[8];
+                // factor of this model: one contiguous run; the first eight pieces of every thread stay in flight
+                // across the load-case loop below
+                const double *wf = L.Lm + (size_t)model * T.nSlots + 2 * st;
+                double2 fv[4];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int s = u * NS + st;
-                    fv[u] = s < T.nSlots ? wf[(size_t)s * ld] : 0.0;
+                for (int u = 0; u < 4; u++) {
+                    const int s = 2 * (u * NS + st);
+                    fv[u] = s < T.nSlots ? __ldcs(reinterpret_cast<const double2 *>(wf + 2 * u * NS)) : make_double2(0.0, 0.0);
                 }
                 TICK(7);
                 // load cases -> xs (free rows), dummy rows = 0; checks of model.go:692-696 and 424-437.  The
@@ -975,11 +977,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                     sts_f64(xsB + (unsigned)(r / 3) * BS + (unsigned)(r % 3) * 8u + (unsigned)c * 24u, 0.0);
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int s = u * NS + st;
-                    if (s < T.nSlots) sts_f64(lvB + (unsigned)s * 8u, fv[u]);
+                for (int u = 0; u < 4; u++) {
+                    const int s = 2 * (u * NS + st);
+                    if (s < T.nSlots) asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(lvB + (unsigned)s * 8u), "d"(fv[u].x), "d"(fv[u].y) : "memory");
                 }
-                for (int s = 8 * NS + st; s < T.nSlots; s += NS) sts_f64(lvB + (unsigned)s * 8u, wf[(size_t)s * ld]);
+                for (int s = 2 * (4 * NS + st); s < T.nSlots; s += 2 * NS) {
+                    const double2 v = __ldcs(reinterpret_cast<const double2 *>(L.Lm + (size_t)model * T.nSlots + s));
+                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(lvB + (unsigned)s * 8u), "d"(v.x), "d"(v.y) : "memory");
+                }
                 if (badLoad) atomicMax(&s_flag[buf], 1);
                 if (failC != 0x7fffffff) atomicMin(&s_fail[buf], failC);
                 TICK(8);
