@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include "device_topo.hpp"
+#include "element.cuh"
 #include "hdb_internal.hpp"
 #include "modal.hpp"
 
@@ -143,6 +144,30 @@ static int ensure_device(hdb_topology *t)
     UP(dropped, dropped);
     UP(S.gptr, gptr);
     UP(pad(S.gsrc), gsrc);
+    { // fixed-width (ELL) copies of the two gather lists the solve path uses: [width][n], -1 = no contribution.
+      // Every index load of a slot is then independent and coalesced; widths above 8 keep the CSR walk.
+        auto ell = [](const std::vector<int32_t> &ptr, const std::vector<int32_t> &src, int n, int &width) {
+            width = 0;
+            for (int s2 = 0; s2 < n; s2++) width = std::max(width, ptr[s2 + 1] - ptr[s2]);
+            if (width > 8) width = 0;
+            std::vector<int32_t> o((size_t)width * n, -1);
+            for (int s2 = 0; s2 < n && width; s2++)
+                for (int k = ptr[s2]; k < ptr[s2 + 1]; k++) o[(size_t)(k - ptr[s2]) * n + s2] = src[k];
+            return o;
+        };
+        UP(ell(S.gptr, pad(S.gsrc), S.nSlots, D.gWidth), gEll);
+        UP(ell(S.rgptr, pad(S.rgsrc), S.nnzR, D.rgWidth), rgEll);
+        std::vector<double> geom((size_t)S.nB * 3);
+        for (int b = 0; b < S.nB; b++) { // same routines, same rounding as on the device (element.cuh)
+            const int n0 = S.beamN32[2 * b], n1 = S.beamN32[2 * b + 1];
+            const double x0 = S.points[2 * n0], y0 = S.points[2 * n0 + 1], x1 = S.points[2 * n1], y1 = S.points[2 * n1 + 1];
+            const double len = beam_length(x0, y0, x1, y1);
+            double c, sn;
+            beam_cs(x0, y0, x1, y1, len, c, sn);
+            geom[3 * b] = c; geom[3 * b + 1] = sn; geom[3 * b + 2] = len;
+        }
+        UP(geom, geom);
+    }
     UP(S.slotInit, slotInit);
     UP(S.rgptr, rgptr);
     UP(pad(S.rgsrc), rgsrc);

@@ -21,6 +21,7 @@ constexpr int OP_SRC_SHIFT = 14;
 struct DevTopo {
     int nP, nB, dof, nFree, nBlk, nPad, nSlots, nSup, nnzR, nnzK, nDummy, maxBlkCount, winNeed;
     int nFwdOps, nBwdOps; // records incl. run headers and terminators
+    int gWidth, rgWidth;  // widths of the ELL gather lists, 0 = use the CSR lists
     // geometry / topology (shared by every model of a batch)
     const double *points;      // [nP][2]
     const int32_t *beamN;      // [nB][2]
@@ -28,6 +29,8 @@ struct DevTopo {
     const uint8_t *dropped;    // [nB*36] 1 = matrix position absent from the representative pattern
     // assembly gather lists (codes are padded smem indices beam*KE_LD + local)
     const int32_t *gptr, *gsrc;   // factor slots
+    const int32_t *gEll, *rgEll;  // [gWidth][nSlots], [rgWidth][nnzR]: the same lists, fixed width, -1 = none
+    const double *geom;           // [nB][3] cos, sin, length of every beam (element.cuh routines, evaluated once on the host)
     const uint8_t *slotInit;      // [nSlots]
     const int32_t *rgptr, *rgsrc; // reaction entries
     const int32_t *kptr, *ksrc;   // full CSR pattern (tests)

@@ -33,13 +33,11 @@ struct BeamGeom {
 };
 
 __device__ __forceinline__ BeamGeom beam_geom(const DevTopo &T, int b)
-{
-    const int n0 = T.beamN[2 * b], n1 = T.beamN[2 * b + 1];
-    const double x0 = T.points[2 * n0], y0 = T.points[2 * n0 + 1];
-    const double x1 = T.points[2 * n1], y1 = T.points[2 * n1 + 1];
+{ // feBeam2d.go:142-172 evaluated once per topology on the host with the routines of element.cuh
     BeamGeom g;
-    g.length = beam_length(x0, y0, x1, y1);
-    beam_cs(x0, y0, x1, y1, g.length, g.c, g.s);
+    g.c = __ldg(T.geom + 3 * b);
+    g.s = __ldg(T.geom + 3 * b + 1);
+    g.length = __ldg(T.geom + 3 * b + 2);
     return g;
 }
 
@@ -87,19 +85,46 @@ __global__ void __launch_bounds__(ASM_MAX_THREADS) k_assemble(const DevTopo T, c
     if (flag) atomicMax(&s_flag, flag == HDB_STATUS_NONFINITE ? 100 : flag); // NONFINITE wins
     __syncthreads();
 
-    // phase B: gather; one thread per slot, contributions in beam order
-    for (int s = tid; s < T.nSlots; s += ASM_THREADS) {
-        double sum = T.slotInit[s] ? 1.0 : 0.0; // unit diagonal of a dummy unknown
-        const int q1 = T.gptr[s + 1];
-        for (int q = T.gptr[s]; q < q1; q++) sum = __dadd_rn(sum, ke[T.gsrc[q]]);
-        L.W[(size_t)s * L.ld + model] = sum;
+    // phase B: gather; one thread per slot, contributions in beam order.  The fixed-width lists make every
+    // index load independent and coalesced (the CSR walk is a chain of dependent global loads per slot).
+    if (T.gWidth > 0) {
+        for (int s = tid; s < T.nSlots; s += ASM_THREADS) {
+            int idx[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) idx[k] = k < T.gWidth ? __ldg(T.gEll + (size_t)k * T.nSlots + s) : -1;
+            double sum = T.slotInit[s] ? 1.0 : 0.0; // unit diagonal of a dummy unknown
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (idx[k] >= 0) sum = __dadd_rn(sum, ke[idx[k]]);
+            L.W[(size_t)s * L.ld + model] = sum;
+        }
+    } else {
+        for (int s = tid; s < T.nSlots; s += ASM_THREADS) {
+            double sum = T.slotInit[s] ? 1.0 : 0.0;
+            const int q1 = T.gptr[s + 1];
+            for (int q = T.gptr[s]; q < q1; q++) sum = __dadd_rn(sum, ke[T.gsrc[q]]);
+            L.W[(size_t)s * L.ld + model] = sum;
+        }
     }
     double *ksf = L.Ksf + (size_t)model * T.nnzR;
-    for (int s = tid; s < T.nnzR; s += ASM_THREADS) {
-        double sum = 0.0;
-        const int q1 = T.rgptr[s + 1];
-        for (int q = T.rgptr[s]; q < q1; q++) sum = __dadd_rn(sum, ke[T.rgsrc[q]]);
-        ksf[s] = sum;
+    if (T.rgWidth > 0) {
+        for (int s = tid; s < T.nnzR; s += ASM_THREADS) {
+            int idx[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) idx[k] = k < T.rgWidth ? __ldg(T.rgEll + (size_t)k * T.nnzR + s) : -1;
+            double sum = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (idx[k] >= 0) sum = __dadd_rn(sum, ke[idx[k]]);
+            ksf[s] = sum;
+        }
+    } else {
+        for (int s = tid; s < T.nnzR; s += ASM_THREADS) {
+            double sum = 0.0;
+            const int q1 = T.rgptr[s + 1];
+            for (int q = T.rgptr[s]; q < q1; q++) sum = __dadd_rn(sum, ke[T.rgsrc[q]]);
+            ksf[s] = sum;
+        }
     }
     if (L.kval) {
         double *kv = L.kval + (size_t)model * T.nnzK;
