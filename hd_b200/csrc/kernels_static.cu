@@ -51,7 +51,35 @@ __device__ __forceinline__ bool section_ok(double v)
 // ------------------------------------------------------------------------------------------------
 constexpr int ASM_MAX_THREADS = 512;
 
-__global__ void __launch_bounds__(ASM_MAX_THREADS) k_assemble(const DevTopo T, const StaticLaunch L)
+// gather of one slot from the fixed-width list: W index loads, all independent
+template <int W>
+__device__ __forceinline__ double gather_slot(const int32_t *__restrict__ ell, const int n, const int s, const double *ke, double sum)
+{
+    int idx[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) idx[k] = __ldg(ell + (size_t)k * n + s);
+#pragma unroll
+    for (int k = 0; k < W; k++)
+        if (idx[k] >= 0) sum = __dadd_rn(sum, ke[idx[k]]);
+    return sum;
+}
+__device__ __forceinline__ double gather_slot_w(const int w, const int32_t *__restrict__ ell, const int n, const int s, const double *ke,
+                                                double sum)
+{
+    switch (w) { // warp-uniform
+    case 1: return gather_slot<1>(ell, n, s, ke, sum);
+    case 2: return gather_slot<2>(ell, n, s, ke, sum);
+    case 3: return gather_slot<3>(ell, n, s, ke, sum);
+    case 4: return gather_slot<4>(ell, n, s, ke, sum);
+    case 5: return gather_slot<5>(ell, n, s, ke, sum);
+    case 6: return gather_slot<6>(ell, n, s, ke, sum);
+    case 7: return gather_slot<7>(ell, n, s, ke, sum);
+    default: return gather_slot<8>(ell, n, s, ke, sum);
+    }
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_assemble(const DevTopo T, const StaticLaunch L)
 {
     const int ASM_THREADS = blockDim.x; // one thread per beam when nB <= 512: a single round of element work
     extern __shared__ double smem_d[];
@@ -88,16 +116,9 @@ __global__ void __launch_bounds__(ASM_MAX_THREADS) k_assemble(const DevTopo T, c
     // phase B: gather; one thread per slot, contributions in beam order.  The fixed-width lists make every
     // index load independent and coalesced (the CSR walk is a chain of dependent global loads per slot).
     if (T.gWidth > 0) {
-        for (int s = tid; s < T.nSlots; s += ASM_THREADS) {
-            int idx[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) idx[k] = k < T.gWidth ? __ldg(T.gEll + (size_t)k * T.nSlots + s) : -1;
-            double sum = T.slotInit[s] ? 1.0 : 0.0; // unit diagonal of a dummy unknown
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (idx[k] >= 0) sum = __dadd_rn(sum, ke[idx[k]]);
-            L.W[(size_t)s * L.ld + model] = sum;
-        }
+        double *w = L.W + model;
+        for (int s = tid; s < T.nSlots; s += ASM_THREADS) // initial value 1: unit diagonal of a dummy unknown
+            w[(size_t)s * L.ld] = gather_slot_w(T.gWidth, T.gEll, T.nSlots, s, ke, T.slotInit[s] ? 1.0 : 0.0);
     } else {
         for (int s = tid; s < T.nSlots; s += ASM_THREADS) {
             double sum = T.slotInit[s] ? 1.0 : 0.0;
@@ -108,16 +129,7 @@ __global__ void __launch_bounds__(ASM_MAX_THREADS) k_assemble(const DevTopo T, c
     }
     double *ksf = L.Ksf + (size_t)model * T.nnzR;
     if (T.rgWidth > 0) {
-        for (int s = tid; s < T.nnzR; s += ASM_THREADS) {
-            int idx[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) idx[k] = k < T.rgWidth ? __ldg(T.rgEll + (size_t)k * T.nnzR + s) : -1;
-            double sum = 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                if (idx[k] >= 0) sum = __dadd_rn(sum, ke[idx[k]]);
-            ksf[s] = sum;
-        }
+        for (int s = tid; s < T.nnzR; s += ASM_THREADS) ksf[s] = gather_slot_w(T.rgWidth, T.rgEll, T.nnzR, s, ke, 0.0);
     } else {
         for (int s = tid; s < T.nnzR; s += ASM_THREADS) {
             double sum = 0.0;
@@ -146,13 +158,17 @@ bool assemble_fits_smem(const DevTopo &T, int smemOptin)
 cudaError_t launch_assemble(const DevTopo &T, const StaticLaunch &L, cudaStream_t st)
 {
     const size_t smem = L.keScratch ? 0 : (size_t)T.nB * KE_LD * sizeof(double);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
     int threads = ((T.nB + 31) / 32) * 32;
     threads = threads < 128 ? 128 : (threads > ASM_MAX_THREADS ? ASM_MAX_THREADS : threads);
-    k_assemble<<<L.nModels, threads, smem, st>>>(T, L);
+    // up to 320 threads two blocks share an SM (register budget set by the launch bounds); the carve-out
+    // preference keeps the driver from picking a shared-memory split that fits only one
+    auto kern = threads <= 320 ? k_assemble<320, 2> : k_assemble<ASM_MAX_THREADS, 1>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<L.nModels, threads, smem, st>>>(T, L);
     return cudaGetLastError();
 }
 
