@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -273,14 +273,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the first warm-up step to the end of the timed region (one step is a few ms, far
+    # below nvidia-smi's sampling period), and over untimed repeats of the same step if that is still too short
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_warm = time.time()
     for _ in range(args.warmup):
         step()
     barrier()
     assert int(d_status.abs().sum().item()) == 0, "a model failed"
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     topo.set_profiling(2)  # accumulate per-kernel CUDA-event times over the timed region
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -294,7 +296,14 @@ def main():
     kernel_ms = topo.last_kernel_ms()  # sums over every launch of the timed region
     topo.set_profiling(0)
     launches = _lib.launch_count() - launches0
+    extra = 0
+    while time.time() - t_warm < 0.6:  # same step, untimed: keeps the GPU under the same load for the sampler
+        step()
+        extra += 1
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = f"warm-up + timed region + {extra} untimed repeats of the same step (nvidia-smi -lms 20)"
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     bad = d_status.abs().sum().to(torch.float64).reshape(1)
     if world > 1:
@@ -340,9 +349,9 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_solve_recover) ----
+    # ---- roofline of the dominant kernel (k_solve_pipe) ----
     peaks, peak_src = measured_peaks()
-    names = ["k_assemble", "k_factor", "k_solve_recover"]
+    names = ["k_assemble", "k_factor", "k_solve_pipe"]
     sub = int(os.environ.get("HDB_SUB_BATCH", "4096"))
     n_launch = args.steps * ((M + sub - 1) // sub)
     roof = None
@@ -354,8 +363,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get("k_solve_recover_dram_bytes_per_launch")
-        roof = {"bound": "hbm", "kernel": "k_solve_recover", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                traffic = json.load(f).get("k_solve_pipe_dram_bytes_per_launch")
+        roof = {"bound": "hbm", "kernel": "k_solve_pipe", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                 "launch_ms": dur * 1e3, "models_per_launch": per_launch_models,
                 "kernel_ms_total": dict(zip(names, kernel_ms)), "kernel_share": {n: k / sum(kernel_ms) for n, k in zip(names, kernel_ms)}}

@@ -577,7 +577,11 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
     // the solve kernel of sub-batch i runs on the caller's stream (the factor kernel is a latency chain on
     // a few warps per SM and hides completely behind the bandwidth-bound solve).  Two workspace sets.
     const int nSub = (nModels + sb - 1) / sb;
-    const bool pipelined = solve && nSub > 1 && !t->keScratch && !t->dbgClocks;
+    // Overlapping the assembly/factorization of sub-batch i+1 with the solve of sub-batch i on a second stream
+    // stopped paying once the solve kernel became persistent (one block per SM holding ~210 kB of shared
+    // memory: the other kernels' blocks only get an SM when a solve block retires).  Opt-in for experiments.
+    static const bool wantOverlap = std::getenv("HDB_OVERLAP_PREP") != nullptr;
+    const bool pipelined = wantOverlap && solve && nSub > 1 && !t->keScratch && !t->dbgClocks;
     cudaStream_t ps = pipelined ? t->prepStream : st;
     if (pipelined) {
         CUDA_TRY(cudaEventRecord(t->evFork, st));

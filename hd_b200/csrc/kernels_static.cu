@@ -8,7 +8,7 @@
 //   k_factor         one THREAD per model (SIMT over models, workspace interleaved so every access is
 //                    coalesced): sparse LDL^T along the precomputed schedule; replaces
 //                    sparse.LU.Factorize (model.go:326-331).
-//   k_solve_recover  one CTA per model: load cases -> shared memory, forward / diagonal / backward
+//   k_solve_pipe     persistent block per SM, three-stage pipeline: load cases -> shared memory, forward / backward
 //                    substitution with one lane per load case (model.go:440), then displacement
 //                    unpack (model.go:446-451), beam end forces k*(T*d) (model.go:455-468) and
 //                    reactions -p + K[r,:]d (model.go:470-489), all written once, coalesced.
