@@ -403,6 +403,8 @@ cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t 
 constexpr int PIPE_THREADS = 512; // warp 0 = solver, warps 4, 8, 12 idle, the other twelve stream
 constexpr int LC = 4;             // load cases handled together by one work item of the streaming stages
 constexpr int NS = PIPE_THREADS / 32 / 4 * 3 * 32; // streaming threads: the warps outside SM sub-partition 0
+constexpr int NH = (PIPE_THREADS / 32 / 4 - 1) * 32; // helper threads: warps 4, 8, 12 of the solver's sub-partition
+constexpr int REACT_HELPER_PCT = 45;               // share of the reaction items the helper warps take
 constexpr int LOAD_U = 7;         // 16-byte loads in flight per streaming thread in the load stage
 constexpr unsigned FST_BYTES = 32u * 6u * 8u; // per-warp 32 x 6 staging tile of the force stage
 
@@ -523,7 +525,8 @@ __device__ __forceinline__ int lds_s32(unsigned a)
     return v;
 }
 __device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void bar_stream(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); }
+__device__ __forceinline__ void bar_stream(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); } // recover stage: streaming + helper warps
+__device__ __forceinline__ void bar_load(int n) { asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); }   // load stage: streaming warps
 
 // ---- the sequential part: one lane per load case walks the op runs (device_topo.hpp) -----------------
 // A block column of the factor in shared memory: header [1/d0 1/d1 1/d2 v10 v20 v21], off blocks L_IJ
@@ -749,6 +752,29 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
         }                                        \
     } while (0)
 
+    // reactions (model.go:470-489: columns ascending, eliminated columns carry d = 0) added to the -p rows of the
+    // load stage with one reduction per entry; item = (group of LC cases, supported DOF)
+    auto react_items = [&](double *orr, const unsigned xsB, const unsigned ksA, const int nc, const int first, const int end, const int stride) {
+        for (int w = first; w < end; w += stride) {
+            const int cg = w / T.nSup, si = w - cg * T.nSup, c = cg * LC;
+            const int q0 = lds_s32(rpA + 4u * si), q1 = lds_s32(rpA + 4u * si + 4u);
+            double acc[LC];
+#pragma unroll
+            for (int j = 0; j < LC; j++) acc[j] = 0.0;
+            for (int q = q0; q < q1; q++) {
+                const double kv = lds_f64(ksA + 8u * q);
+                const unsigned xa = xsB + (unsigned)lds_s32(rcA + 4u * q) + (unsigned)c * 24u;
+#pragma unroll
+                for (int j = 0; j < LC; j++)
+                    if (c + j < nc) acc[j] = fma(kv, lds_f64(xa + 24u * j), acc[j]);
+            }
+            double *pr = orr + (size_t)c * dof + lds_s32(sdA + 4u * si);
+#pragma unroll
+            for (int j = 0; j < LC; j++)
+                if (c + j < nc) atomicAdd(pr + (size_t)j * dof, acc[j]); // RED: no return value
+        }
+    };
+
     for (int i = 0; i < nIt + 2; i++) {
         if (tid < 32) {
             // ================= solver warp: item i-1 =================
@@ -840,31 +866,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                     }
                 }
                 TICK(2);
-                bar_stream(NS); // coefficient table and reaction block complete
+                bar_stream(NS + NH); // coefficient table and reaction block complete
                 TICK(3);
                 // reactions (model.go:470-489: columns ascending, eliminated columns carry d = 0) added to the -p
                 // rows of the load stage with one reduction per entry; item = (group of LC cases, supported DOF)
-                if (orr) {
-                    const int nItems = nGroups * T.nSup;
-                    for (int w = st; w < nItems; w += NS) {
-                        const int cg = w / T.nSup, si = w - cg * T.nSup, c = cg * LC;
-                        const int q0 = lds_s32(rpA + 4u * si), q1 = lds_s32(rpA + 4u * si + 4u);
-                        double acc[LC];
-#pragma unroll
-                        for (int j = 0; j < LC; j++) acc[j] = 0.0;
-                        for (int q = q0; q < q1; q++) {
-                            const double kv = lds_f64(ksA + 8u * q);
-                            const unsigned xa = xsB + (unsigned)lds_s32(rcA + 4u * q) + (unsigned)c * 24u;
-#pragma unroll
-                            for (int j = 0; j < LC; j++)
-                                if (c + j < nc) acc[j] = fma(kv, lds_f64(xa + 24u * j), acc[j]);
-                        }
-                        double *pr = orr + (size_t)c * dof + lds_s32(sdA + 4u * si);
-#pragma unroll
-                        for (int j = 0; j < LC; j++)
-                            if (c + j < nc) atomicAdd(pr + (size_t)j * dof, acc[j]); // RED: no return value
-                    }
-                }
+                if (orr) react_items(orr, xsB, ksA, nc, nGroups * T.nSup * REACT_HELPER_PCT / 100 + st, nGroups * T.nSup, NS);
                 TICK(4);
                 // beam end forces s = k (T Zo), model.go:455-468.  Unit of work of a warp = (32 consecutive beams,
                 // group of LC cases); the 192 results of one case go through the warp's staging tile so that every
@@ -935,7 +941,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                     }
                 }
                 TICK(5);
-                bar_stream(NS); // every reader of this buffer is done: the load stage may overwrite it
+                bar_stream(NS + NH); // every reader of this buffer is done: the load stage may overwrite it
                 TICK(6);
             }
             if (i < nIt) {
@@ -1029,7 +1035,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 if (badLoad) atomicMax(&s_flag[buf], 1);
                 if (failC != 0x7fffffff) atomicMin(&s_fail[buf], failC);
                 TICK(8);
-                bar_stream(NS);
+                bar_load(NS);
                 TICK(9);
                 if (st == 0) { // status of this pass (model.go:424-437); passes of a model arrive in order
                     int s = sOld;
@@ -1046,6 +1052,20 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 }
                 TICK(10);
             }
+        } else if (i >= 2) {
+            // ================= helper warps (4, 8, 12): a share of the reactions of item i-2 =================
+            // They live in the solver's sub-partition, so they get work that is almost all shared memory.
+            const int it = i - 2, pass = it % cfg.nPass;
+            const int model = (int)blockIdx.x + (it / cfg.nPass) * (int)gridDim.x;
+            const int c0 = pass * CSP, nc = min(CSP, L.nLC - c0);
+            const unsigned buf = (unsigned)(i & 1);
+            const unsigned lvB = lvm0 + buf * lvmBytes, xsB = xs0 + buf * xsBytes;
+            const int hx = ((warp >> 2) - 1) * 32 + (tid & 31);
+            bar_stream(NS + NH); // reaction block staged by the streaming warps
+            if (L.react)
+                react_items(L.react + ((size_t)model * L.nLC + c0) * dof, xsB, lvB + 5u * (unsigned)nB * 8u, nc, hx,
+                            ((nc + LC - 1) / LC) * T.nSup * REACT_HELPER_PCT / 100, NH);
+            bar_stream(NS + NH);
         }
         __syncthreads();
     }
