@@ -425,7 +425,7 @@ static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 static size_t pipe_idx_bytes(const DevTopo &T)
 {
     return (size_t)(T.nFwdOps + T.nBwdOps) * 16 +
-           align16(((size_t)T.dof + (size_t)6 * T.nB + (size_t)2 * T.nSup + 1 + (size_t)T.nnzR + (size_t)T.nB) * 4) + (size_t)T.nB * 24 +
+           align16(((size_t)T.dof + (size_t)6 * T.nB + (size_t)2 * T.nSup + 1 + (size_t)T.nnzR + (size_t)T.nB) * 4) + (size_t)T.nB * 24 + 128 +
            (size_t)(NS / 32) * FST_BYTES + 32;
 }
 
@@ -491,7 +491,7 @@ __device__ __forceinline__ void beam_forces_rigid(const BeamCoef &cf, const doub
     o[0] = ax; o[1] = sh; o[2] = m0; o[3] = -ax; o[4] = -sh; o[5] = m1;
 }
 
-__device__ __noinline__ void beam_forces_pinned(const BeamCoef &cf, const uint32_t pm, const double gc, const double gs,
+__device__ __noinline__ void beam_forces_pinned(const BeamCoef cf, const uint32_t pm, const double gc, const double gs, // cf by value: a reference would pin the caller's copy to local memory
                                                 const double *u, double *o)
 { // released ends: the condensed matrix is dense
     double k[36], z[6];
@@ -704,7 +704,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
     const unsigned sdA = rcA + (unsigned)T.nnzR * 4u;                                      // [nSup] supported DOFs
     const unsigned pmA = sdA + (unsigned)T.nSup * 4u;                                      // [nB] pin masks
     const unsigned gmA = (pmA + (unsigned)nB * 4u + 15u) & ~15u;                           // [3][nB] beam cos, sin, length
-    const unsigned fst0 = (gmA + (unsigned)nB * 24u + 15u) & ~15u;                         // staging tiles, one per streaming warp
+    const unsigned zeroA = (gmA + (unsigned)nB * 24u + 15u) & ~15u;                        // 96 zero bytes: "row" of a supported DOF
+    const unsigned fst0 = zeroA + 96u;                                                     // staging tiles, one per streaming warp
     const unsigned lvm0 = fst0 + (unsigned)(NS / 32) * FST_BYTES;
     const unsigned lvmBytes = (unsigned)cfg.lvmDoubles * 8u, xsBytes = (unsigned)cfg.xsDoubles * 8u;
     const unsigned xs0 = lvm0 + 2u * lvmBytes;
@@ -733,6 +734,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
         sts_f64(gmA + (unsigned)(2 * nB + b) * 8u, g.length);
         sts_s32(pmA + 4u * b, (int)T.pinMask[b]);
     }
+    if (tid < 12) sts_f64(zeroA + 8u * tid, 0.0);
     if (tid < 2) {
         s_fail[tid] = 0x7fffffff;
         s_flag[tid] = 0;
@@ -884,26 +886,49 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                         const int cg = w / nBG, bg = w - cg * nBG, c = cg * LC;
                         const int b = bg * 32 + (int)lane;
                         const bool live = b < nB;
-                        const int nOut = min(32, nB - bg * 32) * 6; // doubles this warp writes per case
-                        const unsigned a = lvB + (unsigned)(live ? b : 0) * 8u;
+                        const int bl = live ? b : 0;
+                        const unsigned a = lvB + (unsigned)bl * 8u;
                         BeamCoef cf;
                         cf.EFL = lds_f64(a); cf.EJL3 = lds_f64(a + cs); cf.EJL2 = lds_f64(a + 2u * cs); cf.EJL = lds_f64(a + 3u * cs);
                         cf.EJL4 = lds_f64(a + 4u * cs);
-                        const unsigned ga = gmA + (unsigned)(live ? b : 0) * 8u;
+                        const unsigned ga = gmA + (unsigned)bl * 8u;
                         const double gc = lds_f64(ga), gs = lds_f64(ga + cs);
                         const uint32_t pm = live ? (uint32_t)lds_s32(pmA + 4u * b) : 0u;
-                        unsigned ra[6];
-                        bool rv[6];
+                        unsigned ra[6]; // xs address of the beam's six DOFs for case c; supported DOFs read the zero row
 #pragma unroll
                         for (int e = 0; e < 6; e++) {
-                            const int r = live ? lds_s32(bbA + 4u * (unsigned)(b * 6 + e)) : -1;
-                            rv[e] = r >= 0;
-                            ra[e] = xsB + (unsigned)(r >= 0 ? r : 0) + (unsigned)c * 24u;
+                            const int r = lds_s32(bbA + 4u * (unsigned)(bl * 6 + e));
+                            ra[e] = (live && r >= 0) ? xsB + (unsigned)r + (unsigned)c * 24u : zeroA;
                         }
-                        double *ow = out + ((size_t)c * nB + bg * 32) * 6;
                         // released ends are rare: a warp with any takes the out-of-line general element for all its
                         // lanes, so that the rigid path never touches the local arrays that call needs
                         const bool anyPin = __any_sync(0xffffffffu, pm != 0u);
+                        double *ow = out + ((size_t)c * nB + bg * 32) * 6 + 2 * lane;
+                        const size_t caseStride = (size_t)nB * 6;
+                        if (!anyPin && c + LC <= nc && bg * 32 + 32 <= nB && cfg.vec2) {
+                            // the common unit: full warp, full case group, rigid ends, aligned output: no predicates
+#pragma unroll
+                            for (int j = 0; j < LC; j++) {
+                                double u[6], o[6];
+#pragma unroll
+                                for (int e = 0; e < 6; e++) u[e] = lds_f64(ra[e] + 24u * j);
+                                beam_forces_rigid(cf, gc, gs, u, o);
+                                __syncwarp();
+#pragma unroll
+                                for (int e = 0; e < 6; e += 2)
+                                    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(wb + (lane * 6u + e) * 8u), "d"(o[e]), "d"(o[e + 1]) : "memory");
+                                __syncwarp();
+#pragma unroll
+                                for (int e = 0; e < 3; e++) {
+                                    double x, y;
+                                    lds_v2o<0>(wb + (e * 64u + 2u * lane) * 8u, x, y);
+                                    __stcs(reinterpret_cast<double2 *>(ow + e * 64), make_double2(x, y));
+                                }
+                                ow += caseStride;
+                            }
+                            continue;
+                        }
+                        const int nOut = min(32, nB - bg * 32) * 6; // doubles this warp writes per case
 #pragma unroll
                         for (int j = 0; j < LC; j++) {
                             if (c + j >= nc) break;
@@ -911,12 +936,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                             if (!anyPin) {
                                 double u[6];
 #pragma unroll
-                                for (int e = 0; e < 6; e++) u[e] = rv[e] ? lds_f64(ra[e] + 24u * j) : 0.0;
+                                for (int e = 0; e < 6; e++) u[e] = lds_f64(ra[e] + 24u * j);
                                 beam_forces_rigid(cf, gc, gs, u, o);
                             } else {
                                 double uu[6], oo[6];
 #pragma unroll
-                                for (int e = 0; e < 6; e++) uu[e] = rv[e] ? lds_f64(ra[e] + 24u * j) : 0.0;
+                                for (int e = 0; e < 6; e++) uu[e] = lds_f64(ra[e] + 24u * j);
                                 beam_forces_pinned(cf, pm, gc, gs, uu, oo);
 #pragma unroll
                                 for (int e = 0; e < 6; e++) o[e] = oo[e];
@@ -926,17 +951,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                             for (int e = 0; e < 6; e += 2)
                                 asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(wb + (lane * 6u + e) * 8u), "d"(o[e]), "d"(o[e + 1]) : "memory");
                             __syncwarp();
-                            double *oj = ow + (size_t)j * nB * 6;
 #pragma unroll
                             for (int e = 0; e < 3; e++) {
                                 const unsigned q = 2u * (e * 32u + lane); // doubles q, q+1 of the 192
                                 if ((int)q < nOut) {
                                     double x, y;
                                     lds_v2o<0>(wb + q * 8u, x, y);
-                                    if (cfg.vec2) __stcs(reinterpret_cast<double2 *>(oj + q), make_double2(x, y));
-                                    else { __stcs(oj + q, x); __stcs(oj + q + 1, y); }
+                                    if (cfg.vec2) __stcs(reinterpret_cast<double2 *>(ow + e * 64), make_double2(x, y));
+                                    else { __stcs(ow + e * 64, x); __stcs(ow + e * 64 + 1, y); }
                                 }
                             }
+                            ow += caseStride;
                         }
                     }
                 }
