@@ -352,7 +352,7 @@ def main():
     # ---- roofline of the dominant kernel (k_solve_pipe) ----
     peaks, peak_src = measured_peaks()
     names = ["k_assemble", "k_factor", "k_solve_pipe"]
-    sub = int(os.environ.get("HDB_SUB_BATCH", "4096"))
+    sub = int(os.environ.get("HDB_SUB_BATCH", "8192"))
     n_launch = args.steps * ((M + sub - 1) // sub)
     roof = None
     if len(kernel_ms) >= 3 and kernel_ms[2] > 0:

@@ -24,6 +24,7 @@ SYMBOLS = [
     "hdb_check_model", "hdb_check_loads", "hdb_check_modal", "hdb_assemble_node_loads",
     "hdb_static_batch", "hdb_static_batch_dev", "hdb_assemble_batch", "hdb_element_batch",
     "hdb_modal_mode_count", "hdb_modal_batch", "hdb_modal_batch_dev",
+    "hdb_buckling_max_free", "hdb_buckling_batch", "hdb_buckling_batch_dev",
     "hdb_host_alloc", "hdb_host_free", "hdb_set_profiling", "hdb_last_kernel_ms", "hdb_launch_count",
     "hdb_device_count", "hdb_error_string", "hdb_last_error_detail", "hdb_version",
 ]
@@ -83,6 +84,9 @@ def lib():
         L.hdb_modal_mode_count.argtypes = [vp, i32, vp]
         L.hdb_modal_batch.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp]
         L.hdb_modal_batch_dev.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp]
+        L.hdb_buckling_max_free.argtypes = [vp]
+        L.hdb_buckling_batch.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp]
+        L.hdb_buckling_batch_dev.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
         L.hdb_host_alloc.argtypes = [C.POINTER(vp), i64]
         L.hdb_host_free.argtypes = [vp]
         L.hdb_set_profiling.argtypes = [vp, i32]
@@ -236,6 +240,27 @@ class Topology:
         check(lib().hdb_modal_batch_dev(self._h, nModels, _ptr(sections), len(massN), _np_ptr(massN), _ptr(mass),
                                         maxModes, _ptr(nModes), _ptr(hz), _ptr(shapes), _ptr(status),
                                         C.c_void_p(stream)), "hdb_modal_batch_dev")
+
+    # ---- linear buckling (model.go:491-601) ----
+    def buckling_max_free(self) -> int:
+        return int(lib().hdb_buckling_max_free(self._h))
+
+    def buckling_batch(self, sections, forces, amount, want_shapes=True):
+        """forces[nModels][nLC][nB][6] (from static_batch) -> status[nM], nOut[nM][nLC], factors[nM][nLC][amount],
+        shapes[nM][nLC][amount][nP][3]."""
+        sections = np.ascontiguousarray(sections, dtype=np.float64).reshape(-1, self.nB, 3)
+        nM = sections.shape[0]
+        forces = np.ascontiguousarray(forces, dtype=np.float64).reshape(nM, -1, self.nB, 6)
+        nLC = forces.shape[1]
+        mo = max(int(amount), 1)
+        nOut = np.zeros((nM, nLC), dtype=np.int32)
+        factors = np.zeros((nM, nLC, mo))
+        shapes = np.zeros((nM, nLC, mo, self.nP, 3)) if want_shapes else None
+        status = np.zeros(nM, dtype=np.int32)
+        check(lib().hdb_buckling_batch(self._h, nM, _np_ptr(sections), nLC, _np_ptr(forces), int(amount), mo,
+                                       _np_ptr(nOut), _np_ptr(factors), _np_ptr(shapes), _np_ptr(status)),
+              "hdb_buckling_batch")
+        return status, nOut, factors, shapes
 
     # ---- measurement ----
     def set_profiling(self, on=True):

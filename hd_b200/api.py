@@ -95,12 +95,11 @@ def LinearStatic(out, m: Model, *lcs: LoadCase) -> Optional[HdError]:
             errs.append(msg.value.decode())
     if errs:
         return HdError(name, [HdError("Prepared input data", errs)])
-    if any(lc.AmountLinearBuckling > 0 for lc in lcs):
-        return HdError(name, ["linear buckling (model.go:491-601) is not part of this build yet"])
     try:
         topo = _topology(m)
     except _lib.HdbError as ex:
         return HdError(name, [f"Assembly node load: {ex}"])
+    buckling, buckling_err, ok_upto_b = {}, None, None
     try:
         nLC = len(lcs)
         loads = np.zeros((1, max(nLC, 1), topo.dof))
@@ -115,6 +114,20 @@ def LinearStatic(out, m: Model, *lcs: LoadCase) -> Optional[HdError]:
             with np.errstate(all="ignore"):
                 status, fail, disp, forces, react = topo.static_batch(sec[None], loads[:, :nLC])
             st, fc = int(status[0]), int(fail[0])
+            # buckling block (model.go:491-601) of every case that asks for it and has static results
+            ok_upto = nLC if st == _lib.STATUS_OK else (fc if st == _lib.STATUS_IGNORE_LOAD else 0)
+            for i in range(ok_upto):
+                amount = lcs[i].AmountLinearBuckling
+                if amount <= 0:
+                    continue
+                bst, nOut, fac, shp = topo.buckling_batch(sec[None], forces[:, i:i + 1], amount)
+                if int(bst[0]) != _lib.STATUS_OK:
+                    buckling_err = HdError(name, [f"Linear buckling: {STATUS_TEXT.get(int(bst[0]), int(bst[0]))}"])
+                    ok_upto_b = i
+                    break
+                k = min(int(nOut[0, 0]), amount)
+                buckling[i] = [BucklingResult(Factor=float(fac[0, 0, r]), PointDisplacementGlobal=shp[0, 0, r].tolist())
+                               for r in range(k)]
     finally:
         topo.close()
     upto = nLC
@@ -129,10 +142,14 @@ def LinearStatic(out, m: Model, *lcs: LoadCase) -> Optional[HdError]:
     elif st != _lib.STATUS_OK:
         upto = 0
         err = HdError(name, [f"Assembly node load: {STATUS_TEXT.get(st, st)}"])
+    if buckling_err is not None and err is None:  # the reference stops at the first failing buckling block
+        upto, err = min(upto, ok_upto_b + 1), buckling_err
     for i in range(upto):
         lcs[i].PointDisplacementGlobal = disp[0, i].tolist()
         lcs[i].BeamForces = forces[0, i].tolist()
         lcs[i].Reactions = react[0, i].tolist()
+        if i in buckling:
+            lcs[i].LinearBucklingResult = buckling[i]
     return err
 
 

@@ -68,11 +68,15 @@ struct hdb_topology {
     cudaEvent_t evFork = nullptr, evPrep[2] = {nullptr, nullptr}, evSolve[2] = {nullptr, nullptr}, evJoin = nullptr;
     long long *dbgClocks = nullptr; // HDB_DEBUG_CLOCKS=1: per-model phase stamps of k_solve_recover
     size_t wsModels = 0;
-    int subBatch = 4096;
+    int subBatch = 8192; // the factor kernel runs one thread per model: fewer than ~2 warps per SM leave it pure latency
     // host path
     HostChunk chunk[NBUF];
     cudaStream_t sIn = nullptr, sK = nullptr, sOut = nullptr; // copy-in, compute, copy-out
     int chunkModels = 0, chunkLC = 0;
+    // linear buckling tables (built at the first hdb_buckling_batch call)
+    bool bkReady = false;
+    const int32_t *bkFreeDof = nullptr, *bkGPtr = nullptr, *bkGIdx = nullptr;
+    const double *bkGUnit = nullptr;
     // profiling
     int profiling = 0; // 0 off, 1 per call (reset at every call), 2 accumulate until hdb_set_profiling is called again
     std::vector<cudaEvent_t> events;
@@ -1009,6 +1013,159 @@ int hdb_modal_batch(hdb_topology *t, int32_t nModels, const double *sections, in
     if ((rc = fetch_out(hz, bHz, hzS)) != HDB_OK) return rc;
     if ((rc = fetch_out(shapes, bSh, sh)) != HDB_OK) return rc;
     return fetch_out(status, bN, stt);
+}
+
+static int ensure_buckling_tables(hdb_topology *t)
+{
+    if (t->bkReady) return HDB_OK;
+    const Symbolic &S = t->S;
+    const int s = S.nFree, nB = S.nB;
+    std::vector<double> gUnit((size_t)nB * 36);
+    for (int b = 0; b < nB; b++) { // feBeam2d.go:175-275 for unit axial force, rotated like model.go:619-620
+        const int n0 = S.beamN32[2 * b], n1 = S.beamN32[2 * b + 1];
+        const double x0 = S.points[2 * n0], y0 = S.points[2 * n0 + 1], x1 = S.points[2 * n1], y1 = S.points[2 * n1 + 1];
+        const double len = beam_length(x0, y0, x1, y1);
+        double c, sn, k[36];
+        beam_cs(x0, y0, x1, y1, len, c, sn);
+        geom_unit_beam2d(len, S.pinMask[b], k);
+        rotate_to_global(k, c, sn, gUnit.data() + (size_t)b * 36);
+    }
+    // contributions to the dense G(i, j) over free unknowns, position i + j*s, in beam order
+    std::vector<std::vector<int32_t>> lists((size_t)s * s);
+    for (int b = 0; b < nB; b++)
+        for (int a = 0; a < 6; a++)
+            for (int c2 = 0; c2 < 6; c2++) {
+                if (gUnit[(size_t)b * 36 + a * 6 + c2] == 0.0) continue;
+                const int ga = 3 * S.beamN32[2 * b + a / 3] + a % 3, gc = 3 * S.beamN32[2 * b + c2 / 3] + c2 % 3;
+                const int i = S.freeIndex[ga], j = S.freeIndex[gc];
+                if (i < 0 || j < 0) continue;
+                lists[(size_t)i + (size_t)j * s].push_back(b * 36 + a * 6 + c2);
+            }
+    std::vector<int32_t> gPtr(1, 0), gIdx;
+    for (auto &l : lists) {
+        gIdx.insert(gIdx.end(), l.begin(), l.end());
+        gPtr.push_back((int32_t)gIdx.size());
+    }
+    int rc;
+    if ((rc = upload(t, S.freeDofs, &t->bkFreeDof)) != HDB_OK) return rc;
+    if ((rc = upload(t, gPtr, &t->bkGPtr)) != HDB_OK) return rc;
+    if ((rc = upload(t, gIdx, &t->bkGIdx)) != HDB_OK) return rc;
+    if ((rc = upload(t, gUnit, &t->bkGUnit)) != HDB_OK) return rc;
+    t->bkReady = true;
+    return HDB_OK;
+}
+
+int hdb_buckling_max_free(hdb_topology *t)
+{
+    if (!t || ensure_device(t) != HDB_OK) return 0;
+    return buckling_max_s(t->smemOptin);
+}
+
+int hdb_buckling_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *forces,
+                           int32_t amount, int32_t maxOut, int32_t *nOut, double *factors, double *shapes, int32_t *status,
+                           void *stream)
+{
+    if (!t || nModels < 0 || nLC < 0 || !sections || (nLC > 0 && !forces) || !nOut || !factors || !status || amount < 0 ||
+        maxOut < 0)
+        return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    if (nModels == 0 || nLC == 0) return HDB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    prof_reset(t);
+    const Symbolic &S = t->S;
+    const int s = S.nFree;
+    if (s == 0 || amount == 0) {
+        CUDA_TRY(cudaMemsetAsync(nOut, 0, (size_t)nModels * nLC * sizeof(int32_t), st));
+        CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)nModels * sizeof(int32_t), st));
+        return HDB_OK;
+    }
+    if (s > buckling_max_s(t->smemOptin)) {
+        set_error_detail("hdb_buckling_batch: too many free DOFs for the shared-memory resident eigen solver");
+        return HDB_ERR_UNSUPPORTED;
+    }
+    if ((rc = ensure_buckling_tables(t)) != HDB_OK) return rc;
+    const size_t per = (size_t)s * S.dof * sizeof(double);
+    int sbm = (int)std::max<size_t>(1, std::min<size_t>((size_t)nModels, ((size_t)768 << 20) / (2 * per)));
+    sbm = std::min(sbm, t->subBatch);
+    const size_t need = 2 * per * sbm + 1024;
+    if (need > t->modalBytes) {
+        if (t->modalBuf) {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            cudaFree(t->modalBuf);
+        }
+        t->modalBuf = nullptr;
+        t->modalBytes = 0;
+        CUDA_TRY(cudaMalloc(&t->modalBuf, need));
+        t->modalBytes = need;
+    }
+    double *unitLoads = (double *)t->modalBuf;
+    double *sol = (double *)((char *)t->modalBuf + per * sbm);
+    for (int m0 = 0; m0 < nModels; m0 += sbm) {
+        const int nm = std::min(sbm, nModels - m0);
+        CUDA_TRY(launch_unit_loads(unitLoads, nm, s, S.dof, t->bkFreeDof, st));
+        count_launch(1);
+        // (K^-1)_ff column by column: the LinearStatic kernels with one unit load case per free DOF
+        rc = static_enqueue(t, nm, sections + (size_t)m0 * S.nB * 3, s, unitLoads, sol, nullptr, nullptr, status + m0,
+                            nullptr, nullptr, st, true);
+        if (rc != HDB_OK) return rc;
+        BucklingLaunch B{};
+        B.nModels = nm; B.nLC = nLC; B.s = s; B.dof = S.dof; B.nB = S.nB; B.amount = amount; B.maxOut = maxOut;
+        B.freeDof = t->bkFreeDof; B.gPtr = t->bkGPtr; B.gIdx = t->bkGIdx; B.gUnit = t->bkGUnit;
+        B.sol = sol;
+        B.forces = forces + (size_t)m0 * nLC * S.nB * 6;
+        B.nOut = nOut + (size_t)m0 * nLC;
+        B.factors = factors + (size_t)m0 * nLC * maxOut;
+        B.shapes = shapes ? shapes + (size_t)m0 * nLC * maxOut * S.dof : nullptr;
+        B.status = status + m0;
+        {
+            ProfScope ps(t, KIND_MODAL0 + 1, st);
+            cudaError_t e = launch_buckling_eigen(B, t->smemOptin, st);
+            if (e == cudaErrorInvalidConfiguration) {
+                set_error_detail("buckling eigen kernel does not fit shared memory");
+                return HDB_ERR_UNSUPPORTED;
+            }
+            CUDA_TRY(e);
+        }
+        count_launch(1);
+    }
+    return HDB_OK;
+}
+
+int hdb_buckling_batch(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *forces,
+                       int32_t amount, int32_t maxOut, int32_t *nOut, double *factors, double *shapes, int32_t *status)
+{
+    if (!t || nModels < 0 || nLC < 0 || !sections || (nLC > 0 && !forces) || !nOut || !factors || !status || amount < 0 ||
+        maxOut < 0)
+        return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    if (nModels == 0 || nLC == 0) return HDB_OK;
+    if (is_device_ptr(sections)) {
+        rc = hdb_buckling_batch_dev(t, nModels, sections, nLC, forces, amount, maxOut, nOut, factors, shapes, status, nullptr);
+        if (rc != HDB_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(nullptr));
+        return HDB_OK;
+    }
+    const Symbolic &S = t->S;
+    Staged sec, fr, no, fa, sh, stt;
+    const size_t bSec = (size_t)nModels * S.nB * 3 * sizeof(double), bFr = (size_t)nModels * nLC * S.nB * 6 * sizeof(double);
+    const size_t bN = (size_t)nModels * nLC * sizeof(int32_t), bFa = (size_t)nModels * nLC * maxOut * sizeof(double);
+    const size_t bSh = bFa * S.dof, bSt = (size_t)nModels * sizeof(int32_t);
+    if ((rc = stage_in(sections, bSec, sec)) != HDB_OK) return rc;
+    if ((rc = stage_in(forces, bFr, fr)) != HDB_OK) return rc;
+    if ((rc = stage_out(nOut, bN, no)) != HDB_OK) return rc;
+    if ((rc = stage_out(factors, bFa, fa)) != HDB_OK) return rc;
+    if ((rc = stage_out(shapes, bSh, sh)) != HDB_OK) return rc;
+    if ((rc = stage_out(status, bSt, stt)) != HDB_OK) return rc;
+    rc = hdb_buckling_batch_dev(t, nModels, (const double *)sec.dev, nLC, (const double *)fr.dev, amount, maxOut,
+                                (int32_t *)no.dev, (double *)fa.dev, (double *)sh.dev, (int32_t *)stt.dev, nullptr);
+    if (rc != HDB_OK) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if ((rc = fetch_out(nOut, bN, no)) != HDB_OK) return rc;
+    if ((rc = fetch_out(factors, bFa, fa)) != HDB_OK) return rc;
+    if ((rc = fetch_out(shapes, bSh, sh)) != HDB_OK) return rc;
+    return fetch_out(status, bSt, stt);
 }
 
 } // extern "C"

@@ -109,6 +109,41 @@ HD_FN void stiff_beam2d(const BeamCoef &c, uint32_t pinMask, double k[36])
     }
 }
 
+// feBeam2d.go:175-275 without the axial-force factor: the geometric stiffness of a beam is
+// axialForce * g(length, pins), axialForce = max(0, bf[0], -bf[3]) (:180-192, applied by the caller).
+HD_FN void geom_unit_beam2d(double length, uint32_t pinMask, double k[36])
+{
+#pragma unroll
+    for (int q = 0; q < 36; q++) k[q] = 0.0;
+    const bool p2 = (pinMask >> 2) & 1u, p5 = (pinMask >> 5) & 1u;
+    if (!p2 && !p5) { // :197
+        const double G1 = HD_DIV(6., HD_MUL(5., length));
+        k[1 * 6 + 1] = G1;  k[4 * 6 + 4] = G1;  k[1 * 6 + 4] = -G1; k[4 * 6 + 1] = -G1;
+        k[1 * 6 + 2] = 0.1; k[2 * 6 + 1] = 0.1; k[1 * 6 + 5] = 0.1; k[5 * 6 + 1] = 0.1;
+        k[2 * 6 + 4] = -0.1; k[4 * 6 + 2] = -0.1; k[5 * 6 + 4] = -0.1; k[4 * 6 + 5] = -0.1;
+        const double G2 = HD_DIV(HD_MUL(2., length), 15.);
+        k[2 * 6 + 2] = G2;  k[5 * 6 + 5] = G2;
+        const double G3 = HD_DIV(-length, 30.);
+        k[5 * 6 + 2] = G3;  k[2 * 6 + 5] = G3;
+    } else if (p2 && !p5) { // :226
+        const double G1 = HD_DIV(6., HD_MUL(5., length));
+        k[1 * 6 + 1] = G1;  k[4 * 6 + 4] = G1;  k[1 * 6 + 4] = -G1; k[4 * 6 + 1] = -G1;
+        k[1 * 6 + 5] = HD_DIV(1., 5.);  k[5 * 6 + 1] = HD_DIV(1., 5.);
+        k[4 * 6 + 5] = HD_DIV(-1., 5.); k[5 * 6 + 4] = HD_DIV(-1., 5.);
+        k[5 * 6 + 5] = HD_DIV(length, 5.0);
+    } else if (!p2 && p5) { // :245
+        const double G1 = HD_DIV(6., HD_MUL(5., length));
+        k[1 * 6 + 1] = G1;  k[4 * 6 + 4] = G1;  k[1 * 6 + 4] = -G1; k[4 * 6 + 1] = -G1;
+        k[1 * 6 + 2] = HD_DIV(1., 5.);  k[2 * 6 + 1] = HD_DIV(1., 5.);
+        k[4 * 6 + 2] = HD_DIV(-1., 5.); k[2 * 6 + 4] = HD_DIV(-1., 5.);
+        k[2 * 6 + 2] = HD_DIV(length, 5.0);
+    } else { // :264
+        const double g = HD_DIV(1.0, length);
+        k[2 * 6 + 2] = g;  k[5 * 6 + 5] = g;
+        k[2 * 6 + 5] = -g; k[5 * 6 + 2] = -g;
+    }
+}
+
 // feBeam2d.go:142-172: direction cosines use end minus start
 HD_FN void beam_cs(double x0, double y0, double x1, double y1, double length, double &c, double &s)
 {

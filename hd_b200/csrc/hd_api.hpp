@@ -40,7 +40,12 @@ struct LoadCase { // model.go:80-130
     std::vector<std::array<double, 6>> BeamForces;
     std::vector<std::array<double, 3>> Reactions;
     uint16_t AmountLinearBuckling = 0;
-    void reset() { PointDisplacementGlobal.clear(); BeamForces.clear(); Reactions.clear(); } // model.go:214-219
+    struct BucklingResult { // model.go:275-291
+        double Factor;
+        std::vector<std::array<double, 3>> PointDisplacementGlobal;
+    };
+    std::vector<BucklingResult> LinearBucklingResult;
+    void reset() { PointDisplacementGlobal.clear(); BeamForces.clear(); Reactions.clear(); LinearBucklingResult.clear(); } // model.go:214-219
 };
 struct ModalMass { // model.go:294-301
     int64_t N;
@@ -124,8 +129,6 @@ inline Error LinearStatic(Model &m, std::vector<LoadCase *> lcs)
             et.add(msg);
     }
     if (et) { Error e; e.add(name + "Prepared input data: " + et.str()); return e; }
-    for (auto *lc : lcs)
-        if (lc->AmountLinearBuckling > 0) { Error e; e.add(name + "linear buckling is not on the GPU path yet"); return e; }
     detail::Topo t;
     int rc = detail::create(m, t);
     if (rc != HDB_OK) { Error e; e.add(name + "Assembly node load: " + detail::api_error(rc, "hdb_topology_create")); return e; }
@@ -165,6 +168,22 @@ inline Error LinearStatic(Model &m, std::vector<LoadCase *> lcs)
             }
         for (size_t b = 0; b < nB; b++)
             for (int k = 0; k < 6; k++) lc.BeamForces[b][k] = forces[(i * nB + b) * 6 + k];
+        if (lc.AmountLinearBuckling > 0) { // buckling block, model.go:491-601
+            const int amount = lc.AmountLinearBuckling;
+            std::vector<double> fac((size_t)amount), shp((size_t)amount * dof);
+            int32_t nOut = 0, bst = 0;
+            rc = hdb_buckling_batch(t.h, 1, sec.data(), 1, forces.data() + i * nB * 6, amount, amount, &nOut, fac.data(), shp.data(), &bst);
+            if (rc != HDB_OK) { e.add(name + detail::api_error(rc, "hdb_buckling_batch")); return e; }
+            if (bst != HDB_STATUS_OK) { e.add(name + "Linear buckling: eigen decomposition failed"); return e; }
+            for (int r = 0; r < nOut && r < amount; r++) {
+                LoadCase::BucklingResult br;
+                br.Factor = fac[(size_t)r];
+                br.PointDisplacementGlobal.resize(nP);
+                for (size_t p = 0; p < nP; p++)
+                    for (int k = 0; k < 3; k++) br.PointDisplacementGlobal[p][k] = shp[(size_t)r * dof + 3 * p + k];
+                lc.LinearBucklingResult.push_back(br);
+            }
+        }
     }
     return e;
 }

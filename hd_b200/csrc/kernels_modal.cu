@@ -8,6 +8,7 @@
 //                   tql2 pair, parallelised over rows), Hz = 1/(2 pi sqrt(lambda)) ascending
 //                   (model.go:830, 846), shapes = K^-1[:,S] M^1/2 y as one dense FP64 contraction,
 //                   scaled to unit 2-norm over the 3*nP entries (what Dgeev returns, model.go:836-841).
+#include <cstdlib>
 #include <cmath>
 
 #include "modal.hpp"
@@ -72,33 +73,18 @@ __device__ __forceinline__ double block_sum(double v, double *red)
     return s;
 }
 
-__global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunch M, const int LD)
+// Symmetric eigenproblem resident in shared memory: Householder tridiagonalisation (tred2), accumulation of
+// the transformations, implicit QL with accumulated vectors (tql2).  V[n][n] (element (i, j) at i + j * LD)
+// holds the symmetric matrix on entry and the eigenvectors (columns) on exit, d the eigenvalues.  Called by
+// every thread of a block of EIG_THREADS threads; returns non-zero if the QL iteration did not converge.
+__device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, double *e, double *cc, double *ss, double *red)
 {
-    extern __shared__ __align__(16) double sm[];
-    const int n = M.s, tid = threadIdx.x, model = blockIdx.x;
-    double *V = sm;                 // [n][n] element (i, j) at i + j * LD
-    double *d = V + (size_t)LD * n; // [n]
-    double *e = d + n;              // [n]
-    double *cc = e + n;             // [n] rotation cosines of one QL sweep
-    double *ss = cc + n;            // [n] rotation sines
-    double *red = ss + n;           // [EIG_THREADS/32 + 8]
-    int *order = reinterpret_cast<int *>(red + EIG_THREADS / 32 + 8); // [n]
+    const int tid = threadIdx.x;
     __shared__ double s_h, s_hh;
     __shared__ int s_m, s_more, s_fail;
 #define VV(i, j) V[(i) + (size_t)(j) * LD]
-    const double *sol = M.sol + (size_t)model * n * M.dof;
-    const double *ms = M.msqrt + (size_t)model * n;
-
     if (tid == 0) s_fail = 0;
-    // ---- B = M^1/2 (K^-1)_SS M^1/2, symmetrised ----
-    for (int idx = tid; idx < n * n; idx += EIG_THREADS) {
-        const int i = idx % n, j = idx / n;
-        const double bij = ms[i] * sol[(size_t)j * M.dof + M.massDof[i]];
-        const double bji = ms[j] * sol[(size_t)i * M.dof + M.massDof[j]];
-        VV(i, j) = 0.5 * (bij + bji);
-    }
     __syncthreads();
-
     // ---- Householder reduction to tridiagonal form (tred2), lower triangle ----
     for (int j = tid; j < n; j += EIG_THREADS) d[j] = VV(n - 1, j);
     __syncthreads();
@@ -286,6 +272,37 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
         __syncthreads();
     }
 
+    __syncthreads();
+    return s_fail;
+#undef VV
+}
+
+__global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunch M, const int LD)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int n = M.s, tid = threadIdx.x, model = blockIdx.x;
+    double *V = sm;                 // [n][n] element (i, j) at i + j * LD
+    double *d = V + (size_t)LD * n; // [n]
+    double *e = d + n;              // [n]
+    double *cc = e + n;             // [n] rotation cosines of one QL sweep
+    double *ss = cc + n;            // [n] rotation sines
+    double *red = ss + n;           // [EIG_THREADS/32 + 8]
+    int *order = reinterpret_cast<int *>(red + EIG_THREADS / 32 + 8); // [n]
+#define VV(i, j) V[(i) + (size_t)(j) * LD]
+    const double *sol = M.sol + (size_t)model * n * M.dof;
+    const double *ms = M.msqrt + (size_t)model * n;
+
+    // ---- B = M^1/2 (K^-1)_SS M^1/2, symmetrised ----
+    for (int idx = tid; idx < n * n; idx += EIG_THREADS) {
+        const int i = idx % n, j = idx / n;
+        const double bij = ms[i] * sol[(size_t)j * M.dof + M.massDof[i]];
+        const double bji = ms[j] * sol[(size_t)i * M.dof + M.massDof[j]];
+        VV(i, j) = 0.5 * (bij + bji);
+    }
+    __syncthreads();
+
+    const int failed = sym_eig_smem(V, LD, n, d, e, cc, ss, red);
+
     // ---- order: ascending Hz = descending lambda (stable on ties) ----
     for (int j = tid; j < n; j += EIG_THREADS) {
         const double lj = fabs(d[j]);
@@ -304,7 +321,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
     }
     if (tid == 0) {
         M.nModes[model] = nOut;
-        if (s_fail && M.status[model] == HDB_STATUS_OK) M.status[model] = HDB_STATUS_EIGEN;
+        if (failed && M.status[model] == HDB_STATUS_OK) M.status[model] = HDB_STATUS_EIGEN;
     }
     if (!M.shapes) return;
 
@@ -378,6 +395,193 @@ cudaError_t launch_modal_eigen(const ModalLaunch &M, int smemOptin, cudaStream_t
         if (e != cudaSuccess) return e;
     }
     k_modal_eigen<<<M.nModels, EIG_THREADS, smem, st>>>(M, LD);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// linear buckling (model.go:491-601).  The reference forms the dense H = K^-1 G and takes the real eigenvalues of
+// the non-symmetric product.  Only free rows and columns matter (eliminated rows of H are zero), and with
+// S = (K^-1)_ff = C C^T (Cholesky; K is SPD where the model is stable) the eigenvalues of S G are those of the
+// symmetric B = C^T G C, eigenvectors x = C y: the shared-memory symmetric solver above does the rest.
+// One block per (model, load case).  G(i, j) = sum over beams of axialForce(beam) * gUnit (feBeam2d.go:175-275).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_unit_loads(double *loads, int nModels, int s, int dof, const int32_t *freeDof)
+{
+    const size_t n = (size_t)nModels * s * dof;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % dof), c = (int)((i / dof) % s);
+        loads[i] = (freeDof[c] == g) ? 1.0 : 0.0;
+    }
+}
+
+cudaError_t launch_unit_loads(double *loads, int nModels, int s, int dof, const int32_t *freeDof, cudaStream_t st)
+{
+    k_unit_loads<<<1184, 256, 0, st>>>(loads, nModels, s, dof, freeDof);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(EIG_THREADS, 1) k_buckling_eigen(const BucklingLaunch P, const int LD)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int n = P.s, tid = threadIdx.x;
+    const int model = blockIdx.x / P.nLC, lc = blockIdx.x - model * P.nLC;
+    double *A = sm;                  // S, then its Cholesky factor C (lower), element (i, j) at i + j * LD
+    double *Gm = A + (size_t)LD * n; // G, then B = C^T G C, then the eigenvectors Y
+    double *Tm = Gm + (size_t)LD * n; // G C, then X = C Y
+    double *d = Tm + (size_t)LD * n;
+    double *e = d + n, *cc = e + n, *ss = cc + n;
+    double *red = ss + n;            // [EIG_THREADS/32 + 8]
+    double *ax = red + EIG_THREADS / 32 + 8; // [nB] axial force of every beam
+    int *order = reinterpret_cast<int *>(ax + P.nB);
+    __shared__ int s_bad, s_cnt;
+#define AA(i, j) A[(i) + (size_t)(j) * LD]
+#define GG(i, j) Gm[(i) + (size_t)(j) * LD]
+#define TT(i, j) Tm[(i) + (size_t)(j) * LD]
+    const double *sol = P.sol + (size_t)model * n * P.dof;
+    const double *bf = P.forces + ((size_t)model * P.nLC + lc) * P.nB * 6;
+    if (tid == 0) { s_bad = 0; s_cnt = 0; }
+    for (int b = tid; b < P.nB; b += EIG_THREADS) { // feBeam2d.go:180-188
+        double a = 0.0;
+        if (bf[6 * b] > 0) a = bf[6 * b];
+        if (-bf[6 * b + 3] > a) a = -bf[6 * b + 3];
+        ax[b] = a;
+    }
+    for (int idx = tid; idx < n * n; idx += EIG_THREADS) {
+        const int i = idx % n, j = idx / n;
+        AA(i, j) = 0.5 * (sol[(size_t)j * P.dof + P.freeDof[i]] + sol[(size_t)i * P.dof + P.freeDof[j]]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += EIG_THREADS) {
+        const int i = idx % n, j = idx / n;
+        double sum = 0.0;
+        for (int q = P.gPtr[idx]; q < P.gPtr[idx + 1]; q++) {
+            const int code = P.gIdx[q];
+            sum = fma(ax[code / 36], P.gUnit[code], sum);
+        }
+        GG(i, j) = sum;
+    }
+    // ---- Cholesky S = C C^T, in place, right-looking ----
+    for (int k = 0; k < n; k++) {
+        __syncthreads();
+        const double piv = AA(k, k);
+        if (!(piv > 0.0)) { // not positive definite: unstable or failed model
+            if (tid == 0) s_bad = 1;
+            break; // uniform: every thread reads the same value
+        }
+        const double r = sqrt(piv);
+        __syncthreads();
+        for (int i = k + tid; i < n; i += EIG_THREADS) AA(i, k) = (i == k) ? r : AA(i, k) / r;
+        __syncthreads();
+        const int m = n - k - 1;
+        for (int idx = tid; idx < m * m; idx += EIG_THREADS) {
+            const int i = k + 1 + idx % m, j = k + 1 + idx / m;
+            if (j <= i) AA(i, j) = fma(-AA(i, k), AA(j, k), AA(i, j));
+        }
+    }
+    __syncthreads();
+    if (s_bad) {
+        if (tid == 0) {
+            P.nOut[(size_t)model * P.nLC + lc] = 0;
+            if (P.status[model] == HDB_STATUS_OK) P.status[model] = HDB_STATUS_EIGEN;
+        }
+        return;
+    }
+    for (int idx = tid; idx < n * n; idx += EIG_THREADS) { // upper triangle of C = 0
+        const int i = idx % n, j = idx / n;
+        if (j > i) AA(i, j) = 0.0;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += EIG_THREADS) { // T = G C
+        const int i = idx % n, j = idx / n;
+        double sum = 0.0;
+        for (int k = j; k < n; k++) sum = fma(GG(i, k), AA(k, j), sum);
+        TT(i, j) = sum;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += EIG_THREADS) { // B = C^T T (lower triangle computed, mirrored)
+        const int i = idx % n, j = idx / n;
+        if (j > i) continue;
+        double sum = 0.0;
+        for (int k = i; k < n; k++) sum = fma(AA(k, i), TT(k, j), sum);
+        GG(i, j) = sum;
+        GG(j, i) = sum;
+    }
+    __syncthreads();
+    const int failed = sym_eig_smem(Gm, LD, n, d, e, cc, ss, red);
+    for (int idx = tid; idx < n * n; idx += EIG_THREADS) { // X = C Y
+        const int i = idx % n, r = idx / n;
+        double sum = 0.0;
+        for (int k = 0; k <= i; k++) sum = fma(AA(i, k), GG(k, r), sum);
+        TT(i, r) = sum;
+    }
+    __syncthreads();
+    // ---- model.go:560-600: non-zero eigenvalues, factor 1/|val|, ascending factor, first `amount` ----
+    if (tid == 0) { // n is small: a serial scan is cheaper than a reduction
+        double mx = 0.0;
+        for (int j = 0; j < n; j++) mx = fmax(mx, fabs(d[j]));
+        red[0] = mx;
+    }
+    __syncthreads();
+    const double vmax = red[0];
+    const double tiny = vmax * 1e-13; // an exact zero of the reference's H shows up as round-off here
+    for (int j = tid; j < n; j += EIG_THREADS) {
+        const double lj = fabs(d[j]);
+        if (!(lj > tiny)) continue;
+        int rank = 0;
+        for (int i = 0; i < n; i++) {
+            const double li = fabs(d[i]);
+            if (li > tiny && (li > lj || (li == lj && i < j))) rank++;
+        }
+        order[rank] = j;
+        atomicAdd(&s_cnt, 1);
+    }
+    __syncthreads();
+    const int cnt = min(s_cnt, P.amount), nOut = min(cnt, P.maxOut);
+    double *fo = P.factors + ((size_t)model * P.nLC + lc) * P.maxOut;
+    for (int r = tid; r < nOut; r += EIG_THREADS) fo[r] = 1. / fabs(d[order[r]]);
+    if (tid == 0) {
+        P.nOut[(size_t)model * P.nLC + lc] = cnt;
+        if (failed && P.status[model] == HDB_STATUS_OK) P.status[model] = HDB_STATUS_EIGEN;
+    }
+    if (!P.shapes) return;
+    double *out = P.shapes + ((size_t)model * P.nLC + lc) * P.maxOut * P.dof;
+    for (int idx = tid; idx < nOut * P.dof; idx += EIG_THREADS) out[idx] = 0.0;
+    __syncthreads();
+    for (int r = 0; r < nOut; r++) { // unit 2-norm over all DOFs (eliminated DOFs stay zero)
+        const int col = order[r];
+        double p2 = 0.0;
+        for (int i = tid; i < n; i += EIG_THREADS) p2 = fma(TT(i, col), TT(i, col), p2);
+        const double nrm = sqrt(block_sum(p2, red));
+        for (int i = tid; i < n; i += EIG_THREADS) out[(size_t)r * P.dof + P.freeDof[i]] = TT(i, col) / nrm;
+    }
+#undef AA
+#undef GG
+#undef TT
+}
+
+static size_t buckling_smem(int n, int nB, int &LD)
+{
+    LD = n | 1;
+    return ((size_t)3 * LD * n + 4 * (size_t)n + EIG_THREADS / 32 + 8 + nB) * sizeof(double) + (size_t)n * sizeof(int) + 64;
+}
+
+int buckling_max_s(int smemOptin)
+{
+    int n = 0, LD;
+    while (buckling_smem(n + 1, 0, LD) + 16384 <= (size_t)smemOptin) n++;
+    return n;
+}
+
+cudaError_t launch_buckling_eigen(const BucklingLaunch &B, int smemOptin, cudaStream_t st)
+{
+    int LD;
+    const size_t smem = buckling_smem(B.s, B.nB, LD);
+    if (smem + 1024 > (size_t)smemOptin) return cudaErrorInvalidConfiguration;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_buckling_eigen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_buckling_eigen<<<B.nModels * B.nLC, EIG_THREADS, smem, st>>>(B, LD);
     return cudaGetLastError();
 }
 

@@ -40,6 +40,25 @@ struct ModalLaunch {
     int32_t *status;          // device [nModels]
 };
 
+// ---- linear buckling (model.go:491-601): eigenvalues of (K^-1)_ff G_ff per (model, load case) ----
+struct BucklingLaunch {
+    int nModels, nLC, s, dof, nB, amount, maxOut;
+    const int32_t *freeDof;   // device [s] global DOF of free unknown i (ascending)
+    const int32_t *gPtr;      // device [s*s+1] contributions to G(i, j), position i + j*s
+    const int32_t *gIdx;      // device [gPtr[s*s]] beam*36 + local index into gUnit
+    const double *gUnit;      // device [nB][36] geometric element matrices in global axes for unit axial force
+    const double *sol;        // device [nModels][s][dof] K^-1 applied to the unit loads of the free DOFs
+    const double *forces;     // device [nModels][nLC][nB][6] beam end forces of the load cases
+    int32_t *nOut;            // device [nModels][nLC]
+    double *factors;          // device [nModels][nLC][maxOut]
+    double *shapes;           // device [nModels][nLC][maxOut][dof] or NULL
+    int32_t *status;          // device [nModels]
+};
+// loads[nModels][s][dof] = unit load on free DOF i in case i
+cudaError_t launch_unit_loads(double *loads, int nModels, int s, int dof, const int32_t *freeDof, cudaStream_t st);
+cudaError_t launch_buckling_eigen(const BucklingLaunch &B, int smemOptin, cudaStream_t st);
+int buckling_max_s(int smemOptin);
+
 cudaError_t launch_modal_loads(const ModalLaunch &M, cudaStream_t st);
 // returns cudaErrorInvalidConfiguration when s is too large for the shared-memory resident eigen solver
 cudaError_t launch_modal_eigen(const ModalLaunch &M, int smemOptin, cudaStream_t st);

@@ -179,6 +179,21 @@ int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections
                         const int64_t *massN /*host*/, const double *mass, int32_t maxModes,
                         int32_t *nModes, double *hz, double *shapes, int32_t *status, void *stream);
 
+/* ---- linear buckling: replaces the buckling block of LinearStatic (model.go:491-601) and getGeometricBeam2d
+ * (feBeam2d.go:175-275) for one value of AmountLinearBuckling.
+ * forces[nModels][nLC][nB][6] are the beam end forces of the load cases (output of hdb_static_batch).  Per
+ * (model, case): nOut = number of buckling factors found (<= amount), factors[maxOut] ascending = 1/|eigenvalue| of
+ * K^-1 G (model.go:578), shapes[maxOut][nP][3] (unit 2-norm, sign free) or NULL.  The reference takes the real
+ * eigenvalues of the dense non-symmetric H = K^-1 G; here the same eigenvalues come from the symmetric
+ * C^T G C with (K^-1)_ff = C C^T, which needs a stable (positive definite) model: otherwise HDB_STATUS_EIGEN.
+ * The free DOF count must not exceed hdb_buckling_max_free() (shared-memory resident solver). */
+int hdb_buckling_max_free(hdb_topology *t);
+int hdb_buckling_batch(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *forces,
+                       int32_t amount, int32_t maxOut, int32_t *nOut, double *factors, double *shapes, int32_t *status);
+int hdb_buckling_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *forces,
+                           int32_t amount, int32_t maxOut, int32_t *nOut, double *factors, double *shapes,
+                           int32_t *status, void *stream);
+
 /* ---- pinned host memory for asynchronous batches (cgo: wrap with unsafe.Slice) ---- */
 int hdb_host_alloc(void **ptr, int64_t bytes);
 int hdb_host_free(void *ptr);

@@ -54,6 +54,22 @@ int main()
         CHECK(lcs[0].PointDisplacementGlobal[1][0] > 0 && lcs[1].PointDisplacementGlobal[1][1] > 0 &&
               lcs[2].PointDisplacementGlobal[1][1] > 0);
     }
+    { // linear buckling through the mirror: cantilever column, Euler load pi^2 E J / (4 L^2) (example.go:56-89 family)
+        hd::Model m;
+        const int n = 8;
+        const double L = 3.0, E = 2.0e11, J = 120e-8;
+        for (int i = 0; i <= n; i++) { m.Points.push_back({0.0, L * i / n}); m.Supports.push_back({0, 0, 0}); }
+        m.Supports[0] = {1, 1, 1};
+        for (int i = 0; i < n; i++) m.Beams.push_back({{i, i + 1}, 12e-4, J, E});
+        hd::LoadCase lc;
+        lc.LoadNodes = {{n, {0.0, -1000.0, 0.0}}};
+        lc.AmountLinearBuckling = 2;
+        CHECK(!hd::LinearStatic(m, {&lc}));
+        CHECK(lc.LinearBucklingResult.size() == 2);
+        const double euler = M_PI * M_PI * E * J / (4 * L * L);
+        CHECK(std::fabs(lc.LinearBucklingResult[0].Factor * 1000.0 - euler) / euler < 1e-3);
+        CHECK(lc.LinearBucklingResult[1].Factor > lc.LinearBucklingResult[0].Factor);
+    }
     { // Truss + TestWrongLoad (model_test.go:18-25): a moment on a fully pinned node must be rejected
         hd::Model m;
         m.Points = {{0, 0}, {0, 12}, {4, 0}, {4, 6}, {8, 0}};
