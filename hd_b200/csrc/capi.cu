@@ -146,6 +146,13 @@ static int ensure_device(hdb_topology *t)
     UP(S.beamN32, beamN);
     UP(S.pinMask, pinMask);
     UP(dropped, dropped);
+    {
+        std::vector<unsigned long long> mask((size_t)S.nB, 0ull);
+        for (int b = 0; b < S.nB; b++)
+            for (int e = 0; e < 36; e++)
+                if (dropped[(size_t)b * 36 + e]) mask[b] |= 1ull << e;
+        UP(mask, droppedMask);
+    }
     UP(S.gptr, gptr);
     UP(pad(S.gsrc), gsrc);
     { // fixed-width (ELL) copies of the two gather lists the solve path uses: [width][n], -1 = no contribution.
@@ -159,7 +166,17 @@ static int ensure_device(hdb_topology *t)
                 for (int k = ptr[s2]; k < ptr[s2 + 1]; k++) o[(size_t)(k - ptr[s2]) * n + s2] = src[k];
             return o;
         };
-        UP(ell(S.gptr, pad(S.gsrc), S.nSlots, D.gWidth), gEll);
+        {
+            std::vector<int32_t> g = ell(S.gptr, pad(S.gsrc), S.nSlots, D.gWidth);
+            bool ok = D.gWidth > 0;
+            for (int s2 = 0; s2 < S.nSlots && ok; s2++) // unit diagonal of a dummy unknown: marker in row 0
+                if (S.slotInit[s2]) {
+                    if (S.gptr[s2 + 1] != S.gptr[s2]) ok = false; // never the case: such a slot has no stiffness entry
+                    else g[s2] = -2;
+                }
+            if (!ok) D.gWidth = 0;
+            UP(g, gEll);
+        }
         UP(ell(S.rgptr, pad(S.rgsrc), S.nnzR, D.rgWidth), rgEll);
         std::vector<double> geom((size_t)S.nB * 3);
         for (int b = 0; b < S.nB; b++) { // same routines, same rounding as on the device (element.cuh)

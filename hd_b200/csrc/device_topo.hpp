@@ -27,6 +27,7 @@ struct DevTopo {
     const int32_t *beamN;      // [nB][2]
     const uint32_t *pinMask;   // [nB]
     const uint8_t *dropped;    // [nB*36] 1 = matrix position absent from the representative pattern
+    const unsigned long long *droppedMask; // [nB] the same, one bit per position
     // assembly gather lists (codes are padded smem indices beam*KE_LD + local)
     const int32_t *gptr, *gsrc;   // factor slots
     const int32_t *gEll, *rgEll;  // [gWidth][nSlots], [rgWidth][nnzR]: the same lists, fixed width, -1 = none

@@ -51,30 +51,41 @@ __device__ __forceinline__ bool section_ok(double v)
 // ------------------------------------------------------------------------------------------------
 constexpr int ASM_MAX_THREADS = 512;
 
-// gather of one slot from the fixed-width list: W index loads, all independent
-template <int W>
-__device__ __forceinline__ double gather_slot(const int32_t *__restrict__ ell, const int n, const int s, const double *ke, double sum)
+// Gather of up to U slots (s, s + stride, ...) from a fixed-width list: U * W index loads, all independent and
+// coalesced, before the first dependent shared-memory read.  Index -2 in row 0 = the slot starts at 1.0 (unit
+// diagonal of a dummy unknown) and has no contribution.
+template <int W, int U>
+__device__ __forceinline__ void gather_slots(const int32_t *__restrict__ ell, const int n, const int s, const int stride, const double *ke,
+                                             double *out, const size_t outStride)
 {
-    int idx[W];
+    int idx[U][W];
 #pragma unroll
-    for (int k = 0; k < W; k++) idx[k] = __ldg(ell + (size_t)k * n + s);
+    for (int u = 0; u < U; u++)
 #pragma unroll
-    for (int k = 0; k < W; k++)
-        if (idx[k] >= 0) sum = __dadd_rn(sum, ke[idx[k]]);
-    return sum;
+        for (int k = 0; k < W; k++) idx[u][k] = (s + u * stride < n) ? __ldg(ell + (size_t)k * n + s + u * stride) : -1;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (s + u * stride >= n) break;
+        double sum = idx[u][0] == -2 ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < W; k++)
+            if (idx[u][k] >= 0) sum = __dadd_rn(sum, ke[idx[u][k]]);
+        out[(size_t)(s + u * stride) * outStride] = sum;
+    }
 }
-__device__ __forceinline__ double gather_slot_w(const int w, const int32_t *__restrict__ ell, const int n, const int s, const double *ke,
-                                                double sum)
+template <int U>
+__device__ __forceinline__ void gather_slots_w(const int w, const int32_t *__restrict__ ell, const int n, const int s, const int stride,
+                                               const double *ke, double *out, const size_t outStride)
 {
     switch (w) { // warp-uniform
-    case 1: return gather_slot<1>(ell, n, s, ke, sum);
-    case 2: return gather_slot<2>(ell, n, s, ke, sum);
-    case 3: return gather_slot<3>(ell, n, s, ke, sum);
-    case 4: return gather_slot<4>(ell, n, s, ke, sum);
-    case 5: return gather_slot<5>(ell, n, s, ke, sum);
-    case 6: return gather_slot<6>(ell, n, s, ke, sum);
-    case 7: return gather_slot<7>(ell, n, s, ke, sum);
-    default: return gather_slot<8>(ell, n, s, ke, sum);
+    case 1: gather_slots<1, U>(ell, n, s, stride, ke, out, outStride); break;
+    case 2: gather_slots<2, U>(ell, n, s, stride, ke, out, outStride); break;
+    case 3: gather_slots<3, U>(ell, n, s, stride, ke, out, outStride); break;
+    case 4: gather_slots<4, U>(ell, n, s, stride, ke, out, outStride); break;
+    case 5: gather_slots<5, U>(ell, n, s, stride, ke, out, outStride); break;
+    case 6: gather_slots<6, U>(ell, n, s, stride, ke, out, outStride); break;
+    case 7: gather_slots<7, U>(ell, n, s, stride, ke, out, outStride); break;
+    default: gather_slots<8, U>(ell, n, s, stride, ke, out, outStride); break;
     }
 }
 
@@ -101,13 +112,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_assemble(const DevTopo T, const 
         double k[36], kg[36];
         stiff_beam2d(cf, T.pinMask[b], k);
         rotate_to_global(k, g.c, g.s, kg);
-        const uint8_t *dr = T.dropped + (size_t)b * 36;
+        const unsigned long long dr = T.droppedMask[b]; // bit e: matrix position e is absent from the representative pattern
 #pragma unroll
         for (int e = 0; e < 36; e++) {
             const double v = kg[e];
             ke[b * KE_LD + e] = v;
             if (!isfinite(v)) flag = max(flag, (int)HDB_STATUS_NONFINITE);
-            else if (dr[e] && v != 0.0) flag = max(flag, (int)HDB_STATUS_PATTERN);
+            else if (((dr >> e) & 1ull) && v != 0.0) flag = max(flag, (int)HDB_STATUS_PATTERN);
         }
     }
     if (flag) atomicMax(&s_flag, flag == HDB_STATUS_NONFINITE ? 100 : flag); // NONFINITE wins
@@ -116,9 +127,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_assemble(const DevTopo T, const 
     // phase B: gather; one thread per slot, contributions in beam order.  The fixed-width lists make every
     // index load independent and coalesced (the CSR walk is a chain of dependent global loads per slot).
     if (T.gWidth > 0) {
-        double *w = L.W + model;
-        for (int s = tid; s < T.nSlots; s += ASM_THREADS) // initial value 1: unit diagonal of a dummy unknown
-            w[(size_t)s * L.ld] = gather_slot_w(T.gWidth, T.gEll, T.nSlots, s, ke, T.slotInit[s] ? 1.0 : 0.0);
+        for (int s = tid; s < T.nSlots; s += 4 * ASM_THREADS)
+            gather_slots_w<4>(T.gWidth, T.gEll, T.nSlots, s, ASM_THREADS, ke, L.W + model, (size_t)L.ld);
     } else {
         for (int s = tid; s < T.nSlots; s += ASM_THREADS) {
             double sum = T.slotInit[s] ? 1.0 : 0.0;
@@ -129,7 +139,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_assemble(const DevTopo T, const 
     }
     double *ksf = L.Ksf + (size_t)model * T.nnzR;
     if (T.rgWidth > 0) {
-        for (int s = tid; s < T.nnzR; s += ASM_THREADS) ksf[s] = gather_slot_w(T.rgWidth, T.rgEll, T.nnzR, s, ke, 0.0);
+        for (int s = tid; s < T.nnzR; s += 4 * ASM_THREADS) gather_slots_w<4>(T.rgWidth, T.rgEll, T.nnzR, s, ASM_THREADS, ke, ksf, 1);
     } else {
         for (int s = tid; s < T.nnzR; s += ASM_THREADS) {
             double sum = 0.0;
