@@ -1023,20 +1023,37 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                                 }
                             }
                         }
+                        // DOF info of all pairs of the round first (independent shared-memory reads, issued while the
+                        // global loads are in flight), then the stores: the ld/st.shared wrappers are ordered asm
+                        // statements, so interleaving them per pair would serialise one shared-memory latency per pair
+                        unsigned a0[LOAD_U], a1[LOAD_U], fl = 0; // xs address or 0 (not free); 4 flag bits per pair
+                        static_assert(LOAD_U <= 8, "4 flag bits per pair");
+#pragma unroll
+                        for (int u = 0; u < LOAD_U; u++) {
+                            const int f = f0 + 2 * (u * NS + st);
+                            int g1 = g + 1;
+                            unsigned c1 = cOff;
+                            if (g1 == dof) { g1 = 0; c1 += 24u; }
+                            const int i0 = f < nFlat ? lds_s32(xbA + 4u * g) : (int)0x80000000;
+                            const int i1 = f + 1 < nFlat ? lds_s32(xbA + 4u * g1) : (int)0x80000000;
+                            a0[u] = i0 >= 0 ? xsB + (unsigned)i0 + cOff : 0u;
+                            a1[u] = i1 >= 0 ? xsB + (unsigned)i1 + c1 : 0u;
+                            fl |= (unsigned)((i0 & 3) | ((i1 & 3) << 2)) << (4 * u);
+                            g += (2 * NS) % dof;
+                            cOff += (unsigned)((2 * NS) / dof) * 24u;
+                            if (g >= dof) { g -= dof; cOff += 24u; }
+                        }
 #pragma unroll
                         for (int u = 0; u < LOAD_U; u++) {
                             const int f = f0 + 2 * (u * NS + st);
                             if (f < nFlat) {
-                                int g1 = g + 1;
-                                unsigned c1 = cOff;
-                                if (g1 == dof) { g1 = 0; c1 += 24u; }
-                                const int i0 = lds_s32(xbA + 4u * g), i1 = f + 1 < nFlat ? lds_s32(xbA + 4u * g1) : (int)0x80000000;
                                 const double v0 = v[u].x, v1 = v[u].y;
+                                const unsigned b4 = fl >> (4 * u);
                                 badLoad |= !(fabs(v0) <= 1.7976931348623157e308) | !(fabs(v1) <= 1.7976931348623157e308);
-                                if (i0 >= 0) sts_f64(xsB + (unsigned)i0 + cOff, v0);
-                                if (i1 >= 0) sts_f64(xsB + (unsigned)i1 + c1, v1);
+                                if (a0[u]) sts_f64(a0[u], v0);
+                                if (a1[u]) sts_f64(a1[u], v1);
                                 if (orr) {
-                                    const double r0 = (i0 & 1) ? -v0 : 0.0, r1 = (i1 & 1) ? -v1 : 0.0;
+                                    const double r0 = (b4 & 1u) ? -v0 : 0.0, r1 = (b4 & 4u) ? -v1 : 0.0;
                                     double *o = orr + f0 + 2 * u * NS;
                                     if (cfg.vec2) *reinterpret_cast<double2 *>(o) = make_double2(r0, r1);
                                     else {
@@ -1044,12 +1061,11 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                                         if (f + 1 < nFlat) o[1] = r1;
                                     }
                                 }
-                                if (((i0 & 2) && v0 != 0.0)) failC = min(failC, c0 + (int)(cOff / 24u));
-                                if (((i1 & 2) && v1 != 0.0)) failC = min(failC, c0 + (int)(c1 / 24u));
+                                if (b4 & 10u) { // a load on a DOF without stiffness (model.go:424-437); rare
+                                    if ((b4 & 2u) && v0 != 0.0) failC = min(failC, c0 + f / dof);
+                                    if ((b4 & 8u) && v1 != 0.0) failC = min(failC, c0 + (f + 1) / dof);
+                                }
                             }
-                            g += (2 * NS) % dof;
-                            cOff += (unsigned)((2 * NS) / dof) * 24u;
-                            if (g >= dof) { g -= dof; cOff += 24u; }
                         }
                     }
                 }
