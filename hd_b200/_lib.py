@@ -24,7 +24,7 @@ SYMBOLS = [
     "hdb_check_model", "hdb_check_loads", "hdb_check_modal", "hdb_assemble_node_loads",
     "hdb_static_batch", "hdb_static_batch_dev", "hdb_assemble_batch", "hdb_element_batch",
     "hdb_modal_mode_count", "hdb_modal_batch", "hdb_modal_batch_dev",
-    "hdb_buckling_max_free", "hdb_buckling_batch", "hdb_buckling_batch_dev",
+    "hdb_buckling_max_free", "hdb_buckling_batch", "hdb_buckling_batch_dev", "hdb_uniform_loads_dev",
     "hdb_host_alloc", "hdb_host_free", "hdb_set_profiling", "hdb_last_kernel_ms", "hdb_launch_count",
     "hdb_device_count", "hdb_error_string", "hdb_last_error_detail", "hdb_version",
 ]
@@ -87,6 +87,7 @@ def lib():
         L.hdb_buckling_max_free.argtypes = [vp]
         L.hdb_buckling_batch.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp]
         L.hdb_buckling_batch_dev.argtypes = [vp, i32, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
+        L.hdb_uniform_loads_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp]
         L.hdb_host_alloc.argtypes = [C.POINTER(vp), i64]
         L.hdb_host_free.argtypes = [vp]
         L.hdb_set_profiling.argtypes = [vp, i32]
@@ -240,6 +241,16 @@ class Topology:
         check(lib().hdb_modal_batch_dev(self._h, nModels, _ptr(sections), len(massN), _np_ptr(massN), _ptr(mass),
                                         maxModes, _ptr(nModes), _ptr(hz), _ptr(shapes), _ptr(status),
                                         C.c_void_p(stream)), "hdb_modal_batch_dev")
+
+    # ---- mod.LoadUniform + assemblyNodeLoad on the device ----
+    def uniform_loads_dev(self, nModels, nLC, ubeam, uproj, q, nodes, f, loads, stream=0):
+        """q, f, loads: device tensors; ubeam, uproj, nodes: host arrays."""
+        ubeam = np.ascontiguousarray(ubeam, dtype=np.int32)
+        uproj = np.ascontiguousarray(uproj, dtype=np.uint8)
+        nodes = np.ascontiguousarray(nodes, dtype=np.int64)
+        check(lib().hdb_uniform_loads_dev(self._h, nModels, nLC, len(ubeam), _np_ptr(ubeam), _np_ptr(uproj), _ptr(q),
+                                          len(nodes), _np_ptr(nodes), _ptr(f), _ptr(loads), C.c_void_p(stream)),
+              "hdb_uniform_loads_dev")
 
     # ---- linear buckling (model.go:491-601) ----
     def buckling_max_free(self) -> int:

@@ -1185,4 +1185,79 @@ int hdb_buckling_batch(hdb_topology *t, int32_t nModels, const double *sections,
     return fetch_out(status, bSt, stt);
 }
 
+int hdb_uniform_loads_dev(hdb_topology *t, int32_t nModels, int32_t nLC, int32_t nU, const int32_t *ubeam, const uint8_t *uproj,
+                          const double *q, int32_t nN, const int64_t *nodes, const double *f, double *loads, void *stream)
+{
+    if (!t || nModels < 0 || nLC < 0 || nU < 0 || nN < 0 || (nU > 0 && (!ubeam || !uproj || !q)) || (nN > 0 && (!nodes || !f)) ||
+        !loads)
+        return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    if (nModels == 0 || nLC == 0) return HDB_OK;
+    const Symbolic &S = t->S;
+    cudaStream_t st = (cudaStream_t)stream;
+    // per-DOF contribution lists in LoadNodes order (mod/uniform.go:108-210, then the node loads)
+    std::vector<std::vector<int32_t>> ul((size_t)S.dof), nl((size_t)S.dof);
+    std::vector<double> geo((size_t)nU * 4);
+    for (int u = 0; u < nU; u++) {
+        const int b = ubeam[u];
+        if (b < 0 || b >= S.nB) {
+            set_error_detail("hdb_uniform_loads: index of beam is outside of model slice");
+            return HDB_ERR_INPUT;
+        }
+        const int n0 = S.beamN32[2 * b], n1 = S.beamN32[2 * b + 1];
+        const double dx = S.points[2 * n0] - S.points[2 * n1], dy = S.points[2 * n0 + 1] - S.points[2 * n1 + 1];
+        double lx, ly;
+        if (uproj[u]) { lx = std::fabs(dx); ly = std::fabs(dy); }
+        else { lx = std::sqrt(dx * dx + dy * dy); ly = lx; }
+        geo[4 * u] = dx; geo[4 * u + 1] = dy; geo[4 * u + 2] = lx; geo[4 * u + 3] = ly;
+        auto add = [&](int node, int comp, int code) { ul[(size_t)3 * node + comp].push_back(u * 8 + code); };
+        if (dx > 0) { add(n0, 2, 1); add(n1, 2, 0); }
+        else if (dx < 0) { add(n0, 2, 0); add(n1, 2, 1); }
+        if (dy > 0) { add(n0, 2, 2); add(n1, 2, 3); }
+        else if (dy < 0) { add(n0, 2, 3); add(n1, 2, 2); }
+        for (int n : {n0, n1}) { add(n, 0, 4); add(n, 1, 5); }
+    }
+    for (int j = 0; j < nN; j++) {
+        if (nodes[j] < 0 || nodes[j] >= S.nP) {
+            set_error_detail("hdb_uniform_loads: index of point is outside of model slice");
+            return HDB_ERR_INPUT;
+        }
+        for (int c = 0; c < 3; c++) nl[(size_t)3 * nodes[j] + c].push_back(j * 3 + c);
+    }
+    std::vector<int32_t> uPtr(1, 0), uIdx, nPtr(1, 0), nIdx;
+    for (int g = 0; g < S.dof; g++) {
+        uIdx.insert(uIdx.end(), ul[g].begin(), ul[g].end());
+        uPtr.push_back((int32_t)uIdx.size());
+        nIdx.insert(nIdx.end(), nl[g].begin(), nl[g].end());
+        nPtr.push_back((int32_t)nIdx.size());
+    }
+    const size_t bI = (uPtr.size() + nPtr.size() + std::max<size_t>(uIdx.size(), 1) + std::max<size_t>(nIdx.size(), 1)) * sizeof(int32_t);
+    const size_t bG = std::max<size_t>(geo.size(), 1) * sizeof(double);
+    char *tab = nullptr;
+    CUDA_TRY(cudaMalloc(&tab, bG + bI + 64));
+    double *dGeo = (double *)tab;
+    int32_t *dUPtr = (int32_t *)(tab + bG), *dNPtr = dUPtr + uPtr.size(), *dUIdx = dNPtr + nPtr.size();
+    int32_t *dNIdx = dUIdx + std::max<size_t>(uIdx.size(), 1);
+    auto cp = [&](void *d, const void *h, size_t b) { return b ? cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+    cudaError_t e = cp(dGeo, geo.data(), geo.size() * sizeof(double));
+    if (e == cudaSuccess) e = cp(dUPtr, uPtr.data(), uPtr.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cp(dNPtr, nPtr.data(), nPtr.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cp(dUIdx, uIdx.data(), uIdx.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cp(dNIdx, nIdx.data(), nIdx.size() * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st); // the host vectors go out of scope
+    if (e == cudaSuccess) {
+        UniformLaunch U{};
+        U.nModels = nModels; U.nLC = nLC; U.nU = nU; U.nN = nN; U.dof = S.dof;
+        U.uPtr = dUPtr; U.uIdx = dUIdx; U.uGeo = dGeo; U.nPtr = dNPtr; U.nIdx = dNIdx;
+        U.q = q; U.f = nN > 0 ? f : nullptr; U.loads = loads;
+        e = launch_uniform_loads(U, st);
+        count_launch(1);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st); // the tables are freed below
+    cudaFree(tab);
+    CUDA_TRY(e);
+    return HDB_OK;
+}
+
 } // extern "C"

@@ -64,6 +64,18 @@ struct StaticLaunch {
     long long *dbgClocks;      // [nModels][8] phase time stamps of k_solve_recover (HDB_DEBUG_CLOCKS=1) or NULL
 };
 
+// mod.LoadUniform + assemblyNodeLoad on the device (mod/uniform.go:46-211, model.go:683-698)
+struct UniformLaunch {
+    int nModels, nLC, nU, nN, dof;
+    const int32_t *uPtr, *uIdx;   // per DOF: contributions of the uniform loads, uIdx = item * 8 + code
+    const double *uGeo;           // [nU][4] dx, dy, projected/true lengths used for Fx and Fy
+    const int32_t *nPtr, *nIdx;   // per DOF: contributions of the node loads, nIdx = node item * 3 + component
+    const double *q;              // [nModels][nLC][nU][2]
+    const double *f;              // [nModels][nLC][nN][3] or NULL
+    double *loads;                // [nModels][nLC][dof]
+};
+cudaError_t launch_uniform_loads(const UniformLaunch &U, cudaStream_t st);
+
 // each returns cudaGetLastError() of its launch
 cudaError_t launch_assemble(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);

@@ -1156,4 +1156,46 @@ cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaSt
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_uniform_loads: mod.LoadUniform (mod/uniform.go:46-211) for a fixed list of uniformly loaded beams with
+// per-model, per-case intensities, followed by a fixed list of loaded nodes, flattened like assemblyNodeLoad
+// (model.go:683-698): one thread per (model, case, DOF) adds its contributions in the reference's order, so the
+// result is bit-identical to building the LoadNode list on the host.  Codes: 0/1 = +/-(q1*dx*dx)/12,
+// 2/3 = +/-(q0*dx*dx)/12 (the reference uses dx for the dy branch too, uniform.go:146-153), 4 = (q0*ly)/2,
+// 5 = (q1*lx)/2.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_uniform_loads(const UniformLaunch U)
+{
+    const size_t n = (size_t)U.nModels * U.nLC * U.dof;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % U.dof);
+        const size_t mc = i / U.dof;
+        const double *q = U.q + mc * U.nU * 2;
+        double sum = 0.0;
+        for (int e = U.uPtr[g]; e < U.uPtr[g + 1]; e++) {
+            const int code = U.uIdx[e] & 7, u = U.uIdx[e] >> 3;
+            const double *geo = U.uGeo + 4 * u;
+            double v;
+            if (code < 4) {
+                const double dx = geo[0];
+                v = __ddiv_rn(__dmul_rn(__dmul_rn(q[2 * u + (code < 2 ? 1 : 0)], dx), dx), 12.0);
+                if (code & 1) v = -v;
+            } else if (code == 4) v = __ddiv_rn(__dmul_rn(q[2 * u], geo[3]), 2.0);
+            else v = __ddiv_rn(__dmul_rn(q[2 * u + 1], geo[2]), 2.0);
+            sum = __dadd_rn(sum, v);
+        }
+        if (U.f) {
+            const double *f = U.f + mc * U.nN * 3;
+            for (int e = U.nPtr[g]; e < U.nPtr[g + 1]; e++) sum = __dadd_rn(sum, f[U.nIdx[e]]);
+        }
+        U.loads[i] = sum;
+    }
+}
+
+cudaError_t launch_uniform_loads(const UniformLaunch &U, cudaStream_t st)
+{
+    k_uniform_loads<<<148 * 8, 256, 0, st>>>(U);
+    return cudaGetLastError();
+}
+
 } // namespace hdb

@@ -194,6 +194,17 @@ int hdb_buckling_batch_dev(hdb_topology *t, int32_t nModels, const double *secti
                            int32_t amount, int32_t maxOut, int32_t *nOut, double *factors, double *shapes,
                            int32_t *status, void *stream);
 
+/* ---- load cases built on the device: replaces mod.LoadUniform (mod/uniform.go:46-211) followed by assemblyNodeLoad
+ * (model.go:683-698) for sweeps in which every case of every model loads the same beams / nodes with different
+ * intensities.  ubeam[nU], uproj[nU] (host): uniformly loaded beams and their projection flags; q[nModels][nLC][nU][2]
+ * (device): intensities {qx, qy}; nodes[nN] (host), f[nModels][nLC][nN][3] (device, may be NULL when nN == 0): node
+ * loads appended after the uniform loads.  loads[nModels][nLC][dof] (device) is bit-identical to flattening the
+ * LoadNode list the reference would build (same order of additions).  Moves 16 bytes per loaded beam and case over
+ * PCIe instead of 8*dof bytes per case. */
+int hdb_uniform_loads_dev(hdb_topology *t, int32_t nModels, int32_t nLC, int32_t nU, const int32_t *ubeam,
+                          const uint8_t *uproj, const double *q, int32_t nN, const int64_t *nodes, const double *f,
+                          double *loads, void *stream);
+
 /* ---- pinned host memory for asynchronous batches (cgo: wrap with unsafe.Slice) ---- */
 int hdb_host_alloc(void **ptr, int64_t bytes);
 int hdb_host_free(void *ptr);
