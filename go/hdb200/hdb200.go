@@ -98,3 +98,44 @@ func (t *Topology) ModalBatch(nModels int, sections []float64, massN []int, mass
 func (t *Topology) ModeCount(massN []int) int {
 	return int(C.hdb_modal_mode_count(t.h, C.int32_t(len(massN)), (*C.int64_t)(unsafe.Pointer(&massN[0]))))
 }
+
+// BucklingBatch is the buckling block of LinearStatic (model.go:491-601) for nModels models and nLC load cases:
+// forces [nModels][nLC][nB][6] are the beam end forces StaticBatch returned; per (model, case) nOut factors
+// (ascending, at most amount) and their shapes [maxOut][nP][3].
+func (t *Topology) BucklingBatch(nModels, nLC int, sections, forces []float64, amount, maxOut int,
+	nOut []int32, factors, shapes []float64, status []int32) error {
+	p := func(s []float64) *C.double {
+		if len(s) == 0 {
+			return nil
+		}
+		return (*C.double)(unsafe.Pointer(&s[0]))
+	}
+	rc := C.hdb_buckling_batch(t.h, C.int32_t(nModels), p(sections), C.int32_t(nLC), p(forces), C.int32_t(amount),
+		C.int32_t(maxOut), (*C.int32_t)(unsafe.Pointer(&nOut[0])), p(factors), p(shapes),
+		(*C.int32_t)(unsafe.Pointer(&status[0])))
+	return errOf(rc, "hdb_buckling_batch")
+}
+
+// UniformLoadsDev builds loads[nModels][nLC][dof] on the device from mod.LoadUniform parameters (mod/uniform.go:46-211):
+// q and f are device pointers ([nModels][nLC][len(beams)][2], [nModels][nLC][len(nodes)][3]), loads a device pointer.
+func (t *Topology) UniformLoadsDev(nModels, nLC int, beams []int32, projection []bool, q unsafe.Pointer, nodes []int64,
+	f unsafe.Pointer, loads unsafe.Pointer) error {
+	pr := make([]C.uint8_t, len(projection))
+	for i, b := range projection {
+		if b {
+			pr[i] = 1
+		}
+	}
+	var pb *C.int32_t
+	var pp *C.uint8_t
+	var pn *C.int64_t
+	if len(beams) > 0 {
+		pb, pp = (*C.int32_t)(unsafe.Pointer(&beams[0])), &pr[0]
+	}
+	if len(nodes) > 0 {
+		pn = (*C.int64_t)(unsafe.Pointer(&nodes[0]))
+	}
+	rc := C.hdb_uniform_loads_dev(t.h, C.int32_t(nModels), C.int32_t(nLC), C.int32_t(len(beams)), pb, pp, (*C.double)(q),
+		C.int32_t(len(nodes)), pn, (*C.double)(f), (*C.double)(loads), nil)
+	return errOf(rc, "hdb_uniform_loads_dev")
+}
