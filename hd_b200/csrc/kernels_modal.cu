@@ -233,8 +233,11 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
                         h = c * p;
                         // the tridiagonal entries are O(lambda): no overflow / underflow guard needed, and the
                         // scalar recurrence is the critical path of the whole kernel
-                        r = sqrt(fma(p, p, ei * ei));
-                        const double rinv = 1.0 / r;
+                        // one reciprocal square root instead of a square root followed by a division: each of them is
+                        // a ~100-cycle dependent sequence on this chain
+                        const double q2 = fma(p, p, ei * ei);
+                        const double rinv = rsqrt(q2);
+                        r = q2 * rinv;
                         e[i + 1] = s * r;
                         s = ei * rinv;
                         c = p * rinv;
