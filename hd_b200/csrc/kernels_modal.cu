@@ -236,13 +236,15 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
                         // one reciprocal square root instead of a square root followed by a division: each of them is
                         // a ~100-cycle dependent sequence on this chain
                         const double q2 = fma(p, p, ei * ei);
+                        const double di = d[i];
+                        const double tp = fma(p, di, -ei * g); // = r * (c d[i] - s g): off the rsqrt chain
                         const double rinv = rsqrt(q2);
                         r = q2 * rinv;
                         e[i + 1] = s * r;
                         s = ei * rinv;
                         c = p * rinv;
-                        p = c * d[i] - s * g;
-                        d[i + 1] = h + s * (c * g + s * d[i]);
+                        p = tp * rinv;
+                        d[i + 1] = h + s * (c * g + s * di);
                         cc[i] = c;
                         ss[i] = s;
                     }
