@@ -73,7 +73,7 @@ def _loads_struct(lc: LoadCase):
 
 def _topology(m: Model) -> _lib.Topology:
     pts, bn, sec, pins, sup = _flat(m)
-    return _lib.Topology(pts, bn, sec, pins, sup)
+    return _lib.Topology(pts, bn, sec, pins, sup, ordering=2)  # automatic ordering: results do not depend on it beyond round-off
 
 
 def LinearStatic(out, m: Model, *lcs: LoadCase) -> Optional[HdError]:

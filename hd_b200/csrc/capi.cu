@@ -366,7 +366,13 @@ int hdb_topology_create(int32_t nP, const double *points, int32_t nB, const hdb_
     hdb_topology *t = new (std::nothrow) hdb_topology();
     if (!t) return HDB_ERR_NOMEM;
     std::string detail;
-    int rc = build_symbolic(nP, points, nB, beams, pins, supports, opts ? opts->ordering : 0, t->S, detail);
+    const int ordering = opts ? opts->ordering : 0;
+    int rc = build_symbolic(nP, points, nB, beams, pins, supports, ordering == 2 ? 0 : ordering, t->S, detail);
+    if (rc == HDB_OK && ordering == 2) { // automatic: keep the ordering whose factor is smaller
+        Symbolic rcm;
+        std::string d2;
+        if (build_symbolic(nP, points, nB, beams, pins, supports, 1, rcm, d2) == HDB_OK && rcm.nSlots < t->S.nSlots) t->S = std::move(rcm);
+    }
     if (rc != HDB_OK) {
         set_error_detail(detail);
         delete t;

@@ -104,9 +104,12 @@ struct Topo {
 
 inline int create(Model &m, Topo &t)
 {
+    hdb_options opts{};
+    opts.device = -1;
+    opts.ordering = 2; // automatic: results do not depend on the ordering beyond round-off
     return hdb_topology_create((int32_t)m.Points.size(), m.Points[0].data(), (int32_t)m.Beams.size(),
                                reinterpret_cast<const hdb_beam *>(m.Beams.data()), m.Pins[0].data(), m.Supports[0].data(),
-                               nullptr, &t.h);
+                               &opts, &t.h);
 }
 
 inline std::vector<double> sections_of(const Model &m)

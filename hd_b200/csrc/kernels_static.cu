@@ -310,15 +310,20 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
             // ---- off blocks: rows of L = A (L_JJ D_J)^-T ; stored scaled, u = l * d recovered when needed ----
             for (int a = 0; a < nb; a++) {
                 const int sa = base + BLK_HDR + BLK_STRIDE * a;
+                double w[9]; // read, compute, write back together (see the Schur updates below)
+#pragma unroll
+                for (int e = 0; e < 9; e++) w[e] = WIN(sa + e);
 #pragma unroll
                 for (int r = 0; r < 3; r++) {
-                    const double u0 = WIN(sa + 3 * r);
-                    const double u1 = fma(-l10, u0, WIN(sa + 3 * r + 1));
-                    const double u2 = fma(-l21, u1, fma(-l20, u0, WIN(sa + 3 * r + 2)));
-                    WIN(sa + 3 * r) = u0 * inv0;
-                    WIN(sa + 3 * r + 1) = u1 * inv1;
-                    WIN(sa + 3 * r + 2) = u2 * inv2;
+                    const double u0 = w[3 * r];
+                    const double u1 = fma(-l10, u0, w[3 * r + 1]);
+                    const double u2 = fma(-l21, u1, fma(-l20, u0, w[3 * r + 2]));
+                    w[3 * r] = u0 * inv0;
+                    w[3 * r + 1] = u1 * inv1;
+                    w[3 * r + 2] = u2 * inv2;
                 }
+#pragma unroll
+                for (int e = 0; e < 9; e++) WIN(sa + e) = w[e];
             }
             // ---- Schur updates of every pair of off blocks ----
             const int32_t *tg = T.pairTgt + __ldg(T.pairPtr + J);
@@ -337,20 +342,32 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
                         ub[3 * r + 2] = WIN(sb + 3 * r + 2) * d2;
                     }
                     const int t = __ldg(tg++);
+                    // targets are read into registers first and written back together: the window index is masked,
+                    // so the compiler cannot tell the slots apart and would serialise nine load-FMA-store chains
                     if (a == b) { // diagonal block of row block I_a: header [d0 d1 d2 | (1,0) (2,0) (2,1)]
+                        double tt[6];
+#pragma unroll
+                        for (int e = 0; e < 6; e++) tt[e] = WIN(t + e);
 #pragma unroll
                         for (int r = 0; r < 3; r++)
-                            WIN(t + r) = fma(-la[3 * r + 2], ub[3 * r + 2], fma(-la[3 * r + 1], ub[3 * r + 1], fma(-la[3 * r], ub[3 * r], WIN(t + r))));
-                        WIN(t + 3) = fma(-la[5], ub[2], fma(-la[4], ub[1], fma(-la[3], ub[0], WIN(t + 3))));
-                        WIN(t + 4) = fma(-la[8], ub[2], fma(-la[7], ub[1], fma(-la[6], ub[0], WIN(t + 4))));
-                        WIN(t + 5) = fma(-la[8], ub[5], fma(-la[7], ub[4], fma(-la[6], ub[3], WIN(t + 5))));
+                            tt[r] = fma(-la[3 * r + 2], ub[3 * r + 2], fma(-la[3 * r + 1], ub[3 * r + 1], fma(-la[3 * r], ub[3 * r], tt[r])));
+                        tt[3] = fma(-la[5], ub[2], fma(-la[4], ub[1], fma(-la[3], ub[0], tt[3])));
+                        tt[4] = fma(-la[8], ub[2], fma(-la[7], ub[1], fma(-la[6], ub[0], tt[4])));
+                        tt[5] = fma(-la[8], ub[5], fma(-la[7], ub[4], fma(-la[6], ub[3], tt[5])));
+#pragma unroll
+                        for (int e = 0; e < 6; e++) WIN(t + e) = tt[e];
                     } else { // block (I_a, I_b): rows from a, columns from b
+                        double tt[9];
+#pragma unroll
+                        for (int e = 0; e < 9; e++) tt[e] = WIN(t + e);
 #pragma unroll
                         for (int r = 0; r < 3; r++)
 #pragma unroll
                             for (int rp = 0; rp < 3; rp++)
-                                WIN(t + 3 * r + rp) = fma(-la[3 * r + 2], ub[3 * rp + 2],
-                                                          fma(-la[3 * r + 1], ub[3 * rp + 1], fma(-la[3 * r], ub[3 * rp], WIN(t + 3 * r + rp))));
+                                tt[3 * r + rp] = fma(-la[3 * r + 2], ub[3 * rp + 2],
+                                                     fma(-la[3 * r + 1], ub[3 * rp + 1], fma(-la[3 * r], ub[3 * rp], tt[3 * r + rp])));
+#pragma unroll
+                        for (int e = 0; e < 9; e++) WIN(t + e) = tt[e];
                     }
                 }
             }
@@ -628,32 +645,41 @@ __device__ __forceinline__ void chain_bwd(const unsigned pos, const int n, const
 #undef CHAIN_LOAD
 }
 
-// GENERIC run: per-op flags (blocks with several off blocks, blocks without any)
+// GENERIC run: per-op flags (blocks with several off blocks, blocks without any).  Same software pipeline as the
+// chain loops: the off block, the source x (unless it is the block just finished, which lives in registers) and,
+// at the first op of a block, its right-hand side are fetched one op ahead.
 template <bool FWD>
 __device__ __noinline__ void generic_run(const unsigned pos, const int n, const unsigned lvA, const unsigned xA, const unsigned BS)
 {
     double h0 = 0, h1 = 0, h2 = 0, a0 = 0, a1 = 0, a2 = 0;
+    double m00, m01, m02, m10, m11, m12, m20, m21, m22, z0, z1, z2, q0, q1, q2;
+#define GEN_LOAD(REC)                                                                          \
+    do {                                                                                       \
+        const unsigned a_ = lvA + (unsigned)(REC).x * 8u;                                      \
+        const int y_ = (REC).z;                                                                \
+        lds_v2o<0>(a_, m00, m01);                                                              \
+        lds_v2o<16>(a_, m02, m10);                                                             \
+        lds_v2o<32>(a_, m11, m12);                                                             \
+        lds_v2o<48>(a_, m20, m21);                                                             \
+        m22 = lds_f64o<64>(a_);                                                                \
+        const unsigned s_ = xA + (unsigned)((y_ >> OP_SRC_SHIFT) & OP_BLK_MASK) * BS;          \
+        z0 = lds_f64o<0>(s_); z1 = lds_f64o<8>(s_); z2 = lds_f64o<16>(s_);                     \
+        const unsigned t_ = xA + (unsigned)(y_ & OP_BLK_MASK) * BS;                            \
+        q0 = lds_f64o<0>(t_); q1 = lds_f64o<8>(t_); q2 = lds_f64o<16>(t_);                     \
+    } while (0)
+    int4 r = lds_op(pos), rN = lds_op(pos + 16u);
+    GEN_LOAD(r);
     for (int k = 0; k < n; k++) {
-        const int4 r = lds_op(pos + 16u * (unsigned)k);
+        const int4 rNN = lds_op(pos + 16u * (unsigned)(k + 2)); // may run past the run: never used then
         const int y = r.z;
-        const unsigned a_ = lvA + (unsigned)r.x * 8u, h_ = lvA + (unsigned)r.y * 8u;
+        const unsigned h_ = lvA + (unsigned)r.y * 8u;
         const unsigned ta = xA + (unsigned)(y & OP_BLK_MASK) * BS;
         if (y & OPF_FIRST) {
-            a0 = lds_f64o<0>(ta); a1 = lds_f64o<8>(ta); a2 = lds_f64o<16>(ta);
+            a0 = q0; a1 = q1; a2 = q2;
             if (!FWD) { a0 *= lds_f64o<0>(h_); a1 *= lds_f64o<8>(h_); a2 *= lds_f64o<16>(h_); }
         }
         if (!(y & OPF_NOPULL)) {
-            double z0 = h0, z1 = h1, z2 = h2;
-            if (!(y & OPF_PREV)) {
-                const unsigned sa = xA + (unsigned)((y >> OP_SRC_SHIFT) & OP_BLK_MASK) * BS;
-                z0 = lds_f64o<0>(sa); z1 = lds_f64o<8>(sa); z2 = lds_f64o<16>(sa);
-            }
-            double m00, m01, m02, m10, m11, m12, m20, m21, m22;
-            lds_v2o<0>(a_, m00, m01);
-            lds_v2o<16>(a_, m02, m10);
-            lds_v2o<32>(a_, m11, m12);
-            lds_v2o<48>(a_, m20, m21);
-            m22 = lds_f64o<64>(a_);
+            if (y & OPF_PREV) { z0 = h0; z1 = h1; z2 = h2; }
             if (FWD) {
                 a0 = fma(-m02, z2, fma(-m01, z1, fma(-m00, z0, a0)));
                 a1 = fma(-m12, z2, fma(-m11, z1, fma(-m10, z0, a1)));
@@ -664,13 +690,20 @@ __device__ __noinline__ void generic_run(const unsigned pos, const int n, const 
                 a2 = fma(-m22, z2, fma(-m12, z1, fma(-m02, z0, a2)));
             }
         }
+        double v10 = 0, v20 = 0, v21 = 0;
+        if (y & OPF_LAST) { v10 = lds_f64o<24>(h_); v20 = lds_f64o<32>(h_); v21 = lds_f64o<40>(h_); }
+        // the next op's values; its source or right-hand side may be the block this op is about to store, in
+        // which case PREV is set (source) or it is a different block (right-hand side): both safe to read now
+        GEN_LOAD(rN);
         if (y & OPF_LAST) {
-            const double v10 = lds_f64o<24>(h_), v20 = lds_f64o<32>(h_), v21 = lds_f64o<40>(h_);
             if (FWD) { h0 = a0; h1 = fma(v10, a0, a1); h2 = fma(v21, a1, fma(v20, a0, a2)); }
             else { h2 = a2; h1 = fma(v21, a2, a1); h0 = fma(v20, a2, fma(v10, a1, a0)); }
             sts_f64(ta, h0); sts_f64(ta + 8u, h1); sts_f64(ta + 16u, h2);
         }
+        r = rN;
+        rN = rNN;
     }
+#undef GEN_LOAD
 }
 
 template <bool FWD>

@@ -84,7 +84,9 @@ typedef struct hdb_modal_mass {
 typedef struct hdb_options {
     int32_t device;    /* CUDA device ordinal; -1 = current device                         */
     int32_t ordering;  /* 0 natural (identity permutation: what the reference's LU uses),
-                          1 reverse Cuthill-McKee on the free-DOF node graph               */
+                          1 reverse Cuthill-McKee on the free-DOF node graph,
+                          2 automatic: whichever of the two gives the smaller factor (multi-storey
+                            frames need it: natural order fills a band as wide as a storey)      */
     int32_t reserved[6];
 } hdb_options;
 
