@@ -1183,7 +1183,8 @@ cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaSt
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int grid = L.nModels < nSM ? L.nModels : nSM;
+    int grid = L.nModels < nSM ? L.nModels : nSM;
+    if (const char *e = std::getenv("HDB_SOLVE_BLOCKS")) grid = std::max(1, std::min(grid, atoi(e))); // diagnostics: fewer SMs
     if (L.dbgClocks) std::fprintf(stderr, "[hdb] k_solve_pipe: %d blocks, %zu bytes of shared memory, %d cases per pass\n", grid, smem, cfg.casesPerPass);
     kern<<<grid, PIPE_THREADS, smem, st>>>(T, L, cfg);
     return cudaGetLastError();
