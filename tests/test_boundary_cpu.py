@@ -122,6 +122,35 @@ def test_rcm_ordering_is_a_permutation_and_bounds_fill(oracle):
     t0.close(); t1.close()
 
 
+def test_automatic_ordering_picks_the_smaller_factor(oracle):
+    """ordering=2: natural order on a chain (identity permutation kept), RCM on a multi-storey frame whose
+    natural order fills a band as wide as a storey."""
+    from hd_b200.model import BeamProp, Model
+    m = frames.uniform_frame(16)
+    _, t0 = topo_of(oracle, m)
+    _, t2 = topo_of(oracle, m, ordering=2)
+    assert t2.info.nnzL == t0.info.nnzL and np.array_equal(t2.query(_lib.Q_PERM), t0.query(_lib.Q_PERM))
+    t0.close(); t2.close()
+    ms, idx = Model(), {}
+    N, S = 12, 3
+    for s_ in range(S + 1):
+        for i in range(N + 1):
+            idx[(i, s_)] = len(ms.Points)
+            ms.Points.append([6.0 * i, 3.0 * s_])
+            ms.Supports.append([s_ == 0] * 3)
+    for s_ in range(1, S + 1):
+        for i in range(N + 1):
+            ms.Beams.append(BeamProp(N=[idx[(i, s_ - 1)], idx[(i, s_)]], A=12e-4, J=120e-6, E=2e11))
+        for i in range(1, N + 1):
+            ms.Beams.append(BeamProp(N=[idx[(i - 1, s_)], idx[(i, s_)]], A=12e-4, J=120e-6, E=2e11))
+    _, a0 = topo_of(oracle, ms)
+    _, a1 = topo_of(oracle, ms, ordering=1)
+    _, a2 = topo_of(oracle, ms, ordering=2)
+    assert a1.info.nnzL < a0.info.nnzL and a2.info.nnzL == a1.info.nnzL
+    assert np.array_equal(np.sort(a2.query(_lib.Q_PERM)), np.arange(a2.info.nFree))
+    a0.close(); a1.close(); a2.close()
+
+
 def _check_model(m):
     n_pins, n_sup = len(m.Pins), len(m.Supports)
     pts = np.array([[p[0], p[1]] for p in m.Points], dtype=np.float64).reshape(-1, 2)

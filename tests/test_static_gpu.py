@@ -391,3 +391,44 @@ def test_full_size_batch_properties(oracle):
     s2, _, d2, _, _ = t.static_batch(secs[:64], 2.5 * loads[:64], want=("disp",))
     compare_rule(2.5 * disp[:64], d2, 1e-12)
     t.close()
+
+
+def test_multistorey_frame_general_topology(oracle):
+    """A 3-storey frame (factor with several off blocks per column and fill: generic op runs, multi-off-block
+    factor path) under natural, RCM and automatic ordering, random sections and loads, vs the oracle at 1e-9."""
+    from hd_b200.model import BeamProp, Model
+    m, idx = Model(), {}
+    N, S = 6, 3
+    for s_ in range(S + 1):
+        for i in range(N + 1):
+            idx[(i, s_)] = len(m.Points)
+            m.Points.append([6.0 * i, 3.0 * s_])
+            m.Supports.append([s_ == 0] * 3)
+    for s_ in range(1, S + 1):
+        for i in range(N + 1):
+            m.Beams.append(BeamProp(N=[idx[(i, s_ - 1)], idx[(i, s_)]], A=12e-4, J=120e-6, E=2e11))
+        for i in range(1, N + 1):
+            m.Beams.append(BeamProp(N=[idx[(i - 1, s_)], idx[(i, s_)]], A=12e-4, J=120e-6, E=2e11))
+    fm = oracle.flatten_model(m)
+    rng = np.random.default_rng(9)
+    nM, nLC = 5, 7
+    sec = np.tile(fm.sections, (nM, 1, 1))
+    sec[:, :, :2] *= rng.uniform(0.5, 2.0, size=(nM, fm.nB, 2))
+    loads = rng.normal(size=(nM, nLC, fm.dof)) * 1e3
+    want = []
+    for i in range(nM):
+        fmi = oracle.flatten_model(m)
+        fmi.sections[:] = sec[i]
+        rc, disp, forces, react, fc = oracle.linear_static(fmi, loads[i])
+        assert rc == oracle.OK
+        want.append((disp, forces, react))
+    for ordering in (0, 1, 2):
+        t = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports, ordering=ordering)
+        status, fail, disp, forces, react = t.static_batch(sec, loads)
+        assert not status.any()
+        for i in range(nM):
+            for c in range(nLC):
+                compare_rule(want[i][0][c], disp[i, c])
+                compare_rule(want[i][2][c], react[i, c])
+                force_rule(want[i][1][c], forces[i, c])
+        t.close()
