@@ -432,3 +432,39 @@ def test_multistorey_frame_general_topology(oracle):
                 compare_rule(want[i][2][c], react[i, c])
                 force_rule(want[i][1][c], forces[i, c])
         t.close()
+
+
+def test_unaligned_device_buffers_take_the_scalar_paths(oracle):
+    """Device arrays that are only 8-byte aligned (views one element into a larger tensor): the kernel must fall
+    back from its 16-byte accesses and still match the aligned run bit for bit."""
+    import torch
+    N, nM, nLC = 8, 6, 5
+    m = frames.uniform_frame(N)
+    fm = oracle.flatten_model(m)
+    sec = frames.uniform_frame_sections(N, 0, nM)
+    loads = frames.uniform_frame_loads(N, 0, nM, nLC)
+    t = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports)
+    st0, fail0, disp0, forces0, react0 = t.static_batch(sec, loads)
+    dev = torch.device("cuda:0")
+
+    def shifted(a):  # same values, base address = 8 mod 16
+        flat = torch.empty(a.size + 1, dtype=torch.float64, device=dev)
+        v = flat[1:]
+        v.copy_(torch.from_numpy(np.ascontiguousarray(a).reshape(-1)))
+        assert v.data_ptr() % 16 == 8
+        return flat, v
+
+    keep_s, d_sec = shifted(sec)
+    keep_l, d_loads = shifted(loads)
+    keep_d, d_disp = shifted(np.zeros_like(disp0))
+    keep_f, d_forces = shifted(np.zeros_like(forces0))
+    keep_r, d_react = shifted(np.zeros_like(react0))
+    d_st = torch.zeros(nM, dtype=torch.int32, device=dev)
+    d_fc = torch.zeros(nM, dtype=torch.int32, device=dev)
+    t.static_batch_dev(nM, d_sec, nLC, d_loads, d_disp, d_forces, d_react, d_st, d_fc, 0)
+    torch.cuda.synchronize()
+    assert not d_st.cpu().numpy().any()
+    assert np.array_equal(d_disp.cpu().numpy().reshape(disp0.shape), disp0)
+    assert np.array_equal(d_forces.cpu().numpy().reshape(forces0.shape), forces0)
+    assert np.array_equal(d_react.cpu().numpy().reshape(react0.shape), react0)
+    t.close()
