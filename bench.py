@@ -107,6 +107,15 @@ def build_inputs(n_bays, model0, n_models, n_cases):
     return sections, loads
 
 
+def host_threads():
+    """Host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 for every rank, which would make the
+    CPU arm single-threaded at N > 1; the oracle takes its thread count explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port(fm, sections, loads, threads, literal=True):
     """The oracle (CPU restatement of the reference's algorithm) on `threads` host threads."""
     from oracle import hd_oracle as oracle
@@ -163,7 +172,7 @@ def modal_main(args, rank, local_rank, world):
     value = M * args.steps / (ms * 1e-3)
     cpu = None
     if not args.no_cpu:
-        threads = oracle.max_threads()
+        threads = host_threads()
         sample = args.cpu_sample or 2 * threads
         t0 = time.perf_counter()
         ost, _, _, _ = oracle.modal_batch(fm, sections[:sample], massN, mass[:sample], n_threads=threads)
@@ -222,7 +231,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = oracle.max_threads()
+        threads = host_threads()
         sample = args.cpu_sample or 8 * threads
         sections, loads = build_inputs(N, 0, sample, nLC)
         for _ in range(args.warmup):
@@ -372,7 +381,7 @@ def main():
     # ---- CPU baseline: the oracle on the box's host cores, bounded sample of the same workload ----
     cpu = None
     if not args.no_cpu and world == 1:
-        threads = oracle.max_threads()
+        threads = host_threads()
         sample = args.cpu_sample or 8 * threads
         dt = cpu_port(fm, sections[:sample], loads[:sample], threads, literal=True)
         dt_fast = cpu_port(fm, sections[:sample * 8], loads[:sample * 8], threads, literal=False)
