@@ -677,7 +677,7 @@ static void debug_report_clocks(hdb_topology *t, int nModels)
     if (models <= 0) return;
     std::fprintf(stderr, "[hdb] k_solve_pipe cycles/model (last launch, %d blocks): block %.0f | solver warp %.0f | streaming warp 1:\n", n,
                  blk / models, sol / models);
-    static const char *names[11] = {"Ksf->smem", "beam coef", "disp", "(barrier)", "react", "forces", "(barrier)", "factor gather issue",
+    static const char *names[11] = {"Ksf/section loads issued", "-", "disp + Ksf, coefficients -> smem", "(barrier)", "react", "forces", "(barrier)", "factor gather issue",
                                     "load cases", "(barrier)", "status"};
     std::fprintf(stderr, "[hdb]  ");
     for (int k = 0; k < 11; k++) std::fprintf(stderr, " %s %.0f |", names[k], ph[k] / models);

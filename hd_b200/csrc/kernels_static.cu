@@ -851,33 +851,16 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 // the factor buffer is dead once the solve is over: it takes the beam coefficients [5][nB] and the
                 // reaction block K[sup, free] of the model (one coalesced read instead of a dependent global
                 // load per entry)
-                if (orr) {
-                    const double *ksf = L.Ksf + (size_t)model * T.nnzR;
-                    for (int q0 = 0; q0 < T.nnzR; q0 += NS * 4) {
-                        double v[4];
+                // their global reads (first round) are issued here and consumed after the displacement stores, which
+                // hide the latency
+                const double *ksf = L.Ksf + (size_t)model * T.nnzR;
+                const double *sec = L.sections + (size_t)model * nB * 3;
+                double kv[4], s3[3];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int q = q0 + u * NS + st;
-                            v[u] = q < T.nnzR ? __ldcs(ksf + q) : 0.0;
-                        }
+                for (int u = 0; u < 4; u++) kv[u] = (orr && u * NS + st < T.nnzR) ? __ldcs(ksf + u * NS + st) : 0.0;
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int q = q0 + u * NS + st;
-                            if (q < T.nnzR) sts_f64(ksA + 8u * q, v[u]);
-                        }
-                    }
-                }
+                for (int e = 0; e < 3; e++) s3[e] = (L.forces && st < nB) ? __ldg(sec + 3 * st + e) : 1.0;
                 TICK(0);
-                if (L.forces) {
-                    const double *sec = L.sections + (size_t)model * nB * 3;
-                    for (int b = st; b < nB; b += NS) {
-                        const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], lds_f64(gmA + (unsigned)(2 * nB + b) * 8u));
-                        const unsigned a = lvB + (unsigned)b * 8u; // component-major: conflict-free
-                        sts_f64(a, cf.EFL); sts_f64(a + cs, cf.EJL3); sts_f64(a + 2u * cs, cf.EJL2); sts_f64(a + 3u * cs, cf.EJL);
-                        sts_f64(a + 4u * cs, cf.EJL4);
-                    }
-                }
-                TICK(1);
                 // displacements (model.go:446-451): the [cases][dof] block of a model is one contiguous run, walked
                 // in pairs with a constant stride so that every store is base + immediate; (DOF, case) follow
                 // incrementally
@@ -908,6 +891,22 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                             cOff += (unsigned)((2 * NS) / dof) * 24u;
                             if (g >= dof) { g -= dof; cOff += 24u; }
                         }
+                    }
+                }
+                if (orr) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (u * NS + st < T.nnzR) sts_f64(ksA + 8u * (unsigned)(u * NS + st), kv[u]);
+                    for (int q = 4 * NS + st; q < T.nnzR; q += NS) sts_f64(ksA + 8u * q, __ldcs(ksf + q));
+                }
+                if (L.forces) {
+                    for (int b = st; b < nB; b += NS) {
+                        const bool first = b == st;
+                        const BeamCoef cf = beam_coef(first ? s3[0] : sec[3 * b], first ? s3[1] : sec[3 * b + 1], first ? s3[2] : sec[3 * b + 2],
+                                                      lds_f64(gmA + (unsigned)(2 * nB + b) * 8u));
+                        const unsigned a = lvB + (unsigned)b * 8u; // component-major: conflict-free
+                        sts_f64(a, cf.EFL); sts_f64(a + cs, cf.EJL3); sts_f64(a + 2u * cs, cf.EJL2); sts_f64(a + 3u * cs, cf.EJL);
+                        sts_f64(a + 4u * cs, cf.EJL4);
                     }
                 }
                 TICK(2);
@@ -1017,7 +1016,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 const int it = i, pass = it % cfg.nPass;
                 const int model = (int)blockIdx.x + (it / cfg.nPass) * (int)gridDim.x;
                 const int c0 = pass * CSP, nc = min(CSP, L.nLC - c0);
-                const int sOld = st == 0 ? L.status[model] : 0; // needed at the end of the stage only
+                int sOld = 0; // needed at the end of the stage only; volatile asm keeps the load up here
+                if (st == 0) asm volatile("ld.global.s32 %0, [%1];" : "=r"(sOld) : "l"(L.status + model) : "memory");
                 // factor of this model: one contiguous run; the first eight pieces of every thread stay in flight
                 // across the load-case loop below
                 const double *wf = L.Lm + (size_t)model * T.nSlots + 2 * st;
