@@ -428,7 +428,8 @@ cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t 
 // lists, DOF info, beam rows, reaction rows) are staged once per block.
 // ------------------------------------------------------------------------------------------------
 constexpr int PIPE_THREADS = 512; // warp 0 = solver, warps 4, 8, 12 idle, the other twelve stream
-constexpr int LC = 4;             // load cases handled together by one work item of the streaming stages
+constexpr int LC = 5;             // load cases handled together by one work item of the streaming stages
+constexpr unsigned ZERO_BYTES = (24u * LC + 15u) & ~15u; // a zero "row" long enough for the LC cases of a work unit
 constexpr int NS = PIPE_THREADS / 32 / 4 * 3 * 32; // streaming threads: the warps outside SM sub-partition 0
 constexpr int NH = (PIPE_THREADS / 32 / 4 - 1) * 32; // helper threads: warps 4, 8, 12 of the solver's sub-partition
 constexpr int REACT_HELPER_PCT = 45;               // share of the reaction items the helper warps take
@@ -452,7 +453,7 @@ static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 static size_t pipe_idx_bytes(const DevTopo &T)
 {
     return (size_t)(T.nFwdOps + T.nBwdOps) * 16 +
-           align16(((size_t)T.dof + (size_t)6 * T.nB + (size_t)2 * T.nSup + 1 + (size_t)T.nnzR + (size_t)T.nB) * 4) + (size_t)T.nB * 24 + 128 +
+           align16(((size_t)T.dof + (size_t)6 * T.nB + (size_t)2 * T.nSup + 1 + (size_t)T.nnzR + (size_t)T.nB) * 4) + (size_t)T.nB * 24 + 32 + ZERO_BYTES +
            (size_t)(NS / 32) * FST_BYTES + 32;
 }
 
@@ -747,8 +748,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
     const unsigned sdA = rcA + (unsigned)T.nnzR * 4u;                                      // [nSup] supported DOFs
     const unsigned pmA = sdA + (unsigned)T.nSup * 4u;                                      // [nB] pin masks
     const unsigned gmA = (pmA + (unsigned)nB * 4u + 15u) & ~15u;                           // [3][nB] beam cos, sin, length
-    const unsigned zeroA = (gmA + (unsigned)nB * 24u + 15u) & ~15u;                        // 96 zero bytes: "row" of a supported DOF
-    const unsigned fst0 = zeroA + 96u;                                                     // staging tiles, one per streaming warp
+    const unsigned zeroA = (gmA + (unsigned)nB * 24u + 15u) & ~15u;                        // ZERO_BYTES zeros: "row" of a supported DOF
+    const unsigned fst0 = zeroA + ZERO_BYTES;                                                     // staging tiles, one per streaming warp
     const unsigned lvm0 = fst0 + (unsigned)(NS / 32) * FST_BYTES;
     const unsigned lvmBytes = (unsigned)cfg.lvmDoubles * 8u, xsBytes = (unsigned)cfg.xsDoubles * 8u;
     const unsigned xs0 = lvm0 + 2u * lvmBytes;
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
         sts_f64(gmA + (unsigned)(2 * nB + b) * 8u, g.length);
         sts_s32(pmA + 4u * b, (int)T.pinMask[b]);
     }
-    if (tid < 12) sts_f64(zeroA + 8u * tid, 0.0);
+    if (tid < (int)(ZERO_BYTES / 8)) sts_f64(zeroA + 8u * tid, 0.0);
     if (tid < 2) {
         s_fail[tid] = 0x7fffffff;
         s_flag[tid] = 0;
