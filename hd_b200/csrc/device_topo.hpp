@@ -56,7 +56,7 @@ struct StaticLaunch {
     const double *loads;       // [nModels][nLC][dof]
     double *disp, *forces, *react; // outputs, any may be NULL
     int32_t *status, *failCase;    // failCase may be NULL
-    double *W;                 // [nSlots][ld] factor workspace, interleaved over models (assembly -> factorization)
+    double *W;                 // [ld/32][nSlots][32] factor workspace, interleaved over the 32 models of a tile (assembly -> factorization)
     double *Lm;                // [ld][nSlots] finished factor, model-major (factorization -> solve)
     double *Ksf;               // [nModels][nnzR]
     double *kval;              // [nModels][nnzK] or NULL

@@ -41,6 +41,14 @@ __device__ __forceinline__ BeamGeom beam_geom(const DevTopo &T, int b)
     return g;
 }
 
+// Factor workspace W: tiles of W_TILE = 32 models, inside a tile [nSlots][32].  The factor kernel's warp (one tile)
+// then works on one contiguous region with 256-byte rows; a model's slots are 256 bytes apart for the assembly.
+constexpr int W_TILE = 32;
+__device__ __forceinline__ size_t w_tile_base(const DevTopo &T, int model)
+{
+    return (size_t)(model >> 5) * T.nSlots * W_TILE + (size_t)(model & 31);
+}
+
 __device__ __forceinline__ bool section_ok(double v)
 { // check.go:301-324: NaN, Inf, negative, zero are rejected
     return (v > 0.0) && !isinf(v);
@@ -128,13 +136,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_assemble(const DevTopo T, const 
     // index load independent and coalesced (the CSR walk is a chain of dependent global loads per slot).
     if (T.gWidth > 0) {
         for (int s = tid; s < T.nSlots; s += 4 * ASM_THREADS)
-            gather_slots_w<4>(T.gWidth, T.gEll, T.nSlots, s, ASM_THREADS, ke, L.W + model, (size_t)L.ld);
+            gather_slots_w<4>(T.gWidth, T.gEll, T.nSlots, s, ASM_THREADS, ke, L.W + w_tile_base(T, model), (size_t)W_TILE);
     } else {
         for (int s = tid; s < T.nSlots; s += ASM_THREADS) {
             double sum = T.slotInit[s] ? 1.0 : 0.0;
             const int q1 = T.gptr[s + 1];
             for (int q = T.gptr[s]; q < q1; q++) sum = __dadd_rn(sum, ke[T.gsrc[q]]);
-            L.W[(size_t)s * L.ld + model] = sum;
+            L.W[w_tile_base(T, model) + (size_t)s * W_TILE] = sum;
         }
     }
     double *ksf = L.Ksf + (size_t)model * T.nnzR;
@@ -239,8 +247,8 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
     extern __shared__ __align__(16) double smem_d[];
     const int lane = threadIdx.x;
     const int model = blockIdx.x * 32 + lane; // ld is a multiple of 32: padding lanes work on scratch columns
-    double *wg = L.W + model;
-    const size_t ld = (size_t)L.ld;
+    double *wg = L.W + w_tile_base(T, model); // the 32 models of this warp are one tile: its whole workspace is contiguous
+    const size_t ld = (size_t)W_TILE;
     double *win = smem_d + lane;
 #define WIN(s) (*(WS ? (win + (((s) & (WS ? WS - 1 : 0)) << 5)) : (wg + (size_t)(s) * ld)))
     const int nBlk = T.nBlk;
