@@ -123,12 +123,16 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
             __syncthreads();
             h = s_h;
             // e = A d (A symmetric, lower triangle stored), V(j, i) = d[j]
-            for (int j = tid; j < i; j += EIG_THREADS) {
-                VV(j, i) = d[j];
+            // two threads per row (even / odd k), combined with one shuffle: the row loops are the serial part here
+            for (int j0 = 0; j0 < i; j0 += EIG_THREADS / 2) { // uniform trip count: the shuffle needs the whole warp
+                const int j = j0 + (tid >> 1), half = tid & 1;
                 double g = 0.0;
-                for (int k = 0; k <= j; k++) g = fma(VV(j, k), d[k], g);
-                for (int k = j + 1; k < i; k++) g = fma(VV(k, j), d[k], g);
-                e[j] = g / h;
+                if (j < i) {
+                    if (half == 0) VV(j, i) = d[j];
+                    for (int k = half; k < i; k += 2) g = fma(k <= j ? VV(j, k) : VV(k, j), d[k], g);
+                }
+                g += __shfl_xor_sync(0xffffffffu, g, 1);
+                if (j < i && half == 0) e[j] = g / h;
             }
             __syncthreads();
             part = 0.0;
@@ -138,9 +142,9 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
             for (int j = tid; j < i; j += EIG_THREADS) e[j] -= hh * d[j];
             __syncthreads();
             // rank-2 update of the lower triangle: thread k owns row k
-            for (int k = tid; k < i; k += EIG_THREADS) {
+            for (int k = tid >> 1; k < i; k += EIG_THREADS / 2) {
                 const double ek = e[k], dk = d[k];
-                for (int j = 0; j <= k; j++) VV(k, j) -= d[j] * ek + e[j] * dk;
+                for (int j = tid & 1; j <= k; j += 2) VV(k, j) -= d[j] * ek + e[j] * dk;
             }
             __syncthreads();
             for (int j = tid; j < i; j += EIG_THREADS) {
@@ -164,10 +168,14 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
         if (h != 0.0) {
             for (int k = tid; k <= i; k += EIG_THREADS) d[k] = VV(k, i + 1) / h;
             __syncthreads();
-            for (int j = tid; j <= i; j += EIG_THREADS) { // thread j owns column j
+            for (int j0 = 0; j0 <= i; j0 += EIG_THREADS / 2) { // two threads per column (even / odd k)
+                const int j = j0 + (tid >> 1), half = tid & 1;
                 double g = 0.0;
-                for (int k = 0; k <= i; k++) g = fma(VV(k, i + 1), VV(k, j), g);
-                for (int k = 0; k <= i; k++) VV(k, j) -= g * d[k];
+                if (j <= i)
+                    for (int k = half; k <= i; k += 2) g = fma(VV(k, i + 1), VV(k, j), g);
+                g += __shfl_xor_sync(0xffffffffu, g, 1);
+                if (j <= i)
+                    for (int k = half; k <= i; k += 2) VV(k, j) -= g * d[k];
             }
             __syncthreads();
         }
