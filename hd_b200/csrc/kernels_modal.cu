@@ -17,6 +17,7 @@ namespace hdb {
 
 constexpr double GRAVITY = 9.80665; // model.go:713
 constexpr int EIG_THREADS = 256;
+constexpr int QL_RING = 8; // sweeps of rotations in flight between the QL recurrence and their application
 
 int modal_mass_rows(const Symbolic &S, int nMass, const int64_t *massN, std::vector<int32_t> &dofs,
                     std::vector<std::vector<int32_t>> *massOf)
@@ -196,12 +197,19 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
     }
     __syncthreads();
 
-    // ---- implicit QL with accumulated vectors (tql2): thread 0 runs the scalar recurrence of a sweep
-    //      and leaves its rotations in shared memory, then every thread applies them to its own row ----
-    double f = 0.0, tst1 = 0.0; // live in thread 0 only
+    // ---- implicit QL with accumulated vectors (tql2), producer / consumer.  The scalar recurrence of a sweep
+    //      depends only on d and e, never on the vectors: thread 0 runs all sweeps back to back and leaves the
+    //      rotations of each in a ring of QL_RING slots; warps 1.. apply them to the rows of V as they appear.
+    //      (Before, the other 255 threads waited at a barrier for every sweep: 71 % barrier stalls at n = 130.)
+    __shared__ volatile int s_prod, s_cons, s_done;
+    __shared__ int s_lm[2 * QL_RING];
+    if (tid == 0) { s_prod = 0; s_cons = 0; s_done = 0; }
+    __syncthreads();
     const double eps = 2.220446049250313e-16;
-    for (int l = 0; l < n; l++) {
-        if (tid == 0) {
+    if (tid == 0) {
+        double f = 0.0, tst1 = 0.0;
+        int sweep = 0;
+        for (int l = 0; l < n; l++) {
             tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
             int m = l;
             while (m < n) {
@@ -209,15 +217,12 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
                 m++;
             }
             if (m >= n) m = n - 1;
-            s_m = m;
-        }
-        __syncthreads();
-        const int m = s_m;
-        if (m > l) {
-            int iter = 0;
-            do {
-                if (tid == 0) {
+            if (m > l) {
+                int iter = 0, more;
+                do {
                     iter++;
+                    while (sweep - s_cons >= QL_RING) { } // ring full: wait for the consumers
+                    double *rc = cc + (size_t)(sweep % QL_RING) * 2 * n, *rs = rc + n;
                     double g = d[l];
                     double p = (d[l + 1] - g) / (2.0 * e[l]);
                     double r = hypot(p, 1.0);
@@ -239,13 +244,12 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
                         const double ei = e[i];
                         g = c * ei;
                         h = c * p;
-                        // the tridiagonal entries are O(lambda): no overflow / underflow guard needed, and the
-                        // scalar recurrence is the critical path of the whole kernel
-                        // one reciprocal square root instead of a square root followed by a division: each of them is
-                        // a ~100-cycle dependent sequence on this chain
+                        // the tridiagonal entries are O(lambda): no overflow / underflow guard needed.  One reciprocal
+                        // square root instead of a square root followed by a division (each a ~100-cycle dependent
+                        // sequence on this chain), and the next p computed off that chain.
                         const double q2 = fma(p, p, ei * ei);
                         const double di = d[i];
-                        const double tp = fma(p, di, -ei * g); // = r * (c d[i] - s g): off the rsqrt chain
+                        const double tp = fma(p, di, -ei * g); // = r * (c d[i] - s g)
                         const double rinv = rsqrt(q2);
                         r = q2 * rinv;
                         e[i + 1] = s * r;
@@ -253,36 +257,48 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
                         c = p * rinv;
                         p = tp * rinv;
                         d[i + 1] = h + s * (c * g + s * di);
-                        cc[i] = c;
-                        ss[i] = s;
+                        rc[i] = c;
+                        rs[i] = s;
                     }
                     p = -s * s2 * c3 * el1 * e[l] / dl1;
                     e[l] = s * p;
                     d[l] = c * p;
-                    s_more = (fabs(e[l]) > eps * tst1) ? 1 : 0;
+                    more = fabs(e[l]) > eps * tst1;
                     if (iter > 60) {
-                        s_more = 0;
+                        more = 0;
                         s_fail = 1;
                     }
-                }
-                __syncthreads();
-                for (int k = tid; k < n; k += EIG_THREADS) {
-                    double hk = VV(k, m);
-                    for (int i = m - 1; i >= l; i--) {
-                        const double c = cc[i], s = ss[i], vi = VV(k, i);
-                        VV(k, i + 1) = fma(s, vi, c * hk);
-                        hk = fma(c, vi, -s * hk);
-                    }
-                    VV(k, l) = hk;
-                }
-                __syncthreads();
-            } while (s_more);
-        }
-        if (tid == 0) {
+                    s_lm[2 * (sweep % QL_RING)] = l;
+                    s_lm[2 * (sweep % QL_RING) + 1] = m;
+                    __threadfence_block();
+                    sweep++;
+                    s_prod = sweep;
+                } while (more);
+            }
             d[l] = d[l] + f;
             e[l] = 0.0;
         }
-        __syncthreads();
+        __threadfence_block();
+        s_done = 1;
+    } else if (tid >= 32) {
+        const int ct = tid - 32, NC = EIG_THREADS - 32;
+        for (int k = 0;; k++) {
+            while (s_prod <= k && !s_done) { }
+            if (s_prod <= k) break; // producer finished and nothing left (s_prod is final once s_done is visible)
+            const double *rc = cc + (size_t)(k % QL_RING) * 2 * n, *rs = rc + n;
+            const int l = s_lm[2 * (k % QL_RING)], m = s_lm[2 * (k % QL_RING) + 1];
+            for (int row = ct; row < n; row += NC) {
+                double hk = VV(row, m);
+                for (int i = m - 1; i >= l; i--) {
+                    const double c = rc[i], sn = rs[i], vi = VV(row, i);
+                    VV(row, i + 1) = fma(sn, vi, c * hk);
+                    hk = fma(c, vi, -sn * hk);
+                }
+                VV(row, l) = hk;
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(NC) : "memory"); // every consumer is done with this slot
+            if (ct == 0) s_cons = k + 1;
+        }
     }
 
     __syncthreads();
@@ -297,9 +313,9 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
     double *V = sm;                 // [n][n] element (i, j) at i + j * LD
     double *d = V + (size_t)LD * n; // [n]
     double *e = d + n;              // [n]
-    double *cc = e + n;             // [n] rotation cosines of one QL sweep
-    double *ss = cc + n;            // [n] rotation sines
-    double *red = ss + n;           // [EIG_THREADS/32 + 8]
+    double *cc = e + n;             // [QL_RING][2n] rotations of the QL sweeps in flight
+    double *ss = cc + n;            // (cc is the ring of QL rotations: QL_RING slots of [cosines n | sines n])
+    double *red = cc + (size_t)2 * QL_RING * n; // [EIG_THREADS/32 + 8]
     int *order = reinterpret_cast<int *>(red + EIG_THREADS / 32 + 8); // [n]
 #define VV(i, j) V[(i) + (size_t)(j) * LD]
     const double *sol = M.sol + (size_t)model * n * M.dof;
@@ -387,7 +403,7 @@ static size_t eigen_smem(int n, int &LD)
 {
     LD = n | 1;
     if ((LD & 3) == 1) LD += 2; // LD = 3 mod 4 keeps column strides off the same banks
-    return ((size_t)LD * n + 4 * (size_t)n + EIG_THREADS / 32 + 8) * sizeof(double) + (size_t)n * sizeof(int) + 64;
+    return ((size_t)LD * n + 2 * (size_t)n + 2 * (size_t)QL_RING * n + EIG_THREADS / 32 + 8) * sizeof(double) + (size_t)n * sizeof(int) + 64;
 }
 
 int modal_max_s(int smemOptin)
@@ -442,8 +458,8 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_buckling_eigen(const Bucklin
     double *Gm = A + (size_t)LD * n; // G, then B = C^T G C, then the eigenvectors Y
     double *Tm = Gm + (size_t)LD * n; // G C, then X = C Y
     double *d = Tm + (size_t)LD * n;
-    double *e = d + n, *cc = e + n, *ss = cc + n;
-    double *red = ss + n;            // [EIG_THREADS/32 + 8]
+    double *e = d + n, *cc = e + n, *ss = cc + n; // cc: ring of QL rotations, QL_RING slots of 2n
+    double *red = cc + (size_t)2 * QL_RING * n;   // [EIG_THREADS/32 + 8]
     double *ax = red + EIG_THREADS / 32 + 8; // [nB] axial force of every beam
     int *order = reinterpret_cast<int *>(ax + P.nB);
     __shared__ int s_bad, s_cnt;
@@ -575,7 +591,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_buckling_eigen(const Bucklin
 static size_t buckling_smem(int n, int nB, int &LD)
 {
     LD = n | 1;
-    return ((size_t)3 * LD * n + 4 * (size_t)n + EIG_THREADS / 32 + 8 + nB) * sizeof(double) + (size_t)n * sizeof(int) + 64;
+    return ((size_t)3 * LD * n + 2 * (size_t)n + 2 * (size_t)QL_RING * n + EIG_THREADS / 32 + 8 + nB) * sizeof(double) + (size_t)n * sizeof(int) + 64;
 }
 
 int buckling_max_s(int smemOptin)
