@@ -280,8 +280,8 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
         }
         __threadfence_block();
         s_done = 1;
-    } else if (tid >= 32) {
-        const int ct = tid - 32, NC = EIG_THREADS - 32;
+    } else if ((tid >> 5) & 3) { // the producer keeps SM sub-partition 0 (warps 0, 4, ...) to itself
+        const int w_ = tid >> 5, ct = (w_ - (w_ >> 2) - 1) * 32 + (tid & 31), NC = EIG_THREADS / 32 / 4 * 3 * 32;
         for (int k = 0;; k++) {
             while (s_prod <= k && !s_done) { }
             if (s_prod <= k) break; // producer finished and nothing left (s_prod is final once s_done is visible)
