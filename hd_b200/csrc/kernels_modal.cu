@@ -206,80 +206,99 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
     if (tid == 0) { s_prod = 0; s_cons = 0; s_done = 0; }
     __syncthreads();
     const double eps = 2.220446049250313e-16;
-    if (tid == 0) {
+    if (tid < 32) {
+        // warp 0: lane 0 runs the recurrence; the whole warp does the O(n) shift d[i] -= h of every sweep, which
+        // would otherwise sit on the chain as ~n dependent shared-memory round trips
+        const int lane = tid;
         double f = 0.0, tst1 = 0.0;
         int sweep = 0;
         for (int l = 0; l < n; l++) {
-            tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
             int m = l;
-            while (m < n) {
-                if (fabs(e[m]) <= eps * tst1) break;
-                m++;
+            if (lane == 0) {
+                tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+                while (m < n) {
+                    if (fabs(e[m]) <= eps * tst1) break;
+                    m++;
+                }
+                if (m >= n) m = n - 1;
             }
-            if (m >= n) m = n - 1;
+            m = __shfl_sync(0xffffffffu, m, 0);
             if (m > l) {
-                int iter = 0, more;
+                int iter = 0, more = 0;
                 do {
                     iter++;
-                    while (sweep - s_cons >= QL_RING) { } // ring full: wait for the consumers
+                    double g = 0.0, p = 0.0, r = 0.0, dl1 = 0.0, h = 0.0;
                     double *rc = cc + (size_t)(sweep % QL_RING) * 2 * n, *rs = rc + n;
-                    double g = d[l];
-                    double p = (d[l + 1] - g) / (2.0 * e[l]);
-                    double r = hypot(p, 1.0);
-                    if (p < 0) r = -r;
-                    d[l] = e[l] / (p + r);
-                    d[l + 1] = e[l] * (p + r);
-                    const double dl1 = d[l + 1];
-                    double h = g - d[l];
-                    for (int i = l + 2; i < n; i++) d[i] -= h;
-                    f += h;
-                    p = d[m];
-                    double c = 1.0, c2 = c, c3 = c;
-                    const double el1 = e[l + 1];
-                    double s = 0.0, s2 = 0.0;
-                    for (int i = m - 1; i >= l; i--) {
-                        c3 = c2;
-                        c2 = c;
-                        s2 = s;
-                        const double ei = e[i];
-                        g = c * ei;
-                        h = c * p;
-                        // the tridiagonal entries are O(lambda): no overflow / underflow guard needed.  One reciprocal
-                        // square root instead of a square root followed by a division (each a ~100-cycle dependent
-                        // sequence on this chain), and the next p computed off that chain.
-                        const double q2 = fma(p, p, ei * ei);
-                        const double di = d[i];
-                        const double tp = fma(p, di, -ei * g); // = r * (c d[i] - s g)
-                        const double rinv = rsqrt(q2);
-                        r = q2 * rinv;
-                        e[i + 1] = s * r;
-                        s = ei * rinv;
-                        c = p * rinv;
-                        p = tp * rinv;
-                        d[i + 1] = h + s * (c * g + s * di);
-                        rc[i] = c;
-                        rs[i] = s;
+                    if (lane == 0) {
+                        while (sweep - s_cons >= QL_RING) { } // ring full: wait for the consumers
+                        g = d[l];
+                        p = (d[l + 1] - g) / (2.0 * e[l]);
+                        r = hypot(p, 1.0);
+                        if (p < 0) r = -r;
+                        d[l] = e[l] / (p + r);
+                        d[l + 1] = e[l] * (p + r);
+                        dl1 = d[l + 1];
+                        h = g - d[l];
                     }
-                    p = -s * s2 * c3 * el1 * e[l] / dl1;
-                    e[l] = s * p;
-                    d[l] = c * p;
-                    more = fabs(e[l]) > eps * tst1;
-                    if (iter > 60) {
-                        more = 0;
-                        s_fail = 1;
+                    h = __shfl_sync(0xffffffffu, h, 0);
+                    for (int i = l + 2 + lane; i < n; i += 32) d[i] -= h;
+                    __syncwarp();
+                    if (lane == 0) {
+                        f += h;
+                        p = d[m];
+                        double c = 1.0, c2 = c, c3 = c;
+                        const double el1 = e[l + 1];
+                        double s = 0.0, s2 = 0.0;
+                        for (int i = m - 1; i >= l; i--) {
+                            c3 = c2;
+                            c2 = c;
+                            s2 = s;
+                            const double ei = e[i];
+                            g = c * ei;
+                            h = c * p;
+                            // the tridiagonal entries are O(lambda): no overflow / underflow guard needed.  One
+                            // reciprocal square root instead of a square root followed by a division (each a
+                            // ~100-cycle dependent sequence on this chain), and the next p computed off that chain.
+                            const double q2 = fma(p, p, ei * ei);
+                            const double di = d[i];
+                            const double tp = fma(p, di, -ei * g); // = r * (c d[i] - s g)
+                            const double rinv = rsqrt(q2);
+                            r = q2 * rinv;
+                            e[i + 1] = s * r;
+                            s = ei * rinv;
+                            c = p * rinv;
+                            p = tp * rinv;
+                            d[i + 1] = h + s * (c * g + s * di);
+                            rc[i] = c;
+                            rs[i] = s;
+                        }
+                        p = -s * s2 * c3 * el1 * e[l] / dl1;
+                        e[l] = s * p;
+                        d[l] = c * p;
+                        more = fabs(e[l]) > eps * tst1;
+                        if (iter > 60) {
+                            more = 0;
+                            s_fail = 1;
+                        }
+                        s_lm[2 * (sweep % QL_RING)] = l;
+                        s_lm[2 * (sweep % QL_RING) + 1] = m;
+                        __threadfence_block();
+                        s_prod = sweep + 1;
                     }
-                    s_lm[2 * (sweep % QL_RING)] = l;
-                    s_lm[2 * (sweep % QL_RING) + 1] = m;
-                    __threadfence_block();
                     sweep++;
-                    s_prod = sweep;
+                    more = __shfl_sync(0xffffffffu, more, 0);
                 } while (more);
             }
-            d[l] = d[l] + f;
-            e[l] = 0.0;
+            if (lane == 0) {
+                d[l] = d[l] + f;
+                e[l] = 0.0;
+            }
+            __syncwarp();
         }
-        __threadfence_block();
-        s_done = 1;
+        if (lane == 0) {
+            __threadfence_block();
+            s_done = 1;
+        }
     } else if ((tid >> 5) & 3) { // the producer keeps SM sub-partition 0 (warps 0, 4, ...) to itself
         const int w_ = tid >> 5, ct = (w_ - (w_ >> 2) - 1) * 32 + (tid & 31), NC = EIG_THREADS / 32 / 4 * 3 * 32;
         for (int k = 0;; k++) {
