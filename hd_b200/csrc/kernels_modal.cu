@@ -230,7 +230,7 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
                     double g = 0.0, p = 0.0, r = 0.0, dl1 = 0.0, h = 0.0;
                     double *rc = cc + (size_t)(sweep % QL_RING) * 2 * n, *rs = rc + n;
                     if (lane == 0) {
-                        while (sweep - s_cons >= QL_RING) { } // ring full: wait for the consumers
+                        while (sweep - s_cons >= QL_RING) __nanosleep(100); // ring full: wait for the consumers
                         g = d[l];
                         p = (d[l + 1] - g) / (2.0 * e[l]);
                         r = hypot(p, 1.0);
@@ -249,28 +249,38 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
                         double c = 1.0, c2 = c, c3 = c;
                         const double el1 = e[l + 1];
                         double s = 0.0, s2 = 0.0;
+                        // explicit shared-window addresses: generic pointers into dynamic shared memory make the compiler
+                        // re-derive the window base inside the loop (S2UR on the XU pipe), on the critical chain here
+                        const unsigned dA = (unsigned)__cvta_generic_to_shared(d), eA = (unsigned)__cvta_generic_to_shared(e);
+                        const unsigned cA = (unsigned)__cvta_generic_to_shared(rc), sA = (unsigned)__cvta_generic_to_shared(rs);
+                        double eiN, diN; // e[i], d[i] of the next step, loaded one step ahead
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(eiN) : "r"(eA + 8u * (unsigned)(m - 1)));
+                        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(diN) : "r"(dA + 8u * (unsigned)(m - 1)));
                         for (int i = m - 1; i >= l; i--) {
                             c3 = c2;
                             c2 = c;
                             s2 = s;
-                            const double ei = e[i];
+                            const double ei = eiN, di = diN;
+                            if (i > l) {
+                                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(eiN) : "r"(eA + 8u * (unsigned)(i - 1)));
+                                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(diN) : "r"(dA + 8u * (unsigned)(i - 1)));
+                            }
                             g = c * ei;
                             h = c * p;
                             // the tridiagonal entries are O(lambda): no overflow / underflow guard needed.  One
                             // reciprocal square root instead of a square root followed by a division (each a
                             // ~100-cycle dependent sequence on this chain), and the next p computed off that chain.
                             const double q2 = fma(p, p, ei * ei);
-                            const double di = d[i];
                             const double tp = fma(p, di, -ei * g); // = r * (c d[i] - s g)
                             const double rinv = rsqrt(q2);
                             r = q2 * rinv;
-                            e[i + 1] = s * r;
+                            asm volatile("st.shared.f64 [%0], %1;" ::"r"(eA + 8u * (unsigned)(i + 1)), "d"(s * r) : "memory");
                             s = ei * rinv;
                             c = p * rinv;
                             p = tp * rinv;
-                            d[i + 1] = h + s * (c * g + s * di);
-                            rc[i] = c;
-                            rs[i] = s;
+                            asm volatile("st.shared.f64 [%0], %1;" ::"r"(dA + 8u * (unsigned)(i + 1)), "d"(h + s * (c * g + s * di)) : "memory");
+                            asm volatile("st.shared.f64 [%0], %1;" ::"r"(cA + 8u * (unsigned)i), "d"(c) : "memory");
+                            asm volatile("st.shared.f64 [%0], %1;" ::"r"(sA + 8u * (unsigned)i), "d"(s) : "memory");
                         }
                         p = -s * s2 * c3 * el1 * e[l] / dl1;
                         e[l] = s * p;
@@ -302,7 +312,7 @@ __device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, dou
     } else if ((tid >> 5) & 3) { // the producer keeps SM sub-partition 0 (warps 0, 4, ...) to itself
         const int w_ = tid >> 5, ct = (w_ - (w_ >> 2) - 1) * 32 + (tid & 31), NC = EIG_THREADS / 32 / 4 * 3 * 32;
         for (int k = 0;; k++) {
-            while (s_prod <= k && !s_done) { }
+            while (s_prod <= k && !s_done) __nanosleep(200); // back off: the spinning reads share the shared-memory pipe with the producer
             if (s_prod <= k) break; // producer finished and nothing left (s_prod is final once s_done is visible)
             const double *rc = cc + (size_t)(k % QL_RING) * 2 * n, *rs = rc + n;
             const int l = s_lm[2 * (k % QL_RING)], m = s_lm[2 * (k % QL_RING) + 1];
