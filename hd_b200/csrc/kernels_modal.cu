@@ -78,7 +78,7 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 // the transformations, implicit QL with accumulated vectors (tql2).  V[n][n] (element (i, j) at i + j * LD)
 // holds the symmetric matrix on entry and the eigenvectors (columns) on exit, d the eigenvalues.  Called by
 // every thread of a block of EIG_THREADS threads; returns non-zero if the QL iteration did not converge.
-__device__ int sym_eig_smem(double *V, const int LD, const int n, double *d, double *e, double *cc, double *ss, double *red)
+__device__ __forceinline__ int sym_eig_smem(double *V, const int LD, const int n, double *d, double *e, double *cc, double *ss, double *red)
 {
     const int tid = threadIdx.x;
     __shared__ double s_h, s_hh;
