@@ -184,7 +184,7 @@ def modal_main(args, rank, local_rank, world):
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                           "higher_is_better": True, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": f"uniform_frame({N}) modal, {M} models per GPU, {s} modes each"},
-                          "kernel_ms_total": dict(zip(["k_assemble", "k_factor", "k_solve_recover", "k_modal_loads", "k_modal_eigen"], kms)),
+                          "kernel_ms_total": dict(zip(["k_assemble", "k_factor", "k_solve_pipe", "k_modal_loads", "k_modal_eigen"], kms)),
                           "fp64": {"algorithmic_mflop_per_solve": flops / 1e6, "achieved_tflops": value * flops / 1e12,
                                    "peak_tflops": 36.86, "peak_source": "tools/fp64_microbench.cu on this pool's B200",
                                    "frac": value * flops / 1e12 / 36.86},

@@ -66,7 +66,7 @@ struct hdb_topology {
     double *Wbuf[2] = {nullptr, nullptr}, *Lmbuf[2] = {nullptr, nullptr}, *Ksfbuf[2] = {nullptr, nullptr}, *keScratch = nullptr;
     cudaStream_t prepStream = nullptr;
     cudaEvent_t evFork = nullptr, evPrep[2] = {nullptr, nullptr}, evSolve[2] = {nullptr, nullptr}, evJoin = nullptr;
-    long long *dbgClocks = nullptr; // HDB_DEBUG_CLOCKS=1: per-model phase stamps of k_solve_recover
+    long long *dbgClocks = nullptr; // HDB_DEBUG_CLOCKS=1: per-block phase cycle counters of k_solve_pipe
     size_t wsModels = 0;
     int subBatch = 8192; // the factor kernel runs one thread per model: fewer than ~2 warps per SM leave it pure latency
     // host path
@@ -651,7 +651,7 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
         }
         {
             ProfScope pr(t, KIND_SOLVE, st);
-            CUDA_TRY(launch_solve_recover(t->D, L, st));
+            CUDA_TRY(launch_solve_pipe(t->D, L, st));
         }
         if (pipelined) CUDA_TRY(cudaEventRecord(t->evSolve[buf], st));
         count_launch(2);

@@ -61,7 +61,7 @@ struct StaticLaunch {
     double *Ksf;               // [nModels][nnzR]
     double *kval;              // [nModels][nnzK] or NULL
     double *keScratch;         // [nModels][nB*KE_LD] or NULL (NULL = element matrices live in shared memory)
-    long long *dbgClocks;      // [nModels][8] phase time stamps of k_solve_recover (HDB_DEBUG_CLOCKS=1) or NULL
+    long long *dbgClocks;      // [blocks][32] phase cycle counters of k_solve_pipe (HDB_DEBUG_CLOCKS=1) or NULL
 };
 
 // mod.LoadUniform + assemblyNodeLoad on the device (mod/uniform.go:46-211, model.go:683-698)
@@ -79,7 +79,7 @@ cudaError_t launch_uniform_loads(const UniformLaunch &U, cudaStream_t st);
 // each returns cudaGetLastError() of its launch
 cudaError_t launch_assemble(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
-cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
+cudaError_t launch_solve_pipe(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_elements(const DevTopo &T, int nModels, const double *sections, double *klocal, double *tr,
                             double *kglobal, cudaStream_t st);
 // shared-memory requirement checks (host); return false when the model does not fit

@@ -8,13 +8,15 @@
 //   k_factor         one THREAD per model (SIMT over models, workspace interleaved so every access is
 //                    coalesced): sparse LDL^T along the precomputed schedule; replaces
 //                    sparse.LU.Factorize (model.go:326-331).
-//   k_solve_pipe     persistent block per SM, three-stage pipeline: load cases -> shared memory, forward / backward
-//                    substitution with one lane per load case (model.go:440), then displacement
-//                    unpack (model.go:446-451), beam end forces k*(T*d) (model.go:455-468) and
-//                    reactions -p + K[r,:]d (model.go:470-489), all written once, coalesced.
+//   k_solve_pipe     persistent block per SM, three models in flight: streaming warps pull a model's factor and
+//                    load cases into shared memory, a dedicated solver warp runs the forward / backward block
+//                    substitution with one lane per load case (model.go:440), streaming warps write the
+//                    displacements (model.go:446-451), beam end forces k*(T*d) (model.go:455-468) and
+//                    reactions -p + K[r,:]d (model.go:470-489), all with wide contiguous accesses.
+//   k_uniform_loads  mod.LoadUniform + assemblyNodeLoad on the device (mod/uniform.go:46-211, model.go:683-698).
 //
 // Everything is HBM-bound integer-indexed FP64 work: no tensor-core shapes exist here (fronts are
-// <= 6x6); see DESIGN.md for the roofline of each kernel.
+// 3x3 node blocks); see DESIGN.md for the roofline of each kernel.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -1170,7 +1172,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
     }
 }
 
-cudaError_t launch_solve_recover(const DevTopo &T, const StaticLaunch &L, cudaStream_t st)
+cudaError_t launch_solve_pipe(const DevTopo &T, const StaticLaunch &L, cudaStream_t st)
 {
     int dev = 0, optin = 0, nSM = 148;
     cudaGetDevice(&dev);

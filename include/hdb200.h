@@ -212,7 +212,7 @@ int hdb_host_alloc(void **ptr, int64_t bytes);
 int hdb_host_free(void *ptr);
 
 /* ---- measurement: CUDA-event time of each kernel of the last *_dev / *_batch call ----
- * ms[0..n): static: {assemble, factor, solve_recover}; modal: {assemble, factor, reduce, eigen,
+ * ms[0..n): static: {assemble, factor, solve (k_solve_pipe)}; modal: {assemble, factor, reduce, eigen,
  * shapes}.  Blocks until the events have completed.  Returns the count written.
  * hdb_set_profiling: 0 off, 1 time the last call only, 2 accumulate over calls until set again. */
 int hdb_set_profiling(hdb_topology *t, int32_t on);
