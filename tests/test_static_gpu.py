@@ -468,3 +468,33 @@ def test_unaligned_device_buffers_take_the_scalar_paths(oracle):
     assert np.array_equal(d_forces.cpu().numpy().reshape(forces0.shape), forces0)
     assert np.array_equal(d_react.cpu().numpy().reshape(react0.shape), react0)
     t.close()
+
+
+def test_statuses_across_case_passes(oracle):
+    """More load cases than one pass of the solve kernel holds (32): the offending case sits in the second or
+    third pass.  failCase = the first case with a load on a DOF without stiffness (model.go:424-437); a
+    non-finite load anywhere wins (assemblyNodeLoad rejects it before any solve, model.go:692-696)."""
+    m, lcs, _ = fixtures.truss()          # every node is fully pinned: rotations carry no stiffness
+    fm = oracle.flatten_model(m)
+    t = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports)
+    nLC, nM = 70, 4
+    base = oracle.node_loads(fm.nP, lcs[0].LoadNodes)
+    loads = np.tile(base, (nM, nLC, 1)) * np.linspace(0.5, 1.5, nLC)[None, :, None]
+    rot = 3 * 1 + 2                      # rotation of node 1
+    loads[1, 45, rot] = 42.0             # second pass
+    loads[2, 69, rot] = 1.0              # third pass ...
+    loads[2, 40, rot] = 1.0              # ... but an earlier one in the second: the first offender counts
+    loads[3, 66, 0] = np.nan             # non-finite in the third pass
+    loads[3, 5, rot] = 7.0               # and an ignore-load in the first: non-finite still wins
+    sec = np.tile(fm.sections, (nM, 1, 1))
+    with np.errstate(all="ignore"):
+        status, fail, disp, forces, react = t.static_batch(sec, loads)
+    assert list(status) == [_lib.STATUS_OK, _lib.STATUS_IGNORE_LOAD, _lib.STATUS_IGNORE_LOAD, _lib.STATUS_NONFINITE]
+    assert fail[1] == 45 and fail[2] == 40
+    ost, od, of, orr = oracle.static_batch(fm, sec[:1], loads[:1])
+    assert ost[0] == oracle.OK
+    compare_rule(od[0], disp[0])
+    compare_rule(orr[0], react[0])
+    # the cases before the offending one are complete and correct (model.go:415-437: earlier cases keep their results)
+    compare_rule(od[0][:45], disp[1][:45])
+    t.close()
