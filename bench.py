@@ -116,6 +116,24 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that its pinned host buffers (first touch) and
+    its copy-issuing thread sit on the GPU's NUMA node.  Matters for the e2e leg at N > 1; harmless otherwise."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n = (os.cpu_count() + 63) // 64
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = {64 * i + b for i, m in enumerate(masks) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def cpu_port(fm, sections, loads, threads, literal=True):
     """The oracle (CPU restatement of the reference's algorithm) on `threads` host threads."""
     from oracle import hd_oracle as oracle
@@ -260,6 +278,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — hd_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else 0  # N = 1 keeps every core for the CPU baseline
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -395,7 +414,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches), "failed_models": int(bad.item()),
+            "gpu_launches": int(launches), "failed_models": int(bad.item()), "numa_bound_cpus": int(numa_cpus),
             "hbm_frac_whole_step": value / world * (b_in + b_out) / 1e9 / peaks["hbm_gbs"]}
     print(json.dumps(line), flush=True)
     if world > 1:
