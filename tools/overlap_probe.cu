@@ -22,6 +22,31 @@ __device__ __forceinline__ void do_reads(const double2 *p, int n2, int t, int nt
         }
     }
 }
+// reads through a per-thread cp.async.cg ring of D slots (L1 bypass, no registers held)
+template <int D>
+__device__ __forceinline__ void do_reads_async(const double2 *p, int n2, int t, int nt, double *ringBase, double &acc)
+{
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(ringBase) + t * 16u;
+    const int rounds = (n2 + nt - 1) / nt;
+    for (int r = 0; r < D - 1; r++) {
+        const int i = r * nt + t;
+        if (r < rounds && i < n2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (r % D) * nt * 16u), "l"(p + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int r = 0; r < rounds; r++) {
+        const int rp = r + D - 1, ip = rp * nt + t;
+        if (rp < rounds && ip < n2) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (rp % D) * nt * 16u), "l"(p + ip) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+        if (r * nt + t < n2) {
+            double x, y;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(ring + (r % D) * nt * 16u));
+            acc += x + y;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ void do_writes(double2 *o, int n2, int t, int nt, double a)
 {
     for (int i = t; i < n2; i += nt) __stcs(o + i, make_double2(a, a + i));
@@ -51,7 +76,14 @@ __global__ void __launch_bounds__(384, 1) k_probe(const double *in, double *out,
         } else if (mode == 3) { // D
             do_writes(o, nOut / 2, tid, 384, acc);
             __syncthreads();
-        } else { // E: writes with 8 warps only
+        } else if (mode == 5) { // F: 4 warps read through a 16-deep cp.async ring while 8 warps write
+            if (tid < 128) do_reads_async<16>(p, nIn / 2, tid, 128, sm + 4096, acc);
+            else do_writes(o, nOut / 2, tid - 128, 256, acc);
+            __syncthreads();
+        } else if (mode == 6) { // G: the same reads alone
+            if (tid < 128) do_reads_async<16>(p, nIn / 2, tid, 128, sm + 4096, acc);
+            __syncthreads();
+        } else { // E (mode 4): writes with 8 warps only
             if (tid >= 128) do_writes(o, nOut / 2, tid - 128, 256, acc);
             __syncthreads();
         }
@@ -70,9 +102,10 @@ int main()
     cudaMalloc(&cyc, 148 * 8);
     cudaMemset(in, 0, (size_t)M * nIn * 8);
     cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    const char *names[5] = {"A reads then writes (12 warps)", "B reads (4 warps) || writes (8 warps)", "C reads only (12 warps)",
-                            "D writes only (12 warps)", "E writes only (8 warps)"};
-    for (int mode = 0; mode < 5; mode++) {
+    const char *names[7] = {"A reads then writes (12 warps)", "B reads (4 warps) || writes (8 warps)", "C reads only (12 warps)",
+                            "D writes only (12 warps)", "E writes only (8 warps)", "F cp.async reads (4 warps, ring 16) || writes (8 warps)",
+                            "G cp.async reads only (4 warps, ring 16)"};
+    for (int mode : {0, 1, 2, 3, 4, 5, 6}) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
