@@ -463,7 +463,7 @@ static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 static size_t pipe_idx_bytes(const DevTopo &T)
 {
     return (size_t)(T.nFwdOps + T.nBwdOps) * 16 +
-           align16(((size_t)T.dof + (size_t)6 * T.nB + (size_t)2 * T.nSup + 1 + (size_t)T.nnzR + (size_t)T.nB) * 4) + (size_t)T.nB * 24 + 32 + ZERO_BYTES +
+           align16(((size_t)T.dof + (size_t)2 * T.nSup + 1 + (size_t)T.nB) * 4 + ((size_t)6 * T.nB + (size_t)T.nnzR) * 2 + 16) + (size_t)T.nB * 24 + 32 + ZERO_BYTES +
            (size_t)(NS / 32) * FST_BYTES + 32;
 }
 
@@ -562,6 +562,13 @@ __device__ __forceinline__ int lds_s32(unsigned a)
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ unsigned lds_u16(unsigned a)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void bar_stream(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); } // recover stage: streaming + helper warps
 __device__ __forceinline__ void bar_load(int n) { asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); }   // load stage: streaming warps
@@ -752,10 +759,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
     const unsigned smA = (unsigned)__cvta_generic_to_shared(smem_d);
     const unsigned opsA = smA; // forward list, backward list
     const unsigned xbA = opsA + (unsigned)(T.nFwdOps + T.nBwdOps) * 16u;                   // [dof] DOF info, see below
-    const unsigned bbA = xbA + (unsigned)dof * 4u;                                         // [nB*6] xs byte offset or -1
-    const unsigned rpA = bbA + (unsigned)nB * 24u;                                         // [nSup+1]
-    const unsigned rcA = rpA + (unsigned)(T.nSup + 1) * 4u;                                // [nnzR] xs byte offset
-    const unsigned sdA = rcA + (unsigned)T.nnzR * 4u;                                      // [nSup] supported DOFs
+    // 16-bit tables hold xs offsets in units of 8 bytes, 0xffff = none: they keep the block under the 196 kB
+    // shared-memory configuration, which leaves L1 twice the room of the 228 kB one
+    const unsigned bbA = xbA + (unsigned)dof * 4u;                                         // [nB*6] u16 xs offset / 8 or 0xffff
+    const unsigned rpA = (bbA + (unsigned)nB * 12u + 3u) & ~3u;                            // [nSup+1]
+    const unsigned rcA = rpA + (unsigned)(T.nSup + 1) * 4u;                                // [nnzR] u16 xs offset / 8
+    const unsigned sdA = (rcA + (unsigned)T.nnzR * 2u + 3u) & ~3u;                         // [nSup] supported DOFs
     const unsigned pmA = sdA + (unsigned)T.nSup * 4u;                                      // [nB] pin masks
     const unsigned gmA = (pmA + (unsigned)nB * 4u + 15u) & ~15u;                           // [3][nB] beam cos, sin, length
     const unsigned zeroA = (gmA + (unsigned)nB * 24u + 15u) & ~15u;                        // ZERO_BYTES zeros: "row" of a supported DOF
@@ -777,9 +786,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
         const int xr = __ldg(T.xrow + g);
         sts_s32(xbA + 4u * g, (xr >= 0 ? xoff(xr) : (int)0x80000000) | (__ldg(T.supIndex + g) >= 0 ? 1 : 0) | (xr == -2 ? 2 : 0));
     }
-    for (int k = tid; k < nB * 6; k += blockDim.x) sts_s32(bbA + 4u * k, xoff(__ldg(T.beamRows + k)));
+    for (int k = tid; k < nB * 6; k += blockDim.x) {
+        const int r = xoff(__ldg(T.beamRows + k));
+        sts_u16(bbA + 2u * k, r >= 0 ? (unsigned)r >> 3 : 0xffffu);
+    }
     for (int k = tid; k <= T.nSup; k += blockDim.x) sts_s32(rpA + 4u * k, __ldg(T.rptr + k));
-    for (int k = tid; k < T.nnzR; k += blockDim.x) sts_s32(rcA + 4u * k, xoff(__ldg(T.rcol + k)));
+    for (int k = tid; k < T.nnzR; k += blockDim.x) sts_u16(rcA + 2u * k, (unsigned)xoff(__ldg(T.rcol + k)) >> 3);
     for (int k = tid; k < T.nSup; k += blockDim.x) sts_s32(sdA + 4u * k, __ldg(T.supDofs + k));
     for (int b = tid; b < nB; b += blockDim.x) { // geometry is shared by all models: once per block
         const BeamGeom g = beam_geom(T, b);
@@ -819,7 +831,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
             for (int j = 0; j < LC; j++) acc[j] = 0.0;
             for (int q = q0; q < q1; q++) {
                 const double kv = lds_f64(ksA + 8u * q);
-                const unsigned xa = xsB + (unsigned)lds_s32(rcA + 4u * q) + (unsigned)c * 24u;
+                const unsigned xa = xsB + lds_u16(rcA + 2u * q) * 8u + (unsigned)c * 24u;
 #pragma unroll
                 for (int j = 0; j < LC; j++)
                     if (c + j < nc) acc[j] = fma(kv, lds_f64(xa + 24u * j), acc[j]);
@@ -950,8 +962,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                         unsigned ra[6]; // xs address of the beam's six DOFs for case c; supported DOFs read the zero row
 #pragma unroll
                         for (int e = 0; e < 6; e++) {
-                            const int r = lds_s32(bbA + 4u * (unsigned)(bl * 6 + e));
-                            ra[e] = (live && r >= 0) ? xsB + (unsigned)r + (unsigned)c * 24u : zeroA;
+                            const unsigned r = lds_u16(bbA + 2u * (unsigned)(bl * 6 + e));
+                            ra[e] = (live && r != 0xffffu) ? xsB + r * 8u + (unsigned)c * 24u : zeroA;
                         }
                         // released ends are rare: a warp with any takes the out-of-line general element for all its
                         // lanes, so that the rigid path never touches the local arrays that call needs
