@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
         {
             const int end = base + BLK_HDR + BLK_STRIDE * nb;
             double *lm = L.Lm + (size_t)model * T.nSlots;
-            for (int s2 = base; s2 < end; s2++) lm[s2] = WIN(s2);
+            for (int s2 = base; s2 < end; s2 += 2) // base and end are even: 16-byte stores
+                *reinterpret_cast<double2 *>(lm + s2) = make_double2(WIN(s2), WIN(s2 + 1));
         }
     }
 #undef WIN
