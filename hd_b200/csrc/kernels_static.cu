@@ -293,9 +293,13 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
         const double inv2 = __drcp_rn(d2);
         // header for the solve kernel: 1/d and the strictly lower part of V = Ldiag^-1 (both substitutions then
         // finish a block with independent multiply-adds instead of a dependent chain)
-        WIN(base + 0) = inv0; WIN(base + 1) = inv1; WIN(base + 2) = inv2;
-        WIN(base + 3) = -l10; WIN(base + 4) = fma(l10, l21, -l20); WIN(base + 5) = -l21;
+        const double v10 = -l10, v20 = fma(l10, l21, -l20), v21 = -l21;
         const int nb = d.y;
+        double *lm = L.Lm + (size_t)model * T.nSlots; // finished columns leave model-major: the solve kernel reads a model's
+                                                      // factor as one contiguous run (16-byte stores: base is even)
+        *reinterpret_cast<double2 *>(lm + base) = make_double2(inv0, inv1);
+        *reinterpret_cast<double2 *>(lm + base + 2) = make_double2(inv2, v10);
+        *reinterpret_cast<double2 *>(lm + base + 4) = make_double2(v20, v21);
         if (nb == 1) {
             // ---- the banded case: one off block; its values and the Schur update stay in registers ----
             const int sa = base + BLK_HDR, t = d.w;
@@ -308,8 +312,11 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
                 ua[3 * r] = u0; ua[3 * r + 1] = u1; ua[3 * r + 2] = u2;
                 la[3 * r] = u0 * inv0; la[3 * r + 1] = u1 * inv1; la[3 * r + 2] = u2 * inv2;
             }
+            // nobody reads this off block from the window again (the Schur update below has it in registers): it goes
+            // straight to the model-major copy
 #pragma unroll
-            for (int e = 0; e < 9; e++) WIN(sa + e) = la[e];
+            for (int e = 0; e < 8; e += 2) *reinterpret_cast<double2 *>(lm + sa + e) = make_double2(la[e], la[e + 1]);
+            *reinterpret_cast<double2 *>(lm + sa + 8) = make_double2(la[8], 0.0);
 #pragma unroll
             for (int r = 0; r < 3; r++)
                 WIN(t + r) = fma(-la[3 * r + 2], ua[3 * r + 2], fma(-la[3 * r + 1], ua[3 * r + 1], fma(-la[3 * r], ua[3 * r], WIN(t + r))));
@@ -382,14 +389,10 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
                 }
             }
         }
-        // ---- block column J is final: stream it out, model-major.  The solve kernel reads a model's factor as
-        //      one contiguous run; the 8-byte pieces written here complete their sectors in L2 within a few
-        //      iterations, and this kernel (one warp per 32 models) is nowhere near a store-bandwidth limit ----
-        {
+        // ---- off blocks of a column with several of them: stream them out from the window ----
+        if (nb > 1) {
             const int end = base + BLK_HDR + BLK_STRIDE * nb;
-            double *lm = L.Lm + (size_t)model * T.nSlots;
-            for (int s2 = base; s2 < end; s2 += 2) // base and end are even: 16-byte stores
-                *reinterpret_cast<double2 *>(lm + s2) = make_double2(WIN(s2), WIN(s2 + 1));
+            for (int s2 = base + BLK_HDR; s2 < end; s2 += 2) *reinterpret_cast<double2 *>(lm + s2) = make_double2(WIN(s2), WIN(s2 + 1));
         }
     }
 #undef WIN
