@@ -7,8 +7,8 @@
 
 Same argument meaning, same mutation of the arguments (Pins filled when empty, model.go:344-346;
 results reset at entry, :365-367, :726), same error behaviour: nothing raises for bad input —
-an error value is returned and Run keeps going after a failed case (:937-939, 951-954).  The text
-report (`out`) stays host-side string formatting in the reference and is not produced here.
+an error value is returned and Run keeps going after a failed case (:937-939, 951-954).  `out` (any
+object with write(str), or None) receives the reference's text report, byte for byte (report.py).
 Validation is hdb_check_* (check.go restated in the library); all arithmetic runs on the GPU.
 """
 from __future__ import annotations
@@ -19,6 +19,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
+from . import report
 from .model import BucklingResult, LoadCase, ModalCase, ModalResult, Model
 
 
@@ -80,6 +81,8 @@ def LinearStatic(out, m: Model, *lcs: LoadCase) -> Optional[HdError]:
     name = "Linear Elastic Analysis"
     for lc in lcs:
         lc.reset()
+    if out is not None:
+        out.write(name + "\n")  # model.go:370-371
     errs: List[str] = []
     e = _prepare(m)
     if e:
@@ -156,6 +159,8 @@ def LinearStatic(out, m: Model, *lcs: LoadCase) -> Optional[HdError]:
 def Modal(out, m: Model, mc: ModalCase) -> Optional[HdError]:
     name = "Modal Analysis"
     mc.reset()
+    if out is not None:
+        out.write(name + "\n")  # model.go:729-730
     errs: List[str] = []
     e = _prepare(m)
     if e:
@@ -191,15 +196,24 @@ def Modal(out, m: Model, mc: ModalCase) -> Optional[HdError]:
 
 def Run(out, m: Model, lcs: List[LoadCase], mcs: List[ModalCase]) -> Optional[HdError]:
     causes = []
+    w = out.write if out is not None else (lambda s: None)
+    w(report.model_string(m) + "\n")
     if len(lcs) > 0:
         err = LinearStatic(out, m, *lcs)
         if err is not None:
             causes.append(err)
+        w("\n\n")
+        for lc in lcs:
+            w(report.load_case_string(lc) + "\n")
+    w("\n\n")
     for mc in mcs:
         err = Modal(out, m, mc)
         if err is not None:
             causes.append(err)
             continue
+        w("\n\n")
+        w(report.modal_case_string(mc) + "\n")
+    w("\n\n")
     return HdError("Run function", causes) if causes else None
 
 

@@ -5,12 +5,15 @@
 //   hd::LinearStatic(m, lcs)    hd.LinearStatic model.go:358-605   (buckling block not on the GPU yet)
 //   hd::Modal(m, mc)            hd.Modal        model.go:719-851
 // Nothing throws for bad input: an Error value is returned (empty == nil) and Run keeps going after a
-// failed case (model.go:937-939, 951-954).  The text report (`out io.Writer`) stays host formatting in
-// the reference and is not reproduced.  All arithmetic runs in libhdb200.so on the GPU.
+// failed case (model.go:937-939, 951-954).  The text report (`out io.Writer`) is hd::String(...) and the
+// Run overload taking a std::string *out, byte for byte the reference's.  All arithmetic runs in libhdb200.so on
+// the GPU.
 #pragma once
 #include <array>
 #include <cmath>
+#include <cstdarg>
 #include <cstdint>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -229,20 +232,149 @@ inline Error Modal(Model &m, ModalCase &mc)
     return e;
 }
 
-inline Error Run(Model &m, std::vector<LoadCase> &lcs, std::vector<ModalCase> &mcs)
+// ---- text report: Model.String (model.go:853-924), LoadCase.String (:132-211), ModalCase.String (:235-255) ----
+namespace detail {
+inline void outf(std::string &o, const char *fmt, ...)
+{
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    o += buf;
+}
+inline void row3(std::string &o, size_t i, const std::array<double, 3> &v) { outf(o, "%5zu %15.5e %15.5e %15.5e\n", i, v[0], v[1], v[2]); }
+} // namespace detail
+
+inline std::string String(const Model &m)
+{
+    using detail::outf;
+    std::string o = "\nPoint coordinates:\n";
+    outf(o, "%37s %17s\n", "", "   SUPPORT DIRECTION");
+    outf(o, "%5s %15s %15s ", "Index", "X, m", "Y, m");
+    outf(o, "%5s %5s %5s (0 - free, 1 - fixed)\n", "SX", "SY", "SM");
+    for (size_t i = 0; i < m.Points.size(); i++) {
+        outf(o, "%5zu %15.5f %15.5f ", i, m.Points[i][0], m.Points[i][1]);
+        for (int j = 0; j < 3; j++) outf(o, "%5d ", m.Supports[i][j] ? 1 : 0); // the blank follows all three (model.go:873)
+        o += "\n";
+    }
+    o += "Beam property:\n";
+    outf(o, "%5s %15s %15s ", "Index", "Start point", "End point");
+    outf(o, "%15s %15s %15s\n", "Area,sq.m", "Moment inertia,m4", "Elasticity,Pa");
+    for (size_t i = 0; i < m.Beams.size(); i++) {
+        outf(o, "%5zu %15lld %15lld ", i, (long long)m.Beams[i].N[0], (long long)m.Beams[i].N[1]);
+        outf(o, "%15.5e %15.5e %15.5e\n", m.Beams[i].A, m.Beams[i].J, m.Beams[i].E);
+    }
+    bool header = false;
+    for (size_t k = 0; k < m.Pins.size(); k++) {
+        bool any = false;
+        for (int i = 0; i < 6; i++) any = any || m.Pins[k][i];
+        if (!any) continue;
+        if (!header) {
+            o += "Pins of beam in local system coordinate:\n";
+            outf(o, "%5s %23s %23s\n", "", "START OF BEAM     ", "END OF BEAM       ");
+            outf(o, "%5s %23s %23s\n", "", "------------------", "------------------");
+            outf(o, "%5s %7s %7s %7s %7s %7s %7s\n", "Index", "X", "Y", "M", "X", "Y", "M");
+            header = true;
+        }
+        outf(o, "%5zu ", k);
+        for (int i = 0; i < 6; i++) outf(o, i < 5 ? "%7s " : "%7s", m.Pins[k][i] ? "true" : "false");
+        o += "\n";
+    }
+    if (!header) o += "All beams haven`t pins\n";
+    return o;
+}
+
+inline std::string String(const LoadCase &lc)
+{
+    using detail::outf;
+    std::string o = "\nLoad case:\n";
+    outf(o, "%5s %15s %15s %15s\n", "Point", "Fx, N", "Fy, N", "M, N*m");
+    for (auto &ln : lc.LoadNodes) outf(o, "%5lld %15.5f %15.5f %15.5f\n", (long long)ln.N, ln.Forces[0], ln.Forces[1], ln.Forces[2]);
+    if (!lc.PointDisplacementGlobal.empty()) {
+        o += "Point displacement in global system coordinate:\n";
+        outf(o, "%5s %15s %15s %15s\n", "Point", "DX, m", "DY, m", "Angle, rad.");
+        for (size_t i = 0; i < lc.PointDisplacementGlobal.size(); i++) detail::row3(o, i, lc.PointDisplacementGlobal[i]);
+    }
+    if (!lc.BeamForces.empty()) {
+        o += "Local force in beam:\n";
+        outf(o, "%5s %45s %45s\n", "", "START OF BEAM     ", "END OF BEAM       ");
+        outf(o, "%5s %45s %45s\n", "", "------------------------------------", "------------------------------------");
+        outf(o, "%5s %15s %15s %15s %15s %15s %15s\n", "Index", "Fx, N", "Fy, N", "M, N*m", "Fx, N", "Fy, N", "M, N*m");
+        for (size_t i = 0; i < lc.BeamForces.size(); i++) {
+            outf(o, "%5zu ", i);
+            for (int j = 0; j < 6; j++) outf(o, j < 5 ? "%15.5e " : "%15.5e", lc.BeamForces[i][j]);
+            o += "\n";
+        }
+    }
+    if (!lc.Reactions.empty()) {
+        o += "Reaction on support:\n";
+        outf(o, "%5s %15s %15s %15s\n", "Index", "Fx, N", "Fy, N", "M, N*m");
+        for (size_t i = 0; i < lc.Reactions.size(); i++) {
+            const auto &r = lc.Reactions[i];
+            if (r[0] == 0 && r[1] == 0 && r[2] == 0) continue; // points without reaction are not listed (model.go:184-188)
+            detail::row3(o, i, r);
+        }
+    }
+    if (!lc.LinearBucklingResult.empty()) {
+        o += "\nLinear buckling result:\n";
+        for (auto &lbr : lc.LinearBucklingResult) {
+            outf(o, "Linear buckling factor: %15.5f\n", lbr.Factor);
+            outf(o, "%5s %15s %15s %15s\n", "Point", "X", "Y", "M");
+            for (size_t i = 0; i < lbr.PointDisplacementGlobal.size(); i++) detail::row3(o, i, lbr.PointDisplacementGlobal[i]);
+        }
+    } else if (lc.AmountLinearBuckling == 0) {
+        o += "\nLinear buckling result: is not calculated\n";
+    } else {
+        o += "\nLinear buckling result: haven`t valid data. Probably all beams are tension\n";
+    }
+    return o;
+}
+
+inline std::string String(const ModalCase &mc)
+{
+    using detail::outf;
+    std::string o = "\nModal case:\n";
+    outf(o, "%5s %15s\n", "Point", "Mass, N");
+    for (auto &mn : mc.ModalMasses) outf(o, "%5lld %15.5f\n", (long long)mn.N, mn.Mass);
+    for (auto &mr : mc.Result) {
+        outf(o, "Natural frequency : %15.5f Hz\n", mr.Hz);
+        outf(o, "%5s %15s %15s %15s\n", "Point", "X", "Y", "M");
+        for (size_t i = 0; i < mr.ModalDisplacement.size(); i++) detail::row3(o, i, mr.ModalDisplacement[i]);
+    }
+    return o;
+}
+
+// out == nullptr: no report (hd.Run with a nil writer); otherwise the text hd.Run prints is appended to *out
+inline Error Run(std::string *out, Model &m, std::vector<LoadCase> &lcs, std::vector<ModalCase> &mcs)
 {
     Error et;
+    std::string sink;
+    std::string &o = out ? *out : sink;
+    o += String(m) + "\n";
     if (!lcs.empty()) {
         std::vector<LoadCase *> arr;
         for (auto &lc : lcs) arr.push_back(&lc);
+        o += "Linear Elastic Analysis\n"; // model.go:370-371
         Error e = LinearStatic(m, arr);
         if (e) et.add(e);
+        o += "\n\n";
+        for (auto &lc : lcs) o += String(lc) + "\n";
     }
+    o += "\n\n";
     for (auto &mc : mcs) {
+        o += "Modal Analysis\n"; // model.go:729-730
         Error e = Modal(m, mc);
-        if (e) et.add(e);
+        if (e) {
+            et.add(e);
+            continue;
+        }
+        o += "\n\n" + String(mc) + "\n";
     }
+    o += "\n\n";
     return et;
 }
+
+inline Error Run(Model &m, std::vector<LoadCase> &lcs, std::vector<ModalCase> &mcs) { return Run(nullptr, m, lcs, mcs); }
 
 } // namespace hd

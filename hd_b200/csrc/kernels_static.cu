@@ -530,7 +530,8 @@ __device__ __forceinline__ void beam_forces_rigid(const BeamCoef &cf, const doub
     const double sh = fma(cf.EJL2, z2 + z5, cf.EJL3 * (z1 - z4));
     const double m0 = fma(cf.EJL, z5, fma(cf.EJL4, z2, cf.EJL2 * (z1 - z4)));
     const double m1 = fma(cf.EJL4, z5, fma(cf.EJL, z2, cf.EJL2 * (z1 - z4)));
-    o[0] = ax; o[1] = sh; o[2] = m0; o[3] = -ax; o[4] = -sh; o[5] = m1;
+    // 0 - x, not -x: the reference accumulates every force from +0 (gonum Dgemv), so it never prints a negative zero
+    o[0] = ax; o[1] = sh; o[2] = m0; o[3] = 0.0 - ax; o[4] = 0.0 - sh; o[5] = m1;
 }
 
 __device__ __noinline__ void beam_forces_pinned(const BeamCoef cf, const uint32_t pm, const double gc, const double gs, // cf by value: a reference would pin the caller's copy to local memory
@@ -549,7 +550,7 @@ __device__ __noinline__ void beam_forces_pinned(const BeamCoef cf, const uint32_
         double acc = k[i * 6] * z[0];
 #pragma unroll
         for (int l = 1; l < 6; l++) acc = fma(k[i * 6 + l], z[l], acc);
-        o[i] = acc;
+        o[i] = acc + 0.0; // -0 -> +0, as a sum started from +0 gives (see beam_forces_rigid)
     }
 }
 

@@ -38,6 +38,10 @@ class Model:
     def clone(self) -> "Model":
         return copy.deepcopy(self)
 
+    def String(self) -> str:  # model.go:853-924
+        from .report import model_string
+        return model_string(self)
+
 
 @dataclass
 class LoadNode:
@@ -66,6 +70,10 @@ class LoadCase:
         self.Reactions = None
         self.LinearBucklingResult = None
 
+    def String(self) -> str:  # model.go:132-211
+        from .report import load_case_string
+        return load_case_string(self)
+
 
 @dataclass
 class ModalMass:
@@ -86,3 +94,7 @@ class ModalCase:
 
     def reset(self) -> None:  # model.go:231-233
         self.Result = None
+
+    def String(self) -> str:  # model.go:235-255
+        from .report import modal_case_string
+        return modal_case_string(self)

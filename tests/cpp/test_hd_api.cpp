@@ -14,7 +14,7 @@
 
 static bool close6(double a, double b) { return std::fabs(a - b) <= 1.01e-5 * std::fabs(b) + 1e-30; }
 
-int main()
+int main(int argc, char **argv)
 {
     { // ConsoleBeam: golden "beam" (example/testdata/beam)
         hd::Model m;
@@ -26,9 +26,16 @@ int main()
         lcs[1].LoadNodes = {{1, {10, 0, 0}}, {1, {0, 2.3, 0}}};
         std::vector<hd::ModalCase> mcs(1);
         mcs[0].ModalMasses = {{1, 10000}};
-        hd::Error err = hd::Run(m, lcs, mcs);
+        std::string report;
+        hd::Error err = hd::Run(&report, m, lcs, mcs);
         if (err) std::printf("%s", err.str().c_str());
         CHECK(!err);
+        if (argc > 1) { // the caller compares the report with the golden file's digest (example_test.go:12-77)
+            FILE *f = std::fopen(argv[1], "wb");
+            CHECK(f != nullptr);
+            std::fwrite(report.data(), 1, report.size(), f);
+            std::fclose(f);
+        }
         CHECK(m.Pins.size() == 1); // prepare() fills Pins (model.go:344-346)
         for (auto &lc : lcs) {
             CHECK(close6(lc.PointDisplacementGlobal[1][0], 4.16667e-08));

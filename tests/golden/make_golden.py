@@ -9,7 +9,9 @@ example_test.go:12-77 and model_test.go:551).  Numbers are printed with %15.5e /
 6 significant digits.  Output: tests/golden/golden.json with, per file,
   static: [ {disp[nP][3], forces[nB][6], react{point:[3]}, buckling:[{factor, shape[nP][3]}] | null} ]
   modal:  [ [ {hz, shape[nP][3]} ] ]
-Only numbers are extracted; no reference text or source is copied.
+Only numbers are extracted; no reference text or source is copied.  For the report writer
+(hd_b200/report.py) golden_text.json adds two sha256 digests per file: of the whole text and of its skeleton
+(tests/report_util.skeleton: every %e / %f number masked).
 """
 from __future__ import annotations
 
@@ -105,6 +107,23 @@ def main():
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden.json")
     with open(dst, "w") as f:
         json.dump(out, f, indent=None, separators=(",", ":"))
+        f.write("\n")
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    text = {}
+    dst_text = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_text.json")
+    if not os.path.exists(dst_text):
+        with open(dst_text, "w") as f:
+            f.write("{}\n")  # report_util loads it at import
+    import report_util
+
+    for n in NAMES:
+        with open(os.path.join(REF, n)) as f:
+            t = f.read()
+        text[n] = {"sha256": report_util.digest(t), "skeleton_sha256": report_util.digest(report_util.skeleton(t)),
+                   "lines": t.count("\n")}
+    with open(dst_text, "w") as f:
+        json.dump(text, f, indent=1, sort_keys=True)
         f.write("\n")
     for n in NAMES:
         print(n, "static cases:", len(out[n]["static"]), "modal cases:", [len(x) for x in out[n]["modal"]])

@@ -24,5 +24,21 @@ def test_cpp_host_mirror_compiles(tmp_path):
 @pytest.mark.gpu
 def test_cpp_host_mirror_runs(tmp_path):
     exe = _build(str(tmp_path))
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    rep = os.path.join(str(tmp_path), "beam.txt")
+    r = subprocess.run([exe, rep], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+    # hd::Run's text report of ConsoleBeam against the reference's golden file "beam": same skeleton (one printed
+    # number is round-off noise, 5.7e-16 where the reference has an exact 0), and the same text as the Python mirror
+    import io
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fixtures
+    import report_util
+    from hd_b200 import api
+    with open(rep, newline="") as f:
+        text = f.read()
+    assert report_util.digest(report_util.skeleton(text)) == report_util.GOLD_TEXT["beam"]["skeleton_sha256"]
+    m, lcs, mcs = fixtures.GOLDEN["beam"]()
+    out = io.StringIO()
+    assert api.Run(out, m, lcs, mcs) is None
+    assert out.getvalue() == text
