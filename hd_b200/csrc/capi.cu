@@ -178,6 +178,37 @@ static int ensure_device(hdb_topology *t)
             UP(g, gEll);
         }
         UP(ell(S.rgptr, pad(S.rgsrc), S.nnzR, D.rgWidth), rgEll);
+        { // compact element store (k_assemble_quad): per beam 8 values (+1 pad) without pins, 36 (+1) with
+            std::vector<int32_t> keOff((size_t)S.nB);
+            int len = 0;
+            for (int b = 0; b < S.nB; b++) {
+                keOff[b] = len;
+                len += S.pinMask[b] ? 37 : 9;
+            }
+            const unsigned long long negMask = HD_RIGID_NEG;
+            auto compact = [&](const std::vector<int32_t> &src) { // codes beam*36 + position
+                std::vector<int32_t> o(src.size());
+                for (size_t i = 0; i < src.size(); i++) {
+                    const int b = src[i] / 36, e = src[i] % 36;
+                    if (S.pinMask[b]) o[i] = (keOff[b] + e) * 2;
+                    else {
+                        int v = 0;
+                        while (!((HD_RIGID_POS(v) >> e) & 1ull)) v++;
+                        o[i] = (keOff[b] + v) * 2 + (int)((negMask >> e) & 1ull);
+                    }
+                }
+                return o;
+            };
+            int w1 = 0, w2 = 0;
+            std::vector<int32_t> cg = ell(S.gptr, compact(S.gsrc), S.nSlots, w1);
+            for (int s2 = 0; s2 < S.nSlots && w1; s2++)
+                if (S.slotInit[s2]) cg[s2] = -2;
+            std::vector<int32_t> crg = ell(S.rgptr, compact(S.rgsrc), S.nnzR, w2);
+            D.keLen = (D.gWidth > 0 && D.rgWidth > 0 && w1 == D.gWidth && w2 == D.rgWidth) ? len : 0;
+            UP(cg, cgEll);
+            UP(crg, crgEll);
+            UP(keOff, keOff);
+        }
         std::vector<double> geom((size_t)S.nB * 3);
         for (int b = 0; b < S.nB; b++) { // same routines, same rounding as on the device (element.cuh)
             const int n0 = S.beamN32[2 * b], n1 = S.beamN32[2 * b + 1];

@@ -31,6 +31,12 @@ struct DevTopo {
     // assembly gather lists (codes are padded smem indices beam*KE_LD + local)
     const int32_t *gptr, *gsrc;   // factor slots
     const int32_t *gEll, *rgEll;  // [gWidth][nSlots], [rgWidth][nnzR]: the same lists, fixed width, -1 = none
+    // the same two lists over the compact element store of k_assemble_quad: code = (keOff[beam] + value) * 2 + negate,
+    // -1 = none, -2 = unit diagonal of a dummy unknown; a beam without pins keeps its 8 distinct values
+    // (element.cuh: rigid_global_values), a beam with pins all 36 entries
+    const int32_t *cgEll, *crgEll;
+    const int32_t *keOff;         // [nB] first value of a beam in the compact store
+    int keLen;                    // values per model in the compact store; 0 = the compact lists were not built
     const double *geom;           // [nB][3] cos, sin, length of every beam (element.cuh routines, evaluated once on the host)
     const uint8_t *slotInit;      // [nSlots]
     const int32_t *rgptr, *rgsrc; // reaction entries

@@ -219,4 +219,39 @@ HD_FN void rotate_to_global(const double k[36], double c, double s, double kg[36
     }
 }
 
+// The same product for a beam without pins, written out: k has 18 non-zero entries built from five values, so the
+// 36 results are eight distinct values and their negations.  Every sum below is the reference's own sequence of
+// rounded operations (a zero term it adds or skips changes nothing, a sign flips exactly), hence bit-identical to
+// rotate_to_global(stiff_beam2d(cf, 0), c, s).  d[8] = {x1, x2, x3, x4, r, w, EJL4, EJL}:
+//   row 0: [ x1  x2 -r -x1 -x2 -r]   row 1: [ x3  x4  w -x3 -x4  w]   row 2: [-r  w EJL4  r -w EJL ]
+//   row 3: -row 0                    row 4: -row 1                    row 5: [-r  w EJL   r -w EJL4]
+HD_FN void rigid_global_values(const BeamCoef &cf, double c, double s, double d[8])
+{
+    const double p = HD_MUL(c, cf.EFL), t = HD_MUL(s, cf.EFL), q = HD_MUL(s, cf.EJL3), u = HD_MUL(c, cf.EJL3);
+    d[0] = HD_ADD(HD_MUL(p, c), HD_MUL(q, s));
+    d[1] = HD_SUB(HD_MUL(p, s), HD_MUL(q, c));
+    d[2] = HD_SUB(HD_MUL(t, c), HD_MUL(u, s));
+    d[3] = HD_ADD(HD_MUL(t, s), HD_MUL(u, c));
+    d[4] = HD_MUL(s, cf.EJL2);
+    d[5] = HD_MUL(c, cf.EJL2);
+    d[6] = cf.EJL4;
+    d[7] = cf.EJL;
+}
+// matrix positions (bit e = row * 6 + col) that hold +-d[i]
+#define HD_RIGID_POS(i)                                                                                             \
+    ((i) == 0 ? 0x240009ull : (i) == 1 ? 0x480012ull : (i) == 2 ? 0x9000240ull : (i) == 3 ? 0x12000480ull          \
+     : (i) == 4 ? 0x240909024ull : (i) == 5 ? 0x4a4012900ull : (i) == 6 ? 0x800004000ull : 0x100020000ull)
+// matrix positions that hold -d[i] rather than +d[i] (the minus signs of rigid_global_expand)
+#define HD_RIGID_NEG 0x4670d163cull
+HD_FN void rigid_global_expand(const double d[8], double kg[36])
+{
+    const double x1 = d[0], x2 = d[1], x3 = d[2], x4 = d[3], r = d[4], w = d[5], G = d[6], F = d[7];
+    kg[0] = x1;   kg[1] = x2;   kg[2] = -r;  kg[3] = -x1;  kg[4] = -x2;  kg[5] = -r;
+    kg[6] = x3;   kg[7] = x4;   kg[8] = w;   kg[9] = -x3;  kg[10] = -x4; kg[11] = w;
+    kg[12] = -r;  kg[13] = w;   kg[14] = G;  kg[15] = r;   kg[16] = -w;  kg[17] = F;
+    kg[18] = -x1; kg[19] = -x2; kg[20] = r;  kg[21] = x1;  kg[22] = x2;  kg[23] = r;
+    kg[24] = -x3; kg[25] = -x4; kg[26] = -w; kg[27] = x3;  kg[28] = x4;  kg[29] = -w;
+    kg[30] = -r;  kg[31] = w;   kg[32] = F;  kg[33] = r;   kg[34] = -w;  kg[35] = G;
+}
+
 } // namespace hdb

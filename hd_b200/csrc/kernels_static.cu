@@ -119,16 +119,35 @@ __global__ void __launch_bounds__(MAXT, MINB) k_assemble(const DevTopo T, const 
         if (!(section_ok(A) && section_ok(J) && section_ok(E))) flag = max(flag, (int)HDB_STATUS_NONFINITE);
         const BeamGeom g = beam_geom(T, b);
         const BeamCoef cf = beam_coef(A, J, E, g.length);
-        double k[36], kg[36];
-        stiff_beam2d(cf, T.pinMask[b], k);
-        rotate_to_global(k, g.c, g.s, kg);
+        double kg[36];
         const unsigned long long dr = T.droppedMask[b]; // bit e: matrix position e is absent from the representative pattern
+        const uint32_t pm = T.pinMask[b];
+        if (pm == 0) { // rigid ends: eight distinct values (element.cuh), checked once each
+            double d[8];
+            rigid_global_values(cf, g.c, g.s, d);
+            unsigned long long nz = 0;
+            bool fin = true;
 #pragma unroll
-        for (int e = 0; e < 36; e++) {
-            const double v = kg[e];
-            ke[b * KE_LD + e] = v;
-            if (!isfinite(v)) flag = max(flag, (int)HDB_STATUS_NONFINITE);
-            else if (((dr >> e) & 1ull) && v != 0.0) flag = max(flag, (int)HDB_STATUS_PATTERN);
+            for (int i = 0; i < 8; i++) {
+                fin = fin && isfinite(d[i]);
+                if (d[i] != 0.0) nz |= HD_RIGID_POS(i);
+            }
+            if (!fin) flag = max(flag, (int)HDB_STATUS_NONFINITE);
+            else if (dr & nz) flag = max(flag, (int)HDB_STATUS_PATTERN);
+            rigid_global_expand(d, kg);
+#pragma unroll
+            for (int e = 0; e < 36; e++) ke[b * KE_LD + e] = kg[e];
+        } else {
+            double k[36];
+            stiff_beam2d(cf, pm, k);
+            rotate_to_global(k, g.c, g.s, kg);
+#pragma unroll
+            for (int e = 0; e < 36; e++) {
+                const double v = kg[e];
+                ke[b * KE_LD + e] = v;
+                if (!isfinite(v)) flag = max(flag, (int)HDB_STATUS_NONFINITE);
+                else if (((dr >> e) & 1ull) && v != 0.0) flag = max(flag, (int)HDB_STATUS_PATTERN);
+            }
         }
     }
     if (flag) atomicMax(&s_flag, flag == HDB_STATUS_NONFINITE ? 100 : flag); // NONFINITE wins
@@ -170,6 +189,190 @@ __global__ void __launch_bounds__(MAXT, MINB) k_assemble(const DevTopo T, const 
     if (tid == 0) L.status[model] = (s_flag == 100) ? (int)HDB_STATUS_NONFINITE : s_flag;
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_assemble_quad: the same assembly for four models per block.  The element store is compact (eight distinct values
+// of a beam without pins, element.cuh; 36 of a beam with pins) and interleaved over the four models, so one gather
+// index load serves four models, the four values come with two 16-byte shared loads and a slot of the tiled
+// workspace W is written as one full 32-byte sector.  Sums run in the same (beam) order with the same rounded
+// additions as k_assemble: the results are bit-identical.
+// ------------------------------------------------------------------------------------------------
+constexpr int QUAD = 4;
+constexpr int QUAD_THREADS = 320;
+
+__device__ __forceinline__ double flip_sign(double v, int sg) { return __hiloint2double(__double2hiint(v) ^ sg, __double2loint(v)); }
+
+template <int W, int U>
+__device__ __forceinline__ void gather_quad(const int32_t *__restrict__ ell, const int n, const int s, const int stride, const double *ke4,
+                                            double (&sum)[U][QUAD])
+{
+    int idx[U][W];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int k = 0; k < W; k++) idx[u][k] = (s + u * stride < n) ? __ldg(ell + (size_t)k * n + s + u * stride) : -1;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const double init = idx[u][0] == -2 ? 1.0 : 0.0; // unit diagonal of a dummy unknown
+#pragma unroll
+        for (int m = 0; m < QUAD; m++) sum[u][m] = init;
+#pragma unroll
+        for (int k = 0; k < W; k++)
+            if (idx[u][k] >= 0) {
+                const double2 *p = reinterpret_cast<const double2 *>(ke4 + (size_t)(idx[u][k] >> 1) * QUAD);
+                const double2 a = p[0], b = p[1];
+                const int sg = (idx[u][k] & 1) << 31;
+                sum[u][0] = __dadd_rn(sum[u][0], flip_sign(a.x, sg));
+                sum[u][1] = __dadd_rn(sum[u][1], flip_sign(a.y, sg));
+                sum[u][2] = __dadd_rn(sum[u][2], flip_sign(b.x, sg));
+                sum[u][3] = __dadd_rn(sum[u][3], flip_sign(b.y, sg));
+            }
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void quad_slots(const DevTopo &T, const StaticLaunch &L, const double *ke4, const int model0, const int nm,
+                                           const int tid, const int nthreads)
+{
+    constexpr int U = 2;
+    double *wbase = L.W + w_tile_base(T, model0); // model0 is a multiple of 4: 32-byte aligned rows
+    for (int s = tid; s < T.nSlots; s += U * nthreads) {
+        double sum[U][QUAD];
+        gather_quad<W, U>(T.cgEll, T.nSlots, s, nthreads, ke4, sum);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int s2 = s + u * nthreads;
+            if (s2 >= T.nSlots) break;
+            double *o = wbase + (size_t)s2 * W_TILE;
+            if (nm == QUAD) {
+                *reinterpret_cast<double2 *>(o) = make_double2(sum[u][0], sum[u][1]);
+                *reinterpret_cast<double2 *>(o + 2) = make_double2(sum[u][2], sum[u][3]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < QUAD; m++)
+                    if (m < nm) o[m] = sum[u][m];
+            }
+        }
+    }
+}
+template <int W>
+__device__ __forceinline__ void quad_react(const DevTopo &T, const StaticLaunch &L, const double *ke4, const int model0, const int nm,
+                                           const int tid, const int nthreads)
+{
+    constexpr int U = 2;
+    for (int s = tid; s < T.nnzR; s += U * nthreads) {
+        double sum[U][QUAD];
+        gather_quad<W, U>(T.crgEll, T.nnzR, s, nthreads, ke4, sum);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int s2 = s + u * nthreads;
+            if (s2 >= T.nnzR) break;
+#pragma unroll
+            for (int m = 0; m < QUAD; m++)
+                if (m < nm) L.Ksf[(size_t)(model0 + m) * T.nnzR + s2] = sum[u][m];
+        }
+    }
+}
+
+// a beam with pins: all 36 entries, literal product (kept out of line: its two 6x6 arrays would set the register
+// budget of the whole kernel)
+__device__ __noinline__ int quad_pinned_beam(const BeamCoef cf, const uint32_t pm, const double c, const double s, const unsigned long long dr,
+                                             double *dst)
+{
+    double k[36], kg[36];
+    int flag = 0;
+    stiff_beam2d(cf, pm, k);
+    rotate_to_global(k, c, s, kg);
+#pragma unroll
+    for (int e = 0; e < 36; e++) {
+        const double v = kg[e];
+        dst[e * QUAD] = v;
+        if (!isfinite(v)) flag = max(flag, (int)HDB_STATUS_NONFINITE);
+        else if (((dr >> e) & 1ull) && v != 0.0) flag = max(flag, (int)HDB_STATUS_PATTERN);
+    }
+    return flag;
+}
+
+__global__ void __launch_bounds__(QUAD_THREADS, 3) k_assemble_quad(const DevTopo T, const StaticLaunch L)
+{
+    extern __shared__ double smem_d[]; // ke4[keLen][QUAD]
+    __shared__ int s_flag[QUAD];
+    double *ke4 = smem_d;
+    const int model0 = blockIdx.x * QUAD;
+    const int nm = min(QUAD, L.nModels - model0);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    if (tid < QUAD) s_flag[tid] = 0;
+    __syncthreads();
+
+    // phase A: one thread per beam, two models at a time
+    for (int b = tid; b < T.nB; b += nthreads) {
+        const BeamGeom g = beam_geom(T, b);
+        const unsigned long long dr = T.droppedMask[b];
+        const uint32_t pm = T.pinMask[b];
+        double *dst = ke4 + (size_t)T.keOff[b] * QUAD;
+#pragma unroll 1
+        for (int half = 0; half < QUAD; half += 2) {
+            double d[2][8];
+            int flag[2] = {0, 0};
+            BeamCoef cf[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int mm = min(half + j, nm - 1); // a block past the end of the batch repeats its last model
+                const double *sec = L.sections + ((size_t)(model0 + mm) * T.nB + b) * 3;
+                const double A = sec[0], J = sec[1], E = sec[2];
+                if (!(section_ok(A) && section_ok(J) && section_ok(E))) flag[j] = HDB_STATUS_NONFINITE;
+                cf[j] = beam_coef(A, J, E, g.length);
+            }
+            if (pm == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    rigid_global_values(cf[j], g.c, g.s, d[j]);
+                    unsigned long long nz = 0;
+                    bool fin = true;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        fin = fin && isfinite(d[j][i]);
+                        if (d[j][i] != 0.0) nz |= HD_RIGID_POS(i);
+                    }
+                    if (!fin) flag[j] = max(flag[j], (int)HDB_STATUS_NONFINITE);
+                    else if (dr & nz) flag[j] = max(flag[j], (int)HDB_STATUS_PATTERN);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) *reinterpret_cast<double2 *>(dst + i * QUAD + half) = make_double2(d[0][i], d[1][i]);
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < 2; j++) flag[j] = max(flag[j], quad_pinned_beam(cf[j], pm, g.c, g.s, dr, dst + half + j));
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                if (flag[j]) atomicMax(&s_flag[half + j], flag[j] == HDB_STATUS_NONFINITE ? 100 : flag[j]); // NONFINITE wins
+        }
+    }
+    __syncthreads();
+
+    // phase B: one thread per slot and four models
+    switch (T.gWidth) { // block-uniform
+    case 1: quad_slots<1>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 2: quad_slots<2>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 3: quad_slots<3>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 4: quad_slots<4>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 5: quad_slots<5>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 6: quad_slots<6>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 7: quad_slots<7>(T, L, ke4, model0, nm, tid, nthreads); break;
+    default: quad_slots<8>(T, L, ke4, model0, nm, tid, nthreads); break;
+    }
+    switch (T.rgWidth) {
+    case 1: quad_react<1>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 2: quad_react<2>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 3: quad_react<3>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 4: quad_react<4>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 5: quad_react<5>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 6: quad_react<6>(T, L, ke4, model0, nm, tid, nthreads); break;
+    case 7: quad_react<7>(T, L, ke4, model0, nm, tid, nthreads); break;
+    default: quad_react<8>(T, L, ke4, model0, nm, tid, nthreads); break;
+    }
+    if (tid < nm) L.status[model0 + tid] = (s_flag[tid] == 100) ? (int)HDB_STATUS_NONFINITE : s_flag[tid];
+}
+
 bool assemble_fits_smem(const DevTopo &T, int smemOptin)
 {
     return (size_t)T.nB * KE_LD * sizeof(double) + 1024 <= (size_t)smemOptin;
@@ -177,6 +380,21 @@ bool assemble_fits_smem(const DevTopo &T, int smemOptin)
 
 cudaError_t launch_assemble(const DevTopo &T, const StaticLaunch &L, cudaStream_t st)
 {
+    { // four models per block over the compact element store, when two such blocks fit an SM
+        const size_t quadSmem = (size_t)T.keLen * QUAD * sizeof(double);
+        const char *off = std::getenv("HDB_ASSEMBLE_SINGLE"); // diagnostics: the one-model kernel
+        if (T.keLen > 0 && !L.kval && !L.keScratch && quadSmem <= 110 * 1024 && !(off && atoi(off))) {
+            if (quadSmem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(k_assemble_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)quadSmem);
+                if (e != cudaSuccess) return e;
+            }
+            cudaFuncSetAttribute(k_assemble_quad, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            int th = ((T.nB + 31) / 32) * 32;
+            th = th < 128 ? 128 : (th > QUAD_THREADS ? QUAD_THREADS : th);
+            k_assemble_quad<<<(L.nModels + QUAD - 1) / QUAD, th, quadSmem, st>>>(T, L);
+            return cudaGetLastError();
+        }
+    }
     const size_t smem = L.keScratch ? 0 : (size_t)T.nB * KE_LD * sizeof(double);
     int threads = ((T.nB + 31) / 32) * 32;
     threads = threads < 128 ? 128 : (threads > ASM_MAX_THREADS ? ASM_MAX_THREADS : threads);
