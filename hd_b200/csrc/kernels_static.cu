@@ -197,7 +197,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_assemble(const DevTopo T, const 
 // additions as k_assemble: the results are bit-identical.
 // ------------------------------------------------------------------------------------------------
 constexpr int QUAD = 4;
-constexpr int QUAD_THREADS = 320;
+#ifndef QUAD_T
+#define QUAD_T 320
+#endif
+#ifndef QUAD_B
+#define QUAD_B 3
+#endif
+#ifndef QUAD_U
+#define QUAD_U 2
+#endif
+constexpr int QUAD_THREADS = QUAD_T;
 
 __device__ __forceinline__ double flip_sign(double v, int sg) { return __hiloint2double(__double2hiint(v) ^ sg, __double2loint(v)); }
 
@@ -233,7 +242,7 @@ template <int W>
 __device__ __forceinline__ void quad_slots(const DevTopo &T, const StaticLaunch &L, const double *ke4, const int model0, const int nm,
                                            const int tid, const int nthreads)
 {
-    constexpr int U = 2;
+    constexpr int U = QUAD_U;
     double *wbase = L.W + w_tile_base(T, model0); // model0 is a multiple of 4: 32-byte aligned rows
     for (int s = tid; s < T.nSlots; s += U * nthreads) {
         double sum[U][QUAD];
@@ -258,7 +267,7 @@ template <int W>
 __device__ __forceinline__ void quad_react(const DevTopo &T, const StaticLaunch &L, const double *ke4, const int model0, const int nm,
                                            const int tid, const int nthreads)
 {
-    constexpr int U = 2;
+    constexpr int U = QUAD_U;
     for (int s = tid; s < T.nnzR; s += U * nthreads) {
         double sum[U][QUAD];
         gather_quad<W, U>(T.crgEll, T.nnzR, s, nthreads, ke4, sum);
@@ -292,7 +301,7 @@ __device__ __noinline__ int quad_pinned_beam(const BeamCoef cf, const uint32_t p
     return flag;
 }
 
-__global__ void __launch_bounds__(QUAD_THREADS, 3) k_assemble_quad(const DevTopo T, const StaticLaunch L)
+__global__ void __launch_bounds__(QUAD_THREADS, QUAD_B) k_assemble_quad(const DevTopo T, const StaticLaunch L)
 {
     extern __shared__ double smem_d[]; // ke4[keLen][QUAD]
     __shared__ int s_flag[QUAD];
