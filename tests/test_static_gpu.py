@@ -498,3 +498,42 @@ def test_statuses_across_case_passes(oracle):
     # the cases before the offending one are complete and correct (model.go:415-437: earlier cases keep their results)
     compare_rule(od[0][:45], disp[1][:45])
     t.close()
+
+
+def test_quad_assembly_is_bit_identical_to_the_single_model_kernel(oracle, monkeypatch):
+    """k_assemble_quad (four models per block, written-out matrices of beams without pins, compact element store)
+    against k_assemble (literal products; the kernel test_assembly_bit_exact_* pin to the oracle bit for bit):
+    the same sums in the same order, so every result of the whole path must have the same bits.  Batch sizes leave
+    1, 2 and 3 models in the last block; the truss has pins on every beam, the skew frame mixes both kinds."""
+    from hd_b200.model import BeamProp, Model
+    rng = np.random.default_rng(77)
+    cases = []
+    m8 = frames.uniform_frame(8)
+    cases.append((oracle.flatten_model(m8), 33, 2))
+    mt, _, _ = fixtures.truss()
+    # only A varies on the truss: with every end released the literal condensation (feBeam2d.go:58-137, no guard on
+    # a zero pivot) is finite for some J and not for others, in the reference as here
+    cases.append((oracle.flatten_model(mt), 6, 1))
+    ms = Model()
+    ms.Points = [[0.0, 0.0], [1.0, 3.0], [4.5, 3.5], [5.0, 0.0], [8.0, 3.0], [9.0, 0.0]]
+    ms.Supports = [[True] * 3, [False] * 3, [False] * 3, [True] * 3, [False] * 3, [True, True, False]]
+    ms.Beams = [BeamProp(N=n, A=12e-4, J=120e-6, E=2e11) for n in ([0, 1], [1, 2], [3, 2], [2, 4], [5, 4])]
+    ms.Pins = [[False] * 6, [False] * 6, [False, False, False, False, False, True], [False] * 6, [False, False, True, False, False, False]]
+    cases.append((oracle.flatten_model(ms), 7, 2))
+    for fm, nM, nvar in cases:
+        sec = np.tile(fm.sections, (nM, 1, 1))
+        sec[:, :, :nvar] *= rng.uniform(0.5, 2.0, size=(nM, fm.nB, nvar))
+        loads = rng.normal(size=(nM, 3, fm.dof)) * 1e3
+        loads[:, :, np.asarray(fm.supports, dtype=bool).reshape(-1)] = 0.0
+        out = {}
+        for single in ("1", "0"):
+            monkeypatch.setenv("HDB_ASSEMBLE_SINGLE", single)
+            t = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports)
+            ld = loads.copy()
+            for g in t.query(_lib.Q_IGNORE):  # no load on DOFs without stiffness (model.go:424-437)
+                ld[:, :, int(g)] = 0.0
+            out[single] = t.static_batch(sec, ld)
+            t.close()
+        assert not out["1"][0].any(), out["1"][0]
+        for a, b in zip(out["1"], out["0"]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
