@@ -84,6 +84,24 @@ func (t *Topology) StaticBatch(nModels, nLC int, sections, loads, disp, forces, 
 	return errOf(rc, "hdb_static_batch")
 }
 
+// StaticBatchGeom is StaticBatch with per-model coordinates points[nModels][nP][2] (hdb_static_batch_geom): the
+// geometry checks of check.go (NaN / Inf coordinates, beams of length zero) come back per model in status.
+func (t *Topology) StaticBatchGeom(nModels, nLC int, points, sections, loads, disp, forces, react []float64,
+	status, failCase []int32) error {
+	p := func(s []float64) *C.double {
+		if len(s) == 0 {
+			return nil
+		}
+		return (*C.double)(unsafe.Pointer(&s[0]))
+	}
+	rc := C.hdb_static_batch_geom(t.h, C.int32_t(nModels), p(points), p(sections), C.int32_t(nLC), p(loads), p(disp),
+		p(forces), p(react), (*C.int32_t)(unsafe.Pointer(&status[0])), (*C.int32_t)(unsafe.Pointer(&failCase[0])))
+	runtime.KeepAlive(points)
+	runtime.KeepAlive(sections)
+	runtime.KeepAlive(loads)
+	return errOf(rc, "hdb_static_batch_geom")
+}
+
 // ModalBatch is Modal for nModels models (model.go:719-851). massN is shared, mass [nModels][len(massN)].
 func (t *Topology) ModalBatch(nModels int, sections []float64, massN []int, mass []float64, maxModes int,
 	nModes []int32, hz, shapes []float64, status []int32) error {

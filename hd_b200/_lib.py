@@ -22,7 +22,7 @@ Q_ELIMINATED, Q_IGNORE, Q_CSR_ROWPTR, Q_CSR_COLIND, Q_SCATTER, Q_FREE_INDEX, Q_P
 SYMBOLS = [
     "hdb_topology_create", "hdb_topology_destroy", "hdb_topology_get_info", "hdb_topology_query",
     "hdb_check_model", "hdb_check_loads", "hdb_check_modal", "hdb_assemble_node_loads",
-    "hdb_static_batch", "hdb_static_batch_dev", "hdb_assemble_batch", "hdb_element_batch",
+    "hdb_static_batch", "hdb_static_batch_dev", "hdb_static_batch_geom", "hdb_static_batch_geom_dev", "hdb_assemble_batch", "hdb_element_batch",
     "hdb_modal_mode_count", "hdb_modal_batch", "hdb_modal_batch_dev",
     "hdb_buckling_max_free", "hdb_buckling_batch", "hdb_buckling_batch_dev", "hdb_uniform_loads_dev",
     "hdb_host_alloc", "hdb_host_free", "hdb_set_profiling", "hdb_last_kernel_ms", "hdb_launch_count",
@@ -79,6 +79,8 @@ def lib():
         L.hdb_assemble_node_loads.argtypes = [i32, i32, vp, vp]
         L.hdb_static_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
         L.hdb_static_batch_dev.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.hdb_static_batch_geom.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+        L.hdb_static_batch_geom_dev.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         L.hdb_assemble_batch.argtypes = [vp, i32, vp, vp, vp]
         L.hdb_element_batch.argtypes = [vp, i32, vp, vp, vp, vp]
         L.hdb_modal_mode_count.argtypes = [vp, i32, vp]
@@ -186,6 +188,29 @@ class Topology:
                                      _np_ptr(forces), _np_ptr(react), _np_ptr(status), _np_ptr(fail)),
               "hdb_static_batch")
         return status, fail, disp, forces, react
+
+    def static_batch_geom(self, points, sections, loads, want=("disp", "forces", "react")):
+        """static_batch with per-model coordinates points[nModels][nP][2] (hdb_static_batch_geom)."""
+        sections = np.ascontiguousarray(sections, dtype=np.float64).reshape(-1, self.nB, 3)
+        nM = sections.shape[0]
+        points = np.ascontiguousarray(points, dtype=np.float64).reshape(nM, self.nP, 2)
+        loads = np.ascontiguousarray(loads, dtype=np.float64).reshape(nM, -1, self.dof)
+        nLC = loads.shape[1]
+        disp = np.empty((nM, nLC, self.nP, 3)) if "disp" in want else None
+        forces = np.empty((nM, nLC, self.nB, 6)) if "forces" in want else None
+        react = np.empty((nM, nLC, self.nP, 3)) if "react" in want else None
+        status = np.zeros(nM, dtype=np.int32)
+        fail = np.zeros(nM, dtype=np.int32)
+        check(lib().hdb_static_batch_geom(self._h, nM, _np_ptr(points), _np_ptr(sections), nLC, _np_ptr(loads), _np_ptr(disp),
+                                          _np_ptr(forces), _np_ptr(react), _np_ptr(status), _np_ptr(fail)),
+              "hdb_static_batch_geom")
+        return status, fail, disp, forces, react
+
+    def static_batch_geom_dev(self, nModels, points, sections, nLC, loads, disp, forces, react, status, fail, stream=0):
+        """Device tensors (torch) or raw device addresses; asynchronous on `stream`."""
+        check(lib().hdb_static_batch_geom_dev(self._h, nModels, _ptr(points), _ptr(sections), nLC, _ptr(loads), _ptr(disp),
+                                              _ptr(forces), _ptr(react), _ptr(status), _ptr(fail), C.c_void_p(stream)),
+              "hdb_static_batch_geom_dev")
 
     def static_batch_raw(self, nModels, sections, nLC, loads, disp, forces, react, status, fail):
         """Any mix of pinned host buffers / device tensors accepted by hdb_static_batch."""

@@ -217,14 +217,17 @@ def Run(out, m: Model, lcs: List[LoadCase], mcs: List[ModalCase]) -> Optional[Hd
     return HdError("Run function", causes) if causes else None
 
 
-def RunBatch(m: Model, sections, loads, want=("disp", "forces", "react")):
-    """Many models sharing m's topology/geometry: sections[nModels][nB][3], loads[nModels][nLC][dof].
-    Returns (status, failCase, disp, forces, react) as numpy arrays (hdb_static_batch)."""
+def RunBatch(m: Model, sections, loads, want=("disp", "forces", "react"), points=None):
+    """Many models sharing m's topology: sections[nModels][nB][3], loads[nModels][nLC][dof] and, for shape sweeps,
+    points[nModels][nP][2] (default: m's own coordinates for every model).
+    Returns (status, failCase, disp, forces, react) as numpy arrays (hdb_static_batch / hdb_static_batch_geom)."""
     e = _prepare(m)
     if e:
         raise HdError("RunBatch", [e])
     topo = _topology(m)
     try:
+        if points is not None:
+            return topo.static_batch_geom(points, sections, loads, want)
         return topo.static_batch(sections, loads, want)
     finally:
         topo.close()

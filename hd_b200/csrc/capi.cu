@@ -64,6 +64,8 @@ struct hdb_topology {
     // workspace of the device path
     // two workspace sets: the assemble/factor stream prepares sub-batch i+1 while the solve stream works on i
     double *Wbuf[2] = {nullptr, nullptr}, *Lmbuf[2] = {nullptr, nullptr}, *Ksfbuf[2] = {nullptr, nullptr}, *keScratch = nullptr;
+    double *geomBuf = nullptr; // [geomModels][nB][3] per-model beam geometry (hdb_static_batch_geom*)
+    size_t geomModels = 0;
     cudaStream_t prepStream = nullptr;
     cudaEvent_t evFork = nullptr, evPrep[2] = {nullptr, nullptr}, evSolve[2] = {nullptr, nullptr}, evJoin = nullptr;
     long long *dbgClocks = nullptr; // HDB_DEBUG_CLOCKS=1: per-block phase cycle counters of k_solve_pipe
@@ -440,6 +442,7 @@ void hdb_topology_destroy(hdb_topology *t)
         if (t->evJoin) cudaEventDestroy(t->evJoin);
         if (t->prepStream) cudaStreamDestroy(t->prepStream);
         if (t->keScratch) cudaFree(t->keScratch);
+        if (t->geomBuf) cudaFree(t->geomBuf);
         for (auto &c : t->chunk) {
             if (c.base) cudaFree(c.base);
             if (c.evIn) cudaEventDestroy(c.evIn);
@@ -619,7 +622,7 @@ int hdb_last_kernel_ms(hdb_topology *t, float *ms, int32_t capacity)
 // ------------------------------------------------------------------------------------------------
 static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
                           double *disp, double *forces, double *react, int32_t *status, int32_t *failCase,
-                          double *kval, cudaStream_t st, bool solve)
+                          double *kval, cudaStream_t st, bool solve, const double *points = nullptr)
 {
     const Symbolic &S = t->S;
     int cp;
@@ -631,15 +634,20 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
     const int sb = std::min<int>(nModels, t->subBatch);
     int rc = ensure_workspace(t, (size_t)sb);
     if (rc != HDB_OK) return rc;
-    // Two-stage pipeline over sub-batches: assemble + factor of sub-batch i+1 run on the prep stream while
-    // the solve kernel of sub-batch i runs on the caller's stream (the factor kernel is a latency chain on
-    // a few warps per SM and hides completely behind the bandwidth-bound solve).  Two workspace sets.
+    if (points && (size_t)sb > t->geomModels) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (t->geomBuf) cudaFree(t->geomBuf);
+        t->geomBuf = nullptr;
+        t->geomModels = 0;
+        CUDA_TRY(cudaMalloc(&t->geomBuf, (size_t)sb * S.nB * 3 * sizeof(double)));
+        t->geomModels = (size_t)sb;
+    }
     const int nSub = (nModels + sb - 1) / sb;
     // Overlapping the assembly/factorization of sub-batch i+1 with the solve of sub-batch i on a second stream
     // stopped paying once the solve kernel became persistent (one block per SM holding ~210 kB of shared
     // memory: the other kernels' blocks only get an SM when a solve block retires).  Opt-in for experiments.
     static const bool wantOverlap = std::getenv("HDB_OVERLAP_PREP") != nullptr;
-    const bool pipelined = wantOverlap && solve && nSub > 1 && !t->keScratch && !t->dbgClocks;
+    const bool pipelined = wantOverlap && solve && nSub > 1 && !t->keScratch && !t->dbgClocks && !points;
     cudaStream_t ps = pipelined ? t->prepStream : st;
     if (pipelined) {
         CUDA_TRY(cudaEventRecord(t->evFork, st));
@@ -666,6 +674,12 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
         L.keScratch = t->keScratch;
         L.dbgClocks = t->dbgClocks;
         if (pipelined && i >= 2) CUDA_TRY(cudaStreamWaitEvent(ps, t->evSolve[buf], 0)); // workspace set is free again
+        if (points) { // per-model coordinates: beam geometry of this sub-batch first
+            L.points = points + (size_t)m0 * S.nP * 2;
+            L.geom = t->geomBuf;
+            CUDA_TRY(launch_geometry(t->D, L, ps));
+            count_launch(1);
+        }
         {
             ProfScope pr(t, KIND_ASSEMBLE, ps);
             CUDA_TRY(launch_assemble(t->D, L, ps));
@@ -727,6 +741,19 @@ int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *section
                         (cudaStream_t)stream, true);
     if (rc == HDB_OK) debug_report_clocks(t, nModels);
     return rc;
+}
+
+int hdb_static_batch_geom_dev(hdb_topology *t, int32_t nModels, const double *points, const double *sections, int32_t nLC,
+                              const double *loads, double *disp, double *forces, double *react, int32_t *status,
+                              int32_t *failCase, void *stream)
+{
+    if (!t || nModels < 0 || nLC < 0 || !points || !sections || !status || (nLC > 0 && !loads)) return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    if (nModels == 0) return HDB_OK;
+    prof_reset(t);
+    return static_enqueue(t, nModels, sections, nLC, loads, disp, forces, react, status, failCase, nullptr, (cudaStream_t)stream,
+                          true, points);
 }
 
 static int ensure_chunks(hdb_topology *t, int chunkModels, int nLC)
@@ -872,6 +899,37 @@ static int fetch_out(void *p, size_t bytes, Staged &s)
 {
     if (p && s.owned && bytes) CUDA_TRY(cudaMemcpy(p, s.dev, bytes, cudaMemcpyDeviceToHost));
     return HDB_OK;
+}
+
+int hdb_static_batch_geom(hdb_topology *t, int32_t nModels, const double *points, const double *sections, int32_t nLC,
+                          const double *loads, double *disp, double *forces, double *react, int32_t *status, int32_t *failCase)
+{
+    if (!t || nModels < 0 || nLC < 0 || !points || !sections || !status || (nLC > 0 && !loads)) return HDB_ERR_ARG;
+    int rc = ensure_device(t);
+    if (rc != HDB_OK) return rc;
+    if (nModels == 0) return HDB_OK;
+    const Symbolic &S = t->S;
+    Staged pts, sec, ld, dd, ff, rr, stt, fc;
+    const size_t nM = (size_t)nModels, rows = nM * nLC;
+    const size_t bPts = nM * S.nP * 2 * sizeof(double), bSec = nM * S.nB * 3 * sizeof(double), bDof = rows * S.dof * sizeof(double),
+                 bFor = rows * S.nB * 6 * sizeof(double), bSt = nM * sizeof(int32_t);
+    if ((rc = stage_in(points, bPts, pts)) != HDB_OK) return rc;
+    if ((rc = stage_in(sections, bSec, sec)) != HDB_OK) return rc;
+    if ((rc = stage_in(loads, bDof, ld)) != HDB_OK) return rc;
+    if ((rc = stage_out(disp, bDof, dd)) != HDB_OK) return rc;
+    if ((rc = stage_out(forces, bFor, ff)) != HDB_OK) return rc;
+    if ((rc = stage_out(react, bDof, rr)) != HDB_OK) return rc;
+    if ((rc = stage_out(status, bSt, stt)) != HDB_OK) return rc;
+    if ((rc = stage_out(failCase, bSt, fc)) != HDB_OK) return rc;
+    rc = hdb_static_batch_geom_dev(t, nModels, (const double *)pts.dev, (const double *)sec.dev, nLC, (const double *)ld.dev,
+                                   (double *)dd.dev, (double *)ff.dev, (double *)rr.dev, (int32_t *)stt.dev, (int32_t *)fc.dev, nullptr);
+    if (rc != HDB_OK) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if ((rc = fetch_out(disp, bDof, dd)) != HDB_OK) return rc;
+    if ((rc = fetch_out(forces, bFor, ff)) != HDB_OK) return rc;
+    if ((rc = fetch_out(react, bDof, rr)) != HDB_OK) return rc;
+    if ((rc = fetch_out(status, bSt, stt)) != HDB_OK) return rc;
+    return fetch_out(failCase, bSt, fc);
 }
 
 int hdb_assemble_batch(hdb_topology *t, int32_t nModels, const double *sections, double *kval, int32_t *status)

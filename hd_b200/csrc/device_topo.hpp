@@ -59,6 +59,8 @@ constexpr int KE_LD = 37; // padded leading dimension of one element matrix in s
 struct StaticLaunch {
     int nModels, nLC, ld;      // ld = leading dimension (models) of the interleaved factor workspace
     const double *sections;    // [nModels][nB][3]
+    const double *points;      // [nModels][nP][2] per-model coordinates, or NULL: every model has the topology's geometry
+    double *geom;              // [nModels][nB][3] cos, sin, length per model (k_geometry), NULL with points == NULL
     const double *loads;       // [nModels][nLC][dof]
     double *disp, *forces, *react; // outputs, any may be NULL
     int32_t *status, *failCase;    // failCase may be NULL
@@ -83,6 +85,7 @@ struct UniformLaunch {
 cudaError_t launch_uniform_loads(const UniformLaunch &U, cudaStream_t st);
 
 // each returns cudaGetLastError() of its launch
+cudaError_t launch_geometry(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_assemble(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_solve_pipe(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);

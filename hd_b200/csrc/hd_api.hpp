@@ -2,7 +2,7 @@
 //
 // Same names, argument meaning, mutation of arguments and error behaviour as the Go package:
 //   hd::Run(m, lcs, mcs)        hd.Run          model.go:926-969
-//   hd::LinearStatic(m, lcs)    hd.LinearStatic model.go:358-605   (buckling block not on the GPU yet)
+//   hd::LinearStatic(m, lcs)    hd.LinearStatic model.go:358-605   (incl. the linear-buckling block, hdb_buckling_batch)
 //   hd::Modal(m, mc)            hd.Modal        model.go:719-851
 // Nothing throws for bad input: an Error value is returned (empty == nil) and Run keeps going after a
 // failed case (model.go:937-939, 951-954).  The text report (`out io.Writer`) is hd::String(...) and the

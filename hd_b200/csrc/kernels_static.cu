@@ -43,6 +43,49 @@ __device__ __forceinline__ BeamGeom beam_geom(const DevTopo &T, int b)
     return g;
 }
 
+// geometry of beam b of a model: the batch's own table (k_geometry) when coordinates vary per model
+__device__ __forceinline__ BeamGeom beam_geom(const DevTopo &T, const StaticLaunch &L, int model, int b)
+{
+    if (!L.geom) return beam_geom(T, b);
+    const double *q = L.geom + ((size_t)model * T.nB + b) * 3;
+    BeamGeom g;
+    g.c = q[0];
+    g.s = q[1];
+    g.length = q[2];
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_geometry: per-model coordinates -> (cos, sin, length) of every beam with the element routines of the reference
+// (feBeam2d.go:11-19, 142-172).  This is also the geometry part of check.go for a batch: a NaN / Inf coordinate
+// (check.go:223-245) or a beam of length zero (check.go:294-300) gives a non-finite entry here, which the assembly
+// kernel reports as HDB_STATUS_NONFINITE for that model only.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_geometry(const DevTopo T, const StaticLaunch L)
+{
+    const size_t n = (size_t)L.nModels * T.nB;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i % T.nB);
+        const double *p = L.points + (i / T.nB) * (size_t)T.nP * 2;
+        const int n0 = T.beamN[2 * b], n1 = T.beamN[2 * b + 1];
+        const double x0 = p[2 * n0], y0 = p[2 * n0 + 1], x1 = p[2 * n1], y1 = p[2 * n1 + 1];
+        const double len = beam_length(x0, y0, x1, y1);
+        double c, s;
+        beam_cs(x0, y0, x1, y1, len, c, s);
+        L.geom[3 * i] = c;
+        L.geom[3 * i + 1] = s;
+        L.geom[3 * i + 2] = len;
+    }
+}
+
+cudaError_t launch_geometry(const DevTopo &T, const StaticLaunch &L, cudaStream_t st)
+{
+    const size_t n = (size_t)L.nModels * T.nB;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+    k_geometry<<<blocks, 256, 0, st>>>(T, L);
+    return cudaGetLastError();
+}
+
 // Factor workspace W: tiles of W_TILE = 32 models, inside a tile [nSlots][32].  The factor kernel's warp (one tile)
 // then works on one contiguous region with 256-byte rows; a model's slots are 256 bytes apart for the assembly.
 constexpr int W_TILE = 32;
@@ -117,7 +160,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_assemble(const DevTopo T, const 
     for (int b = tid; b < T.nB; b += ASM_THREADS) {
         const double A = sec[3 * b], J = sec[3 * b + 1], E = sec[3 * b + 2];
         if (!(section_ok(A) && section_ok(J) && section_ok(E))) flag = max(flag, (int)HDB_STATUS_NONFINITE);
-        const BeamGeom g = beam_geom(T, b);
+        const BeamGeom g = beam_geom(T, L, model, b);
         const BeamCoef cf = beam_coef(A, J, E, g.length);
         double kg[36];
         const unsigned long long dr = T.droppedMask[b]; // bit e: matrix position e is absent from the representative pattern
@@ -323,18 +366,20 @@ __global__ void __launch_bounds__(QUAD_THREADS, QUAD_B) k_assemble_quad(const De
             double d[2][8];
             int flag[2] = {0, 0};
             BeamCoef cf[2];
+            BeamGeom gj[2];
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 const int mm = min(half + j, nm - 1); // a block past the end of the batch repeats its last model
                 const double *sec = L.sections + ((size_t)(model0 + mm) * T.nB + b) * 3;
                 const double A = sec[0], J = sec[1], E = sec[2];
                 if (!(section_ok(A) && section_ok(J) && section_ok(E))) flag[j] = HDB_STATUS_NONFINITE;
-                cf[j] = beam_coef(A, J, E, g.length);
+                gj[j] = L.geom ? beam_geom(T, L, model0 + mm, b) : g;
+                cf[j] = beam_coef(A, J, E, gj[j].length);
             }
             if (pm == 0) {
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    rigid_global_values(cf[j], g.c, g.s, d[j]);
+                    rigid_global_values(cf[j], gj[j].c, gj[j].s, d[j]);
                     unsigned long long nz = 0;
                     bool fin = true;
 #pragma unroll
@@ -349,7 +394,7 @@ __global__ void __launch_bounds__(QUAD_THREADS, QUAD_B) k_assemble_quad(const De
                 for (int i = 0; i < 8; i++) *reinterpret_cast<double2 *>(dst + i * QUAD + half) = make_double2(d[0][i], d[1][i]);
             } else {
 #pragma unroll 1
-                for (int j = 0; j < 2; j++) flag[j] = max(flag[j], quad_pinned_beam(cf[j], pm, g.c, g.s, dr, dst + half + j));
+                for (int j = 0; j < 2; j++) flag[j] = max(flag[j], quad_pinned_beam(cf[j], pm, gj[j].c, gj[j].s, dr, dst + half + j));
             }
 #pragma unroll
             for (int j = 0; j < 2; j++)
@@ -1157,6 +1202,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 if (L.forces) {
                     for (int b = st; b < nB; b += NS) {
                         const bool first = b == st;
+                        if (L.geom) { // coordinates vary per model: this model's row replaces the shared geometry table
+                            const BeamGeom g = beam_geom(T, L, model, b);
+                            sts_f64(gmA + (unsigned)b * 8u, g.c);
+                            sts_f64(gmA + (unsigned)(nB + b) * 8u, g.s);
+                            sts_f64(gmA + (unsigned)(2 * nB + b) * 8u, g.length);
+                        }
                         const BeamCoef cf = beam_coef(first ? s3[0] : sec[3 * b], first ? s3[1] : sec[3 * b + 1], first ? s3[2] : sec[3 * b + 2],
                                                       lds_f64(gmA + (unsigned)(2 * nB + b) * 8u));
                         const unsigned a = lvB + (unsigned)b * 8u; // component-major: conflict-free

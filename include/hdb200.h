@@ -157,6 +157,21 @@ int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *section
                          const double *loads, double *disp, double *forces, double *react,
                          int32_t *status, int32_t *failCase, void *stream);
 
+/* The same with per-model coordinates (shape sweeps): points[nModels][nP][2]; beams, pins and supports are the
+ * topology's.  This is where the geometry part of check.go runs for a batch: a NaN / Inf coordinate
+ * (checkPoints, check.go:223-245) or a beam of length <= 0 (checkBeams, check.go:294-300) gives
+ * HDB_STATUS_NONFINITE for that model only; graphCheck and the index / pin / support checks (check.go:47-109,
+ * 263-397) depend on the topology alone and ran once in hdb_topology_create.  A member that is axis-aligned in the
+ * topology's own coordinates (exact zeros dropped from the pattern, model.go:645-649) and skewed in a batch member
+ * gives HDB_STATUS_PATTERN, as for sections.  hdb_static_batch_geom takes host or device pointers and returns
+ * when the results are in place; the _dev form enqueues on `stream` like hdb_static_batch_dev. */
+int hdb_static_batch_geom(hdb_topology *t, int32_t nModels, const double *points, const double *sections,
+                          int32_t nLC, const double *loads, double *disp, double *forces, double *react,
+                          int32_t *status, int32_t *failCase);
+int hdb_static_batch_geom_dev(hdb_topology *t, int32_t nModels, const double *points, const double *sections,
+                              int32_t nLC, const double *loads, double *disp, double *forces, double *react,
+                              int32_t *status, int32_t *failCase, void *stream);
+
 /* assembled stiffness values only (tests): kval[nModels][nnzK] in HDB_Q_CSR_* order, bit-exact
  * against the reference's summation order (beam order, model.go:652). Host or device pointers. */
 int hdb_assemble_batch(hdb_topology *t, int32_t nModels, const double *sections, double *kval,
