@@ -90,6 +90,17 @@ int main(int argc, char **argv)
         bad.LoadNodes = {{1, {-70000, 0, 42.0}}};
         CHECK(!hd::LinearStatic(m, {&ok}));
         CHECK(close6(ok.BeamForces[0][0], 1.05e5) && close6(ok.Reactions[0][1], 9.57501e4));
+        if (argc > 2) { // report of a model with pins (Model.String prints Go's true / false), compared by the caller
+            std::vector<hd::LoadCase> one(1);
+            one[0].LoadNodes = ok.LoadNodes;
+            std::vector<hd::ModalCase> none;
+            std::string report;
+            CHECK(!hd::Run(&report, m, one, none));
+            FILE *f = std::fopen(argv[2], "wb");
+            CHECK(f != nullptr);
+            std::fwrite(report.data(), 1, report.size(), f);
+            std::fclose(f);
+        }
         hd::Error e = hd::LinearStatic(m, {&ok, &bad});
         CHECK(bool(e));
         CHECK(!ok.PointDisplacementGlobal.empty() && bad.PointDisplacementGlobal.empty()); // earlier case survives

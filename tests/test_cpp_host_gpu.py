@@ -25,7 +25,8 @@ def test_cpp_host_mirror_compiles(tmp_path):
 def test_cpp_host_mirror_runs(tmp_path):
     exe = _build(str(tmp_path))
     rep = os.path.join(str(tmp_path), "beam.txt")
-    r = subprocess.run([exe, rep], capture_output=True, text=True, timeout=300)
+    rep2 = os.path.join(str(tmp_path), "truss.txt")
+    r = subprocess.run([exe, rep, rep2], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
     # hd::Run's text report of ConsoleBeam against the reference's golden file "beam": same skeleton (one printed
     # number is round-off noise, 5.7e-16 where the reference has an exact 0), and the same text as the Python mirror
@@ -42,3 +43,12 @@ def test_cpp_host_mirror_runs(tmp_path):
     out = io.StringIO()
     assert api.Run(out, m, lcs, mcs) is None
     assert out.getvalue() == text
+    # a model with pins: the C++ and Python mirrors print the same report, with the golden file's skeleton up to the
+    # load cases that example runs and this one does not
+    from hd_b200.model import LoadCase
+    m, lcs, _ = fixtures.GOLDEN["truss"]()
+    one = [LoadCase(LoadNodes=lcs[0].LoadNodes)]
+    out = io.StringIO()
+    assert api.Run(out, m, one, []) is None
+    with open(rep2, newline="") as f:
+        assert out.getvalue() == f.read()
