@@ -515,6 +515,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// sixteen consecutive slots (one banded block column) that start on a multiple of 16: no wrap inside the window, so
+// one address pair and immediate offsets instead of sixteen rounds of index arithmetic
+template <int K>
+__device__ __forceinline__ void cp_async8_run(const unsigned s, const double *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%2], 8;" ::"r"(s), "l"(g), "n"((16 - K) * 256) : "memory");
+    if constexpr (K > 1) cp_async8_run<K - 1>(s, g);
+}
+
 template <int WS>
 __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaunch L)
 {
@@ -542,7 +551,12 @@ __global__ void __launch_bounds__(32) k_factor(const DevTopo T, const StaticLaun
         const int4 d = dN;
         if (J + 1 < nBlk) dN = __ldg(T.colDesc + J + 1);
         if (WS) {
-            for (; loaded < d.z; loaded++) cp_async8(&WIN(loaded), wg + (size_t)loaded * ld);
+            if (WS >= 32 && d.z - loaded == 16 && (loaded & 15) == 0) {
+                cp_async8_run<16>((unsigned)__cvta_generic_to_shared(&WIN(loaded)), wg + (size_t)loaded * ld);
+                loaded += 16;
+            } else {
+                for (; loaded < d.z; loaded++) cp_async8(&WIN(loaded), wg + (size_t)loaded * ld);
+            }
             cp_async_commit();
             cp_async_wait<FACTOR_PREFETCH>();
         }
