@@ -627,8 +627,8 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
     const Symbolic &S = t->S;
     int cp;
     size_t smem;
-    if (solve && !solve_config(t->D, nLC, t->smemOptin, cp, smem)) {
-        set_error_detail("model does not fit the shared-memory resident solve kernel");
+    if (solve && !solve_config(t->D, nLC, t->smemOptin, cp, smem) && !solve_general_config(t->D, nLC, t->smemOptin, cp, smem)) {
+        set_error_detail("model does not fit the solve kernels: the right-hand side of one load case exceeds shared memory");
         return HDB_ERR_UNSUPPORTED;
     }
     const int sb = std::min<int>(nModels, t->subBatch);

@@ -89,6 +89,7 @@ cudaError_t launch_geometry(const DevTopo &T, const StaticLaunch &L, cudaStream_
 cudaError_t launch_assemble(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_solve_pipe(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
+bool solve_general_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes);
 cudaError_t launch_elements(const DevTopo &T, int nModels, const double *sections, double *klocal, double *tr,
                             double *kglobal, cudaStream_t st);
 // shared-memory requirement checks (host); return false when the model does not fit

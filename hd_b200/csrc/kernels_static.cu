@@ -1481,6 +1481,171 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_solve_general: the same step for models whose factor does not fit the shared-memory resident pipeline (tall
+// multi-storey frames: bands of a storey width).  One block per model; only the right-hand sides live in shared
+// memory ([padded position][case], cases per pass chosen to fit), the factor is read from global memory / L2 where
+// the factor kernel left it.  One thread per load case walks the block columns of L directly (BLp / BLi):
+// forward z_J = V_J acc_J, acc_I -= L_IJ z_J; backward x_J = V_J^T (D_J^-1 z_J - sum_I L_IJ^T x_I).  Recovery and
+// status rules are those of k_solve_pipe (model.go:421-491).  Correctness path, not a tuned one.
+// ------------------------------------------------------------------------------------------------
+constexpr int GEN_THREADS = 128;
+
+bool solve_general_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes)
+{
+    int cp = nLC < 32 ? nLC : 32;
+    if (cp < 1) cp = 1;
+    for (; cp >= 1; cp--) {
+        const size_t bytes = (size_t)T.nPad * cp * sizeof(double);
+        if (bytes + 2048 <= (size_t)smemOptin) {
+            casesPerPass = cp;
+            smemBytes = bytes;
+            return true;
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS) k_solve_general(const DevTopo T, const StaticLaunch L, const int cp)
+{
+    extern __shared__ double xs[]; // [nPad][cp]
+    __shared__ int s_bad, s_failc;
+    const int model = blockIdx.x, tid = threadIdx.x, dof = T.dof, nB = T.nB;
+    const double *lm = L.Lm + (size_t)model * T.nSlots;
+    const double *ksf = L.Ksf + (size_t)model * T.nnzR;
+    const double *sec = L.sections + (size_t)model * nB * 3;
+    const int nPass = (L.nLC + cp - 1) / cp;
+    for (int pass = 0; pass < (nPass < 1 ? 1 : nPass); pass++) {
+        const int c0 = pass * cp, nc = min(cp, L.nLC - c0);
+        if (tid == 0) {
+            s_bad = 0;
+            s_failc = 0x7fffffff;
+        }
+        __syncthreads();
+        // ---- load cases -> right-hand sides; checks of model.go:692-696 and 424-437; reactions start as -p ----
+        const double *pb = L.loads + ((size_t)model * L.nLC + c0) * dof;
+        bool bad = false;
+        int failC = 0x7fffffff;
+        for (int idx = tid; idx < nc * dof; idx += GEN_THREADS) {
+            const int c = idx / dof, g = idx - c * dof;
+            const double v = pb[idx];
+            if (!(fabs(v) <= 1.7976931348623157e308)) bad = true;
+            const int xr = T.xrow[g];
+            if (xr >= 0) xs[xr * cp + c] = v;
+            else if (xr == -2 && v != 0.0) failC = min(failC, c0 + c);
+            if (L.react) L.react[((size_t)model * L.nLC + c0) * dof + idx] = T.supIndex[g] >= 0 ? -v : 0.0;
+        }
+        for (int idx = tid; idx < T.nDummy * nc; idx += GEN_THREADS) {
+            const int q = idx / nc, c = idx - q * nc;
+            xs[T.dummyPos[q] * cp + c] = 0.0;
+        }
+        if (bad) atomicMax(&s_bad, 1);
+        if (failC != 0x7fffffff) atomicMin(&s_failc, failC);
+        __syncthreads();
+        // ---- both substitutions, one thread per load case ----
+        for (int c = tid; c < nc; c += GEN_THREADS) {
+            double *x = xs + c;
+            for (int J = 0; J < T.nBlk; J++) {
+                const double *h = lm + T.colOff[J];
+                const double a0 = x[(3 * J) * cp], a1 = x[(3 * J + 1) * cp], a2 = x[(3 * J + 2) * cp];
+                const double z0 = a0, z1 = fma(h[3], a0, a1), z2 = fma(h[5], a1, fma(h[4], a0, a2));
+                x[(3 * J + 1) * cp] = z1;
+                x[(3 * J + 2) * cp] = z2;
+                for (int q = T.BLp[J]; q < T.BLp[J + 1]; q++) {
+                    const int I = T.BLi[q];
+                    const double *l = lm + T.blkSlot[q];
+#pragma unroll
+                    for (int r = 0; r < 3; r++)
+                        x[(3 * I + r) * cp] -= fma(l[3 * r + 2], z2, fma(l[3 * r + 1], z1, l[3 * r] * z0));
+                }
+            }
+            for (int J = T.nBlk - 1; J >= 0; J--) {
+                const double *h = lm + T.colOff[J];
+                double t0 = h[0] * x[(3 * J) * cp], t1 = h[1] * x[(3 * J + 1) * cp], t2 = h[2] * x[(3 * J + 2) * cp];
+                for (int q = T.BLp[J]; q < T.BLp[J + 1]; q++) {
+                    const int I = T.BLi[q];
+                    const double *l = lm + T.blkSlot[q];
+                    const double y0 = x[(3 * I) * cp], y1 = x[(3 * I + 1) * cp], y2 = x[(3 * I + 2) * cp];
+                    t0 -= fma(l[6], y2, fma(l[3], y1, l[0] * y0));
+                    t1 -= fma(l[7], y2, fma(l[4], y1, l[1] * y0));
+                    t2 -= fma(l[8], y2, fma(l[5], y1, l[2] * y0));
+                }
+                x[(3 * J) * cp] = fma(h[4], t2, fma(h[3], t1, t0));
+                x[(3 * J + 1) * cp] = fma(h[5], t2, t1);
+                x[(3 * J + 2) * cp] = t2;
+            }
+        }
+        __syncthreads();
+        // ---- displacements (model.go:446-451) ----
+        if (L.disp) {
+            double *ob = L.disp + ((size_t)model * L.nLC + c0) * dof;
+            for (int idx = tid; idx < nc * dof; idx += GEN_THREADS) {
+                const int c = idx / dof, g = idx - c * dof;
+                const int xr = T.xrow[g];
+                ob[idx] = xr >= 0 ? xs[xr * cp + c] : 0.0;
+            }
+        }
+        // ---- reactions (model.go:470-489): -p (stored above by this thread set's own earlier loop) + K[r, free] d ----
+        if (L.react) {
+            double *orr = L.react + ((size_t)model * L.nLC + c0) * dof;
+            for (int idx = tid; idx < nc * T.nSup; idx += GEN_THREADS) {
+                const int c = idx / T.nSup, si = idx - c * T.nSup;
+                double acc = 0.0;
+                for (int q = T.rptr[si]; q < T.rptr[si + 1]; q++) acc = fma(ksf[q], xs[T.rcol[q] * cp + c], acc);
+                const int g = T.supDofs[si];
+                orr[(size_t)c * dof + g] = -pb[(size_t)c * dof + g] + acc;
+            }
+        }
+        // ---- beam end forces s = k (T Zo), model.go:455-468 ----
+        if (L.forces) {
+            double *of = L.forces + ((size_t)model * L.nLC + c0) * nB * 6;
+            for (int idx = tid; idx < nc * nB; idx += GEN_THREADS) {
+                const int c = idx / nB, b = idx - c * nB;
+                const BeamGeom g = beam_geom(T, L, model, b);
+                const BeamCoef cf = beam_coef(sec[3 * b], sec[3 * b + 1], sec[3 * b + 2], g.length);
+                double u[6], o[6];
+#pragma unroll
+                for (int e = 0; e < 6; e++) {
+                    const int r = T.beamRows[b * 6 + e];
+                    u[e] = r >= 0 ? xs[r * cp + c] : 0.0;
+                }
+                const uint32_t pm = T.pinMask[b];
+                if (pm == 0) beam_forces_rigid(cf, g.c, g.s, u, o);
+                else beam_forces_pinned(cf, pm, g.c, g.s, u, o);
+#pragma unroll
+                for (int e = 0; e < 6; e++) of[(size_t)idx * 6 + e] = o[e];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { // status of this pass, as in k_solve_pipe
+            const int sOld = L.status[model];
+            int st2 = sOld;
+            const int fc = s_failc;
+            if (s_bad && (st2 == HDB_STATUS_OK || st2 == HDB_STATUS_IGNORE_LOAD)) st2 = HDB_STATUS_NONFINITE;
+            else if (st2 == HDB_STATUS_OK && fc != 0x7fffffff) st2 = HDB_STATUS_IGNORE_LOAD;
+            if (st2 != sOld) L.status[model] = st2;
+            if (L.failCase) {
+                const int old = pass == 0 ? -1 : L.failCase[model];
+                L.failCase[model] = old >= 0 ? old : (fc != 0x7fffffff ? fc : -1);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static cudaError_t launch_solve_general(const DevTopo &T, const StaticLaunch &L, cudaStream_t st, int optin)
+{
+    int cp = 1;
+    size_t smem = 0;
+    if (!solve_general_config(T, L.nLC, optin, cp, smem)) return cudaErrorInvalidConfiguration;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_solve_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_solve_general<<<L.nModels, GEN_THREADS, smem, st>>>(T, L, cp);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_solve_pipe(const DevTopo &T, const StaticLaunch &L, cudaStream_t st)
 {
     int dev = 0, optin = 0, nSM = 148;
@@ -1489,7 +1654,10 @@ cudaError_t launch_solve_pipe(const DevTopo &T, const StaticLaunch &L, cudaStrea
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
     SolveCfg cfg;
     size_t smem = 0;
-    if (!solve_config(T, L.nLC, optin, cfg.casesPerPass, smem)) return cudaErrorInvalidConfiguration;
+    {
+        const char *force = std::getenv("HDB_SOLVE_GENERAL"); // tests: the general kernel on a model the pipeline could take
+        if ((force && atoi(force)) || !solve_config(T, L.nLC, optin, cfg.casesPerPass, smem)) return launch_solve_general(T, L, st, optin);
+    }
     cfg.nPass = (L.nLC + cfg.casesPerPass - 1) / cfg.casesPerPass;
     if (cfg.nPass < 1) cfg.nPass = 1;
     cfg.lvmDoubles = (int)pipe_lvm_doubles(T);

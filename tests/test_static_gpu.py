@@ -537,3 +537,73 @@ def test_quad_assembly_is_bit_identical_to_the_single_model_kernel(oracle, monke
         assert not out["1"][0].any(), out["1"][0]
         for a, b in zip(out["1"], out["0"]):
             assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def _storey_frame(N, S):
+    from hd_b200.model import BeamProp, Model
+    m, idx = Model(), {}
+    for s_ in range(S + 1):
+        for i in range(N + 1):
+            idx[(i, s_)] = len(m.Points)
+            m.Points.append([6.0 * i, 3.0 * s_])
+            m.Supports.append([s_ == 0] * 3)
+    for s_ in range(1, S + 1):
+        for i in range(N + 1):
+            m.Beams.append(BeamProp(N=[idx[(i, s_ - 1)], idx[(i, s_)]], A=12e-4, J=120e-6, E=2e11))
+        for i in range(1, N + 1):
+            m.Beams.append(BeamProp(N=[idx[(i - 1, s_)], idx[(i, s_)]], A=12e-4, J=120e-6, E=2e11))
+    return m
+
+
+def _check_batch_vs_oracle(oracle, m, nM, nLC, seed, pick=None, nvar=2):
+    fm = oracle.flatten_model(m)
+    rng = np.random.default_rng(seed)
+    sec = np.tile(fm.sections, (nM, 1, 1))
+    sec[:, :, :nvar] *= rng.uniform(0.5, 2.0, size=(nM, fm.nB, nvar))
+    loads = rng.normal(size=(nM, nLC, fm.dof)) * 1e3
+    t = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports, ordering=2)
+    for g in t.query(_lib.Q_IGNORE):
+        loads[:, :, int(g)] = 0.0
+    status, fail, disp, forces, react = t.static_batch(sec, loads)
+    t.close()
+    assert not status.any(), status
+    for i in (range(nM) if pick is None else pick):
+        fmi = oracle.flatten_model(m)
+        fmi.sections[:] = sec[i]
+        rc, od, of, orr, fc = oracle.linear_static(fmi, loads[i])
+        assert rc == oracle.OK
+        for c in range(nLC):
+            compare_rule(od[c], disp[i, c])
+            compare_rule(orr[c], react[i, c])
+            force_rule(of[c], forces[i, c])
+    return status, fail, disp, forces, react
+
+
+def test_general_solve_kernel_on_small_models(oracle, monkeypatch):
+    """k_solve_general (factor read from global memory, right-hand sides in shared memory) forced on models the
+    pipeline takes: same results as the oracle at 1e-9, for a chain, a truss with pins and ignore DOFs, and a
+    multi-storey frame; status and failCase rules as in the pipeline."""
+    monkeypatch.setenv("HDB_SOLVE_GENERAL", "1")
+    _check_batch_vs_oracle(oracle, frames.uniform_frame(8), 9, 5, 1)
+    _check_batch_vs_oracle(oracle, fixtures.truss()[0], 3, 2, 2, nvar=1)  # J fixed: see the quad assembly test
+    _check_batch_vs_oracle(oracle, _storey_frame(6, 3), 4, 37, 3)  # 37 cases: two passes of 32 + 5
+    fm, t = topo_of(oracle, frames.uniform_frame(4))
+    secs = frames.uniform_frame_sections(4, 0, 6)
+    secs[1, 2, 0] = np.nan
+    loads = frames.uniform_frame_loads(4, 0, 6)
+    loads[5, 7, 4] = np.inf
+    with np.errstate(all="ignore"):
+        status, fail, disp, forces, react = t.static_batch(secs, loads)
+    assert list(status) == [0, 1, 0, 0, 0, 1]
+    t.close()
+    m, lcs, _ = fixtures.truss()
+    lcs = [lcs[0], LoadCase(LoadNodes=[LoadNode(1, [-70000, 0, 42.0])])]
+    err = api.LinearStatic(None, m, *lcs)
+    assert err is not None and "not valid directions" in str(err)
+    assert lcs[0].PointDisplacementGlobal is not None and lcs[1].PointDisplacementGlobal is None
+
+
+def test_tall_frame_takes_the_general_solve_kernel(oracle):
+    """32 bays x 8 storeys (891 DOFs): the factor (a band one storey wide) does not fit the shared-memory resident
+    pipeline; the library falls back to k_solve_general instead of refusing the model."""
+    _check_batch_vs_oracle(oracle, _storey_frame(32, 8), 6, 3, 4, pick=[0, 5])
