@@ -607,3 +607,28 @@ def test_tall_frame_takes_the_general_solve_kernel(oracle):
     """32 bays x 8 storeys (891 DOFs): the factor (a band one storey wide) does not fit the shared-memory resident
     pipeline; the library falls back to k_solve_general instead of refusing the model."""
     _check_batch_vs_oracle(oracle, _storey_frame(32, 8), 6, 3, 4, pick=[0, 5])
+
+
+def test_empty_inputs(oracle):
+    """Nothing to do is not an error: a batch of zero models, zero load cases (assembly and factorization still report
+    a status per model, e.g. a singular frame), no outputs requested, hd.Run without cases (model.go:926-969 skips
+    LinearStatic and still prints the model)."""
+    import io
+    fm, t = topo_of(oracle, frames.uniform_frame(4))
+    z = np.zeros(0)
+    zi = np.zeros(0, dtype=np.int32)
+    t.static_batch_raw(0, z, 3, z, z, z, z, zi, zi)  # zero models
+    secs = frames.uniform_frame_sections(4, 0, 5)
+    secs[3, 1, 0] = -1.0
+    status = np.full(5, -7, dtype=np.int32)
+    fail = np.full(5, -7, dtype=np.int32)
+    t.static_batch_raw(5, secs, 0, None, None, None, None, status, fail)  # zero load cases
+    assert list(status) == [0, 0, 0, _lib.STATUS_NONFINITE, 0]
+    loads = frames.uniform_frame_loads(4, 0, 5, 2)
+    st2, fl2, d, f, r = t.static_batch(secs, loads, want=())  # no outputs: statuses only
+    assert d is None and f is None and r is None and list(st2) == [0, 0, 0, _lib.STATUS_NONFINITE, 0]
+    t.close()
+    m, _, _ = fixtures.console_beam()
+    out = io.StringIO()
+    assert api.Run(out, m, [], []) is None
+    assert out.getvalue().startswith("\nPoint coordinates:") and "Linear Elastic Analysis" not in out.getvalue()
