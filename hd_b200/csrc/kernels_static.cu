@@ -772,6 +772,7 @@ static size_t solve_smem_bytes(const DevTopo &T, int cp)
 bool solve_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes)
 {
     int cp = nLC < 32 ? nLC : 32;
+    if (const char *e = std::getenv("HDB_CASES_PER_PASS")) cp = std::min(cp, atoi(e)); // diagnostics: smaller passes
     if (cp < 1) cp = 1;
     for (; cp >= 1; cp--) {
         const size_t bytes = solve_smem_bytes(T, cp);
