@@ -59,10 +59,12 @@ def test_moved_points_vs_oracle(oracle, nM):
             force_rule(want[i][1][c], forces[i, c])
 
 
-def test_uniform_frame_heights_vs_oracle(oracle):
+@pytest.mark.parametrize("nLC", [4, 45])
+def test_uniform_frame_heights_vs_oracle(oracle, nLC):
     """A portal frame whose storey height and bay widths vary per model: columns stay vertical and girders
-    horizontal, so the pattern (exact zeros of axis-aligned members) is the topology's for every model."""
-    N, nM, nLC = 8, 9, 4
+    horizontal, so the pattern (exact zeros of axis-aligned members) is the topology's for every model.
+    45 load cases: two passes of the solve kernel per model (the geometry row is re-staged for each)."""
+    N, nM = 8, 9
     m = frames.uniform_frame(N)
     fm = oracle.flatten_model(m)
     rng = np.random.default_rng(11)
