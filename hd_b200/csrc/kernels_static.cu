@@ -1486,11 +1486,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
 // k_solve_general: the same step for models whose factor does not fit the shared-memory resident pipeline (tall
 // multi-storey frames: bands of a storey width).  One block per model; only the right-hand sides live in shared
 // memory ([padded position][case], cases per pass chosen to fit), the factor is read from global memory / L2 where
-// the factor kernel left it.  One thread per load case walks the block columns of L directly (BLp / BLi):
+// the factor kernel left it.  Four lanes per load case walk the block columns of L directly (BLp / BLi), sharing a column's off blocks:
 // forward z_J = V_J acc_J, acc_I -= L_IJ z_J; backward x_J = V_J^T (D_J^-1 z_J - sum_I L_IJ^T x_I).  Recovery and
 // status rules are those of k_solve_pipe (model.go:421-491).  Correctness path, not a tuned one.
 // ------------------------------------------------------------------------------------------------
 constexpr int GEN_THREADS = 128;
+constexpr int GEN_SUB = 4; // lanes per load case in the substitutions
 
 bool solve_general_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes)
 {
@@ -1543,27 +1544,35 @@ __global__ void __launch_bounds__(GEN_THREADS) k_solve_general(const DevTopo T, 
         if (bad) atomicMax(&s_bad, 1);
         if (failC != 0x7fffffff) atomicMin(&s_failc, failC);
         __syncthreads();
-        // ---- both substitutions, one thread per load case ----
-        for (int c = tid; c < nc; c += GEN_THREADS) {
-            double *x = xs + c;
+        // ---- both substitutions: four lanes per load case share the off blocks of a column ----
+        for (int cb = 0; cb < nc; cb += GEN_THREADS / GEN_SUB) { // uniform trip count for the whole block
+            const int c = cb + (tid >> 2), sub = tid & (GEN_SUB - 1);
+            const bool act = c < nc;
+            double *x = xs + (act ? c : nc - 1); // idle lanes shadow the last case and never write
             for (int J = 0; J < T.nBlk; J++) {
                 const double *h = lm + T.colOff[J];
                 const double a0 = x[(3 * J) * cp], a1 = x[(3 * J + 1) * cp], a2 = x[(3 * J + 2) * cp];
                 const double z0 = a0, z1 = fma(h[3], a0, a1), z2 = fma(h[5], a1, fma(h[4], a0, a2));
-                x[(3 * J + 1) * cp] = z1;
-                x[(3 * J + 2) * cp] = z2;
-                for (int q = T.BLp[J]; q < T.BLp[J + 1]; q++) {
+                __syncwarp(); // everybody has read acc_J
+                if (act && sub == 0) {
+                    x[(3 * J + 1) * cp] = z1;
+                    x[(3 * J + 2) * cp] = z2;
+                }
+                for (int q = T.BLp[J] + sub; q < T.BLp[J + 1]; q += GEN_SUB) { // distinct row blocks: no two lanes on one target
                     const int I = T.BLi[q];
                     const double *l = lm + T.blkSlot[q];
+                    if (act) {
 #pragma unroll
-                    for (int r = 0; r < 3; r++)
-                        x[(3 * I + r) * cp] -= fma(l[3 * r + 2], z2, fma(l[3 * r + 1], z1, l[3 * r] * z0));
+                        for (int r = 0; r < 3; r++)
+                            x[(3 * I + r) * cp] -= fma(l[3 * r + 2], z2, fma(l[3 * r + 1], z1, l[3 * r] * z0));
+                    }
                 }
+                __syncwarp(); // the updates of this column are visible before the next one reads its block
             }
             for (int J = T.nBlk - 1; J >= 0; J--) {
                 const double *h = lm + T.colOff[J];
-                double t0 = h[0] * x[(3 * J) * cp], t1 = h[1] * x[(3 * J + 1) * cp], t2 = h[2] * x[(3 * J + 2) * cp];
-                for (int q = T.BLp[J]; q < T.BLp[J + 1]; q++) {
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+                for (int q = T.BLp[J] + sub; q < T.BLp[J + 1]; q += GEN_SUB) {
                     const int I = T.BLi[q];
                     const double *l = lm + T.blkSlot[q];
                     const double y0 = x[(3 * I) * cp], y1 = x[(3 * I + 1) * cp], y2 = x[(3 * I + 2) * cp];
@@ -1571,9 +1580,22 @@ __global__ void __launch_bounds__(GEN_THREADS) k_solve_general(const DevTopo T, 
                     t1 -= fma(l[7], y2, fma(l[4], y1, l[1] * y0));
                     t2 -= fma(l[8], y2, fma(l[5], y1, l[2] * y0));
                 }
-                x[(3 * J) * cp] = fma(h[4], t2, fma(h[3], t1, t0));
-                x[(3 * J + 1) * cp] = fma(h[5], t2, t1);
-                x[(3 * J + 2) * cp] = t2;
+#pragma unroll
+                for (int o = 1; o < GEN_SUB; o <<= 1) {
+                    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+                    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+                    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+                }
+                t0 = fma(h[0], x[(3 * J) * cp], t0);
+                t1 = fma(h[1], x[(3 * J + 1) * cp], t1);
+                t2 = fma(h[2], x[(3 * J + 2) * cp], t2);
+                __syncwarp();
+                if (act && sub == 0) {
+                    x[(3 * J) * cp] = fma(h[4], t2, fma(h[3], t1, t0));
+                    x[(3 * J + 1) * cp] = fma(h[5], t2, t1);
+                    x[(3 * J + 2) * cp] = t2;
+                }
+                __syncwarp(); // x_J is in place before column J-1 pulls from it
             }
         }
         __syncthreads();
