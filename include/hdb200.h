@@ -42,7 +42,8 @@ enum {
     HDB_ERR_NO_DEVICE = -2,   /* no CUDA device: the product has no CPU path           */
     HDB_ERR_CUDA = -3,        /* CUDA runtime error (hdb_last_error_detail)            */
     HDB_ERR_NOMEM = -4,
-    HDB_ERR_UNSUPPORTED = -5, /* model too large for the resident kernels, see DESIGN.md */
+    HDB_ERR_UNSUPPORTED = -5, /* too large for a shared-memory resident kernel: modal / buckling eigen solves (limits in
+                               * DESIGN.md section 8); LinearStatic only above ~28 k padded DOFs per load case */
     HDB_ERR_INPUT = -6,       /* topology rejected (what check.go rejects for shared data) */
     HDB_ERR_SMALL_BUFFER = -7
 };
