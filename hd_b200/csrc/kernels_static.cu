@@ -732,7 +732,7 @@ constexpr int LC = 5;             // load cases handled together by one work ite
 constexpr unsigned ZERO_BYTES = (24u * LC + 15u) & ~15u; // a zero "row" long enough for the LC cases of a work unit
 constexpr int NS = PIPE_THREADS / 32 / 4 * 3 * 32; // streaming threads: the warps outside SM sub-partition 0
 constexpr int NH = (PIPE_THREADS / 32 / 4 - 1) * 32; // helper threads: warps 4, 8, 12 of the solver's sub-partition
-constexpr int REACT_HELPER_PCT = 51;               // share of the reaction items the helper warps take
+constexpr int REACT_HELPER_PCT = 57;               // share of the reaction items the helper warps take
 constexpr int LOAD_U = 7;         // 16-byte loads in flight per streaming thread in the load stage
 constexpr unsigned FST_BYTES = 32u * 6u * 8u; // per-warp 32 x 6 staging tile of the force stage
 
