@@ -1112,6 +1112,40 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
         }                                        \
     } while (0)
 
+    // displacements (model.go:446-451): the [cases][dof] block of a model is one contiguous run, walked in pairs with a
+    // constant stride so that every store is base + immediate; (DOF, case) follow incrementally.  The helper warps take
+    // their share (threads NS .. NS + NH - 1 of the walk): they would otherwise wait for the reaction block.
+    constexpr int ND = NS + NH;
+    auto disp_items = [&](const int model, const int c0, const int nc, const unsigned xsB, const int t) {
+        double *ob = L.disp + ((size_t)model * L.nLC + c0) * dof + 2 * t;
+        const int nFlat = nc * dof;
+        int g = (2 * t) % dof;
+        unsigned cOff = (unsigned)((2 * t) / dof) * 24u;
+        for (int f0 = 0; f0 < nFlat; f0 += 2 * ND * 4) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int f = f0 + 2 * (u * ND + t);
+                if (f < nFlat) {
+                    int g1 = g + 1;
+                    unsigned c1 = cOff;
+                    if (g1 == dof) { g1 = 0; c1 += 24u; }
+                    const int i0 = lds_s32(xbA + 4u * g), i1 = lds_s32(xbA + 4u * g1);
+                    const double d0 = i0 >= 0 ? lds_f64(xsB + (unsigned)i0 + cOff) : 0.0;
+                    const double d1 = i1 >= 0 ? lds_f64(xsB + (unsigned)i1 + c1) : 0.0;
+                    double *o = ob + f0 + 2 * u * ND;
+                    if (cfg.vec2) __stcs(reinterpret_cast<double2 *>(o), make_double2(d0, d1));
+                    else {
+                        __stcs(o, d0);
+                        if (f + 1 < nFlat) __stcs(o + 1, d1);
+                    }
+                }
+                g += (2 * ND) % dof;
+                cOff += (unsigned)((2 * ND) / dof) * 24u;
+                if (g >= dof) { g -= dof; cOff += 24u; }
+            }
+        }
+    };
+
     // reactions (model.go:470-489: columns ascending, eliminated columns carry d = 0) added to the -p rows of the
     // load stage with one reduction per entry; item = (group of LC cases, supported DOF)
     auto react_items = [&](double *orr, const unsigned xsB, const unsigned ksA, const int nc, const int first, const int end, const int stride) {
@@ -1179,35 +1213,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 // displacements (model.go:446-451): the [cases][dof] block of a model is one contiguous run, walked
                 // in pairs with a constant stride so that every store is base + immediate; (DOF, case) follow
                 // incrementally
-                if (L.disp) {
-                    double *ob = L.disp + ((size_t)model * L.nLC + c0) * dof + 2 * st;
-                    const int nFlat = nc * dof;
-                    int g = (2 * st) % dof;
-                    unsigned cOff = (unsigned)((2 * st) / dof) * 24u;
-                    for (int f0 = 0; f0 < nFlat; f0 += 2 * NS * 4) {
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int f = f0 + 2 * (u * NS + st);
-                            if (f < nFlat) {
-                                int g1 = g + 1;
-                                unsigned c1 = cOff;
-                                if (g1 == dof) { g1 = 0; c1 += 24u; }
-                                const int i0 = lds_s32(xbA + 4u * g), i1 = lds_s32(xbA + 4u * g1);
-                                const double d0 = i0 >= 0 ? lds_f64(xsB + (unsigned)i0 + cOff) : 0.0;
-                                const double d1 = i1 >= 0 ? lds_f64(xsB + (unsigned)i1 + c1) : 0.0;
-                                double *o = ob + f0 + 2 * u * NS;
-                                if (cfg.vec2) __stcs(reinterpret_cast<double2 *>(o), make_double2(d0, d1));
-                                else {
-                                    __stcs(o, d0);
-                                    if (f + 1 < nFlat) __stcs(o + 1, d1);
-                                }
-                            }
-                            g += (2 * NS) % dof;
-                            cOff += (unsigned)((2 * NS) / dof) * 24u;
-                            if (g >= dof) { g -= dof; cOff += 24u; }
-                        }
-                    }
-                }
+                if (L.disp) disp_items(model, c0, nc, xsB, st);
                 if (orr) {
 #pragma unroll
                     for (int u = 0; u < 4; u++)
@@ -1466,6 +1472,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
             const unsigned buf = (unsigned)(i & 1);
             const unsigned lvB = lvm0 + buf * lvmBytes, xsB = xs0 + buf * xsBytes;
             const int hx = ((warp >> 2) - 1) * 32 + (tid & 31);
+            if (L.disp) disp_items(model, c0, nc, xsB, NS + hx);
             bar_stream(NS + NH); // reaction block staged by the streaming warps
             if (L.react)
                 react_items(L.react + ((size_t)model * L.nLC + c0) * dof, xsB, lvB + 5u * (unsigned)nB * 8u, nc, hx,
