@@ -134,9 +134,11 @@ def bind_to_gpu_numa(gpu_index):
         return 0
 
 
-def cpu_port(fm, sections, loads, threads, literal=True):
-    """The oracle (CPU restatement of the reference's algorithm) on `threads` host threads."""
+def cpu_port(model, sections, loads, threads, literal=True):
+    """The oracle (CPU restatement of the reference's algorithm) on `threads` host threads.  The only place (with the
+    post-run parity check) where bench.py touches oracle/."""
     from oracle import hd_oracle as oracle
+    fm = oracle.flatten_model(model)
     oracle.set_literal_scans(literal)
     try:
         t0 = time.perf_counter()
@@ -153,10 +155,10 @@ def modal_main(args, rank, local_rank, world):
     one modal case each, 130 modes per model (frequencies + shapes). Not the driver's headline metric."""
     import torch
     from hd_b200 import _lib, frames
-    from oracle import hd_oracle as oracle
+    from hd_b200.model import flatten_model
     N = 64 if args.bays == 128 else args.bays
     M = 1024 if args.models_per_gpu == 8192 else args.models_per_gpu
-    fm = oracle.flatten_model(frames.uniform_frame(N))
+    fm = flatten_model(frames.uniform_frame(N))
     sections = frames.uniform_frame_sections(N, rank * M, M)
     massN, mass = frames.uniform_frame_masses(N, rank * M, M)
     torch.cuda.set_device(local_rank)
@@ -190,10 +192,11 @@ def modal_main(args, rank, local_rank, world):
     value = M * args.steps / (ms * 1e-3)
     cpu = None
     if not args.no_cpu:
+        from oracle import hd_oracle as oracle  # CPU baseline leg only
         threads = host_threads()
         sample = args.cpu_sample or 2 * threads
         t0 = time.perf_counter()
-        ost, _, _, _ = oracle.modal_batch(fm, sections[:sample], massN, mass[:sample], n_threads=threads)
+        ost, _, _, _ = oracle.modal_batch(oracle.flatten_model(frames.uniform_frame(N)), sections[:sample], massN, mass[:sample], n_threads=threads)
         dt = time.perf_counter() - t0
         cpu = {"value": sample / dt, "unit": "modal solves/s", "cores": threads, "kind": "port",
                "sample": f"first {sample} models, dense non-symmetric eigen solve of K^-1 M as the reference does"}
@@ -234,9 +237,9 @@ def main():
     N, nLC, M = args.bays, args.cases, args.models_per_gpu
 
     from hd_b200 import frames
-    from oracle import hd_oracle as oracle  # CPU baseline legs only (never on the product path)
+    from hd_b200.model import flatten_model
     model = frames.uniform_frame(N)
-    fm = oracle.flatten_model(model)
+    fm = flatten_model(model)
     nP, nB, dof = fm.nP, fm.nB, fm.dof
     b_in, b_out = algorithmic_bytes(nB, dof, nP, nLC)
     workload = f"uniform_frame({N}) x {nLC} load cases, randomised sections+loads, {M} models per GPU"
@@ -253,10 +256,10 @@ def main():
         sample = args.cpu_sample or 8 * threads
         sections, loads = build_inputs(N, 0, sample, nLC)
         for _ in range(args.warmup):
-            cpu_port(fm, sections[:threads], loads[:threads], threads)
+            cpu_port(model, sections[:threads], loads[:threads], threads)
         t = 0.0
         for _ in range(args.steps):
-            t += cpu_port(fm, sections, loads, threads)
+            t += cpu_port(model, sections, loads, threads)
         value = sample * args.steps / t
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -402,8 +405,8 @@ def main():
     if not args.no_cpu and world == 1:
         threads = host_threads()
         sample = args.cpu_sample or 8 * threads
-        dt = cpu_port(fm, sections[:sample], loads[:sample], threads, literal=True)
-        dt_fast = cpu_port(fm, sections[:sample * 8], loads[:sample * 8], threads, literal=False)
+        dt = cpu_port(model, sections[:sample], loads[:sample], threads, literal=True)
+        dt_fast = cpu_port(model, sections[:sample * 8], loads[:sample * 8], threads, literal=False)
         cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {sample} models of the same batch, literal C restatement of the reference algorithm "
                          f"(incl. its O(nSup*nnz) reaction scan), OpenMP over models",

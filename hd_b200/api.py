@@ -118,7 +118,7 @@ def LinearStatic(out, m: Model, *lcs: LoadCase) -> Optional[HdError]:
                 status, fail, disp, forces, react = topo.static_batch(sec[None], loads[:, :nLC])
             st, fc = int(status[0]), int(fail[0])
             # buckling block (model.go:491-601) of every case that asks for it and has static results
-            ok_upto = nLC if st == _lib.STATUS_OK else (fc if st == _lib.STATUS_IGNORE_LOAD else 0)
+            ok_upto = nLC if st == _lib.STATUS_OK else (fc if fc >= 0 else 0)
             for i in range(ok_upto):
                 amount = lcs[i].AmountLinearBuckling
                 if amount <= 0:
@@ -138,10 +138,9 @@ def LinearStatic(out, m: Model, *lcs: LoadCase) -> Optional[HdError]:
     if st == _lib.STATUS_IGNORE_LOAD:
         upto = fc  # cases before the offending one keep their results (model.go:415-437)
         err = HdError(name, [STATUS_TEXT[st]])
-    elif st == _lib.STATUS_NONFINITE and fc < 0 and nLC > 0 and not np.all(np.isfinite(loads)):
-        bad = [i for i in range(nLC) if not np.all(np.isfinite(loads[0, i]))]
-        upto = bad[0]
-        err = HdError(name, [f"Assembly node load: not valid node load"])
+    elif st == _lib.STATUS_NONFINITE and fc >= 0:
+        upto = fc  # assemblyNodeLoad of case fc failed (model.go:692-696): the cases before it keep their results
+        err = HdError(name, ["Assembly node load: not valid node load"])
     elif st != _lib.STATUS_OK:
         upto = 0
         err = HdError(name, [f"Assembly node load: {STATUS_TEXT.get(st, st)}"])

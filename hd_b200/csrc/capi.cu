@@ -118,12 +118,16 @@ static int ensure_device(hdb_topology *t)
     }
     CUDA_TRY(cudaSetDevice(t->device));
     if (t->devReady) return HDB_OK;
+    for (void *p : t->devAllocs) cudaFree(p); // leftovers of an upload that failed half-way
+    t->devAllocs.clear();
     CUDA_TRY(cudaDeviceGetAttribute(&t->smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, t->device));
     CUDA_TRY(cudaDeviceGetAttribute(&t->smCount, cudaDevAttrMultiProcessorCount, t->device));
     const Symbolic &S = t->S;
     DevTopo &D = t->D;
     D.nP = S.nP; D.nB = S.nB; D.dof = S.dof; D.nFree = S.nFree; D.nBlk = S.nBlk; D.nPad = S.nPad; D.nSlots = S.nSlots;
     D.nSup = S.nSup; D.nnzR = S.nnzR; D.nnzK = S.nnzK; D.nDummy = (int)S.dummyPos.size(); D.maxBlkCount = S.maxBlkCount;
+    D.rWidth = 0;
+    for (int i = 0; i < S.nSup; i++) D.rWidth = std::max(D.rWidth, S.rptr[i + 1] - S.rptr[i]);
     D.winNeed = S.winNeed; D.nFwdOps = (int)S.fwdOps.size() / 4; D.nBwdOps = (int)S.bwdOps.size() / 4;
     // gather codes -> padded shared-memory indices
     auto pad = [](const std::vector<int32_t> &src) {
@@ -261,6 +265,18 @@ static int ensure_device(hdb_topology *t)
     UP(S.rptr, rptr);
     UP(S.rcol, rcol);
     UP(S.dummyPos, dummyPos);
+    { // row chunks of k_solve_bulk and the supported DOFs inside each
+        D.rNCh = (S.dof + BULK_CHUNK - 1) / BULK_CHUNK;
+        D.rChunk = D.rNCh > 0 ? (((S.dof + D.rNCh - 1) / D.rNCh + 1) & ~1) : 0;
+        std::vector<int32_t> ptr(1, 0), list;
+        for (int j = 0; j < D.rNCh; j++) {
+            for (int g = j * D.rChunk; g < std::min(S.dof, (j + 1) * D.rChunk); g++)
+                if (S.supIndex[g] >= 0) list.push_back((g - j * D.rChunk) | (S.supIndex[g] << 16));
+            ptr.push_back((int32_t)list.size());
+        }
+        UP(ptr, rsPtr);
+        UP(list, rsList);
+    }
 #undef UP
     if (const char *e = std::getenv("HDB_SUB_BATCH")) {
         int v = std::atoi(e);
@@ -301,11 +317,11 @@ static int ensure_workspace(hdb_topology *t, size_t models)
     for (int i = 0; i < 2; i++) {
         CUDA_TRY(cudaMalloc(&t->Wbuf[i], (size_t)t->S.nSlots * ld * sizeof(double)));
         CUDA_TRY(cudaMalloc(&t->Lmbuf[i], (size_t)t->S.nSlots * ld * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&t->Ksfbuf[i], std::max<size_t>(1, models * (size_t)t->S.nnzR) * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&t->Ksfbuf[i], std::max<size_t>(1, ld * (size_t)t->S.nnzR) * sizeof(double)));
     }
     if (!assemble_fits_smem(t->D, t->smemOptin))
-        CUDA_TRY(cudaMalloc(&t->keScratch, models * (size_t)t->S.nB * KE_LD * sizeof(double)));
-    t->wsModels = ld;
+        CUDA_TRY(cudaMalloc(&t->keScratch, ld * (size_t)t->S.nB * KE_LD * sizeof(double)));
+    t->wsModels = ld; // every buffer above is sized for ld models: a later, larger batch within ld reuses them
     return HDB_OK;
 }
 
@@ -321,6 +337,7 @@ static bool is_device_ptr(const void *p)
 }
 
 enum { KIND_ASSEMBLE = 0, KIND_FACTOR = 1, KIND_SOLVE = 2, KIND_MODAL0 = 3 };
+constexpr size_t PROF_MAX_INTERVALS = 1 << 16;
 
 static void prof_reset(hdb_topology *t)
 {
@@ -344,6 +361,7 @@ struct ProfScope {
     bool on;
     ProfScope(hdb_topology *t_, int kind, cudaStream_t s) : t(t_), st(s), slot(0), on(t_->profiling != 0)
     {
+        if (on && t->evKind.size() >= PROF_MAX_INTERVALS) on = false; // accumulate mode: bounded, the rest goes untimed
         if (!on) return;
         slot = t->evKind.size();
         t->evKind.push_back(kind);
@@ -427,6 +445,10 @@ int hdb_topology_create(int32_t nP, const double *points, int32_t nB, const hdb_
 void hdb_topology_destroy(hdb_topology *t)
 {
     if (!t) return;
+    if (!t->devReady && !t->devAllocs.empty()) { // an upload failed half-way and was never retried
+        cudaSetDevice(t->device);
+        for (void *p : t->devAllocs) cudaFree(p);
+    }
     if (t->devReady) {
         cudaSetDevice(t->device);
         cudaDeviceSynchronize();
@@ -711,22 +733,28 @@ static void debug_report_clocks(hdb_topology *t, int nModels)
     const int n = std::min<int>(std::min<int>(nModels, (int)t->wsModels), t->smCount);
     std::vector<long long> h((size_t)n * 32);
     cudaMemcpy(h.data(), t->dbgClocks, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    double blk = 0, sol = 0, models = 0, ph[16] = {};
+    double blk = 0, sol = 0, models = 0, ph[24] = {};
     for (int b = 0; b < n; b++) {
         const long long *d = h.data() + (size_t)b * 32;
         blk += (double)d[0];
         sol += (double)d[1];
         models += (double)d[2];
-        for (int k = 0; k < 16; k++) ph[k] += (double)d[8 + k];
+        for (int k = 0; k < 24; k++) ph[k] += (double)d[8 + k];
     }
     if (models <= 0) return;
     std::fprintf(stderr, "[hdb] k_solve_pipe cycles/model (last launch, %d blocks): block %.0f | solver warp %.0f | streaming warp 1:\n", n,
                  blk / models, sol / models);
-    static const char *names[11] = {"Ksf/section loads issued", "-", "disp + Ksf, coefficients -> smem", "(barrier)", "react", "forces", "(barrier)", "factor gather issue",
-                                    "load cases", "(barrier)", "status"};
+    static const char *namesPipe[11] = {"Ksf/section loads issued", "-", "disp + Ksf, coefficients -> smem", "(barrier)", "react", "forces", "(barrier)", "factor gather issue",
+                                        "load cases", "(barrier)", "status"};
+    static const char *namesBulk[11] = {"coefficients + Ksf -> smem", "(barrier)", "react", "forces", "disp", "(barrier)", "load cases + factor", "(barrier)", "-", "-", "-"};
+    const char *leg = std::getenv("HDB_SOLVE_LEGACY");
+    const char **names = (leg && atoi(leg)) ? namesPipe : namesBulk;
     std::fprintf(stderr, "[hdb]  ");
     for (int k = 0; k < 11; k++) std::fprintf(stderr, " %s %.0f |", names[k], ph[k] / models);
     std::fprintf(stderr, "\n");
+    if (!(leg && atoi(leg)))
+        std::fprintf(stderr, "[hdb]   disp units: loads %.0f | wait slots %.0f | stores to slot %.0f | fence + issue %.0f || react units: items %.0f | wait slots %.0f | zero + stores %.0f | fence + issue %.0f || helper tables %.0f\n",
+                     ph[8] / models, ph[9] / models, ph[10] / models, ph[11] / models, ph[12] / models, ph[13] / models, ph[14] / models, ph[15] / models, ph[16] / models);
 }
 
 int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
@@ -828,6 +856,17 @@ int hdb_static_batch(hdb_topology *t, int32_t nModels, const double *sections, i
     if (rc != HDB_OK) return rc;
     prof_reset(t);
     int it = 0;
+    // an error exit must not leave copies into the caller's buffers in flight
+    struct Drain {
+        hdb_topology *t;
+        bool armed = true;
+        ~Drain()
+        {
+            if (!armed) return;
+            for (cudaStream_t s : {t->sIn, t->sK, t->sOut})
+                if (s) cudaStreamSynchronize(s);
+        }
+    } drain{t};
     for (int m0 = 0; m0 < nModels; m0 += t->chunkModels, it++) {
         HostChunk &c = t->chunk[it % NBUF];
         const int nm = std::min(t->chunkModels, nModels - m0);
@@ -858,6 +897,7 @@ int hdb_static_batch(hdb_topology *t, int32_t nModels, const double *sections, i
         CUDA_TRY(cudaEventRecord(c.evOut, t->sOut));
     }
     CUDA_TRY(cudaStreamSynchronize(t->sOut));
+    drain.armed = false;
     return HDB_OK;
 }
 

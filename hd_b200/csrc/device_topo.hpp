@@ -22,6 +22,9 @@ struct DevTopo {
     int nP, nB, dof, nFree, nBlk, nPad, nSlots, nSup, nnzR, nnzK, nDummy, maxBlkCount, winNeed;
     int nFwdOps, nBwdOps; // records incl. run headers and terminators
     int gWidth, rgWidth;  // widths of the ELL gather lists, 0 = use the CSR lists
+    int rWidth;           // widest reaction row K[r, free columns] (k_solve_bulk holds the rows as fixed-width lists)
+    int rChunk, rNCh;     // k_solve_bulk: a [dof] output row leaves in rNCh chunks of rChunk doubles (even, <= BULK_CHUNK)
+    const int32_t *rsPtr, *rsList; // supported DOFs of row chunk j: entries [rsPtr[j], rsPtr[j+1]) = position in the chunk | index among the supported DOFs << 16
     // geometry / topology (shared by every model of a batch)
     const double *points;      // [nP][2]
     const int32_t *beamN;      // [nB][2]
@@ -54,6 +57,7 @@ struct DevTopo {
     const int32_t *dummyPos;   // [nDummy]
 };
 
+constexpr int BULK_CHUNK = 192; // doubles per staging slot of k_solve_bulk = one bulk store of 1536 bytes
 constexpr int KE_LD = 37; // padded leading dimension of one element matrix in shared memory
 
 struct StaticLaunch {
@@ -89,6 +93,8 @@ cudaError_t launch_geometry(const DevTopo &T, const StaticLaunch &L, cudaStream_
 cudaError_t launch_assemble(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_factor(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
 cudaError_t launch_solve_pipe(const DevTopo &T, const StaticLaunch &L, cudaStream_t st);
+cudaError_t launch_solve_bulk(const DevTopo &T, const StaticLaunch &L, cudaStream_t st, int smemOptin, int nSM, bool &taken); // kernels_solve_bulk.cu
+bool solve_bulk_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes);
 bool solve_general_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes);
 cudaError_t launch_elements(const DevTopo &T, int nModels, const double *sections, double *klocal, double *tr,
                             double *kglobal, cudaStream_t st);

@@ -160,6 +160,7 @@ inline Error LinearStatic(Model &m, std::vector<LoadCase *> lcs)
     if (rc != HDB_OK) { e.add(name + detail::api_error(rc, "hdb_static_batch")); return e; }
     size_t upto = nLC;
     if (status == HDB_STATUS_IGNORE_LOAD) { upto = (size_t)fail; e.add(name + "Warning: List loads on not valid directions"); }
+    else if (status == HDB_STATUS_NONFINITE && fail >= 0) { upto = (size_t)fail; e.add(name + "Assembly node load: not valid node load"); } // model.go:692-696: earlier cases keep their results
     else if (status == HDB_STATUS_SINGULAR) { upto = 0; e.add(name + "Assembly node load: LU error factorization"); }
     else if (status != HDB_STATUS_OK) { upto = 0; e.add(name + "Assembly node load: not valid value"); }
     for (size_t i = 0; i < upto; i++) {

@@ -24,37 +24,13 @@
 #include "device_topo.hpp"
 #include "element.cuh"
 #include "hdb_internal.hpp"
+#include "solve_ops.cuh"
 
 namespace hdb {
 
 // ------------------------------------------------------------------------------------------------
 // shared element evaluation
 // ------------------------------------------------------------------------------------------------
-struct BeamGeom {
-    double c, s, length;
-};
-
-__device__ __forceinline__ BeamGeom beam_geom(const DevTopo &T, int b)
-{ // feBeam2d.go:142-172 evaluated once per topology on the host with the routines of element.cuh
-    BeamGeom g;
-    g.c = __ldg(T.geom + 3 * b);
-    g.s = __ldg(T.geom + 3 * b + 1);
-    g.length = __ldg(T.geom + 3 * b + 2);
-    return g;
-}
-
-// geometry of beam b of a model: the batch's own table (k_geometry) when coordinates vary per model
-__device__ __forceinline__ BeamGeom beam_geom(const DevTopo &T, const StaticLaunch &L, int model, int b)
-{
-    if (!L.geom) return beam_geom(T, b);
-    const double *q = L.geom + ((size_t)model * T.nB + b) * 3;
-    BeamGeom g;
-    g.c = q[0];
-    g.s = q[1];
-    g.length = q[2];
-    return g;
-}
-
 // ------------------------------------------------------------------------------------------------
 // k_geometry: per-model coordinates -> (cos, sin, length) of every beam with the element routines of the reference
 // (feBeam2d.go:11-19, 142-172).  This is also the geometry part of check.go for a batch: a NaN / Inf coordinate
@@ -736,18 +712,6 @@ constexpr int REACT_HELPER_PCT = 57;               // share of the reaction item
 constexpr int LOAD_U = 7;         // 16-byte loads in flight per streaming thread in the load stage
 constexpr unsigned FST_BYTES = 32u * 6u * 8u; // per-warp 32 x 6 staging tile of the force stage
 
-struct SolveCfg {
-    int casesPerPass; // <= 32
-    int nPass;        // passes over the load cases of a model (1 unless shared memory is short)
-    int lvmDoubles;   // one factor/table buffer
-    int xsDoubles;    // one xs buffer
-    int vec2;         // load and output arrays are 16-byte aligned and dof is even: 16-byte global accesses
-};
-
-// one block of xs = [cases][3] doubles, padded to an odd count: threads that read the same component of
-// consecutive blocks (reactions, beam forces) then fall into different banks
-__host__ __device__ inline int xs_block_doubles(int cp) { return (3 * cp) | 1; }
-
 static size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
 
 static size_t pipe_idx_bytes(const DevTopo &T)
@@ -785,258 +749,11 @@ bool solve_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, s
     return false;
 }
 
-__device__ __forceinline__ double lds_f64(unsigned a)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
-template <int OFF>
-__device__ __forceinline__ double lds_f64o(unsigned a)
-{
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
-    return v;
-}
-template <int OFF>
-__device__ __forceinline__ void lds_v2o(unsigned a, double &x, double &y)
-{
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(x), "=d"(y) : "r"(a), "n"(OFF));
-}
-__device__ __forceinline__ void sts_f64(unsigned a, double v)
-{
-    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
-}
-
-__device__ __forceinline__ void beam_forces_rigid(const BeamCoef &cf, const double gc, const double gs, const double *u,
-                                                  double *o)
-{ // rigid ends: the matrix has five distinct values (feBeam2d.go:28-56)
-    const double z0 = fma(gs, u[1], gc * u[0]), z1 = fma(gc, u[1], -gs * u[0]), z2 = u[2];
-    const double z3 = fma(gs, u[4], gc * u[3]), z4 = fma(gc, u[4], -gs * u[3]), z5 = u[5];
-    const double ax = cf.EFL * (z0 - z3);
-    const double sh = fma(cf.EJL2, z2 + z5, cf.EJL3 * (z1 - z4));
-    const double m0 = fma(cf.EJL, z5, fma(cf.EJL4, z2, cf.EJL2 * (z1 - z4)));
-    const double m1 = fma(cf.EJL4, z5, fma(cf.EJL, z2, cf.EJL2 * (z1 - z4)));
-    // 0 - x, not -x: the reference accumulates every force from +0 (gonum Dgemv), so it never prints a negative zero
-    o[0] = ax; o[1] = sh; o[2] = m0; o[3] = 0.0 - ax; o[4] = 0.0 - sh; o[5] = m1;
-}
-
-__device__ __noinline__ void beam_forces_pinned(const BeamCoef cf, const uint32_t pm, const double gc, const double gs, // cf by value: a reference would pin the caller's copy to local memory
-                                                const double *u, double *o)
-{ // released ends: the condensed matrix is dense
-    double k[36], z[6];
-    stiff_beam2d(cf, pm, k);
-    z[0] = fma(gs, u[1], gc * u[0]);
-    z[1] = fma(gc, u[1], -gs * u[0]);
-    z[2] = u[2];
-    z[3] = fma(gs, u[4], gc * u[3]);
-    z[4] = fma(gc, u[4], -gs * u[3]);
-    z[5] = u[5];
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        double acc = k[i * 6] * z[0];
-#pragma unroll
-        for (int l = 1; l < 6; l++) acc = fma(k[i * 6 + l], z[l], acc);
-        o[i] = acc + 0.0; // -0 -> +0, as a sum started from +0 gives (see beam_forces_rigid)
-    }
-}
-
-
-__device__ __forceinline__ int4 lds_op(unsigned a)
-{
-    int4 v;
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ int lds_s32(unsigned a)
-{
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ unsigned lds_u16(unsigned a)
-{
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
-__device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void bar_stream(int n) { asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory"); } // recover stage: streaming + helper warps
-__device__ __forceinline__ void bar_load(int n) { asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory"); }   // load stage: streaming warps
-
-// ---- the sequential part: one lane per load case walks the op runs (device_topo.hpp) -----------------
-// A block column of the factor in shared memory: header [1/d0 1/d1 1/d2 v10 v20 v21], off blocks L_IJ
-// row-major (+ 1 pad).  All table loads are warp-uniform 16-byte loads; the loads of op k+1 are issued
-// before the result of op k is stored.
-//
-// CHAIN run, forward: z(tgt) = V_tgt (p(tgt) - L z(src)), src = target of the op before
-__device__ __forceinline__ void chain_fwd(const unsigned pos, const int n, const unsigned lvA, const unsigned xA, const unsigned BS)
-{
-    int4 r = lds_op(pos), rN = lds_op(pos + 16u);
-    double h0, h1, h2;
-    {
-        const unsigned sa = xA + (unsigned)((r.z >> OP_SRC_SHIFT) & OP_BLK_MASK) * BS;
-        h0 = lds_f64o<0>(sa); h1 = lds_f64o<8>(sa); h2 = lds_f64o<16>(sa);
-    }
-    double m00, m01, m02, m10, m11, m12, m20, m21, m22, i2, v10, v20, v21, q0, q1, q2;
-    unsigned ta;
-#define CHAIN_LOAD(REC)                                                  \
-    do {                                                                 \
-        const unsigned a_ = lvA + (unsigned)(REC).x * 8u;                \
-        const unsigned h_ = lvA + (unsigned)(REC).y * 8u;                \
-        ta = xA + (unsigned)((REC).z & OP_BLK_MASK) * BS;                \
-        lds_v2o<0>(a_, m00, m01);                                        \
-        lds_v2o<16>(a_, m02, m10);                                       \
-        lds_v2o<32>(a_, m11, m12);                                       \
-        lds_v2o<48>(a_, m20, m21);                                       \
-        m22 = lds_f64o<64>(a_);                                          \
-        lds_v2o<16>(h_, i2, v10);                                        \
-        lds_v2o<32>(h_, v20, v21);                                       \
-        q0 = lds_f64o<0>(ta); q1 = lds_f64o<8>(ta); q2 = lds_f64o<16>(ta); \
-    } while (0)
-    CHAIN_LOAD(r);
-    for (int k = 0; k < n; k++) {
-        const int4 rNN = lds_op(pos + 16u * (unsigned)(k + 2)); // may run past the run: never used then
-        const double a0 = fma(-m02, h2, fma(-m01, h1, fma(-m00, h0, q0)));
-        const double a1 = fma(-m12, h2, fma(-m11, h1, fma(-m10, h0, q1)));
-        const double a2 = fma(-m22, h2, fma(-m21, h1, fma(-m20, h0, q2)));
-        const double z1 = fma(v10, a0, a1), z2 = fma(v21, a1, fma(v20, a0, a2));
-        const unsigned tc = ta;
-        CHAIN_LOAD(rN); // past the end of the run this reads a run header or the terminator: aligned, in range, unused
-        sts_f64(tc, a0); sts_f64(tc + 8u, z1); sts_f64(tc + 16u, z2);
-        h0 = a0; h1 = z1; h2 = z2;
-        rN = rNN;
-    }
-    (void)i2;
-#undef CHAIN_LOAD
-}
-
-// CHAIN run, backward: x(tgt) = V_tgt^T (D^-1 z(tgt) - L^T x(src))
-__device__ __forceinline__ void chain_bwd(const unsigned pos, const int n, const unsigned lvA, const unsigned xA, const unsigned BS)
-{
-    int4 r = lds_op(pos), rN = lds_op(pos + 16u);
-    double h0, h1, h2;
-    {
-        const unsigned sa = xA + (unsigned)((r.z >> OP_SRC_SHIFT) & OP_BLK_MASK) * BS;
-        h0 = lds_f64o<0>(sa); h1 = lds_f64o<8>(sa); h2 = lds_f64o<16>(sa);
-    }
-    double m00, m01, m02, m10, m11, m12, m20, m21, m22, i0, i1, i2, v10, v20, v21, z0, z1, z2;
-    unsigned ta;
-#define CHAIN_LOAD(REC)                                                  \
-    do {                                                                 \
-        const unsigned a_ = lvA + (unsigned)(REC).x * 8u;                \
-        const unsigned h_ = lvA + (unsigned)(REC).y * 8u;                \
-        ta = xA + (unsigned)((REC).z & OP_BLK_MASK) * BS;                \
-        lds_v2o<0>(a_, m00, m01);                                        \
-        lds_v2o<16>(a_, m02, m10);                                       \
-        lds_v2o<32>(a_, m11, m12);                                       \
-        lds_v2o<48>(a_, m20, m21);                                       \
-        m22 = lds_f64o<64>(a_);                                          \
-        lds_v2o<0>(h_, i0, i1);                                          \
-        lds_v2o<16>(h_, i2, v10);                                        \
-        lds_v2o<32>(h_, v20, v21);                                       \
-        z0 = lds_f64o<0>(ta); z1 = lds_f64o<8>(ta); z2 = lds_f64o<16>(ta); \
-    } while (0)
-    CHAIN_LOAD(r);
-    for (int k = 0; k < n; k++) {
-        const int4 rNN = lds_op(pos + 16u * (unsigned)(k + 2));
-        // L^T: column j of the off block against x(src)
-        const double a0 = fma(-m20, h2, fma(-m10, h1, fma(-m00, h0, z0 * i0)));
-        const double a1 = fma(-m21, h2, fma(-m11, h1, fma(-m01, h0, z1 * i1)));
-        const double a2 = fma(-m22, h2, fma(-m12, h1, fma(-m02, h0, z2 * i2)));
-        const double x1 = fma(v21, a2, a1), x0 = fma(v20, a2, fma(v10, a1, a0));
-        const unsigned tc = ta;
-        CHAIN_LOAD(rN);
-        sts_f64(tc, x0); sts_f64(tc + 8u, x1); sts_f64(tc + 16u, a2);
-        h0 = x0; h1 = x1; h2 = a2;
-        rN = rNN;
-    }
-#undef CHAIN_LOAD
-}
-
-// GENERIC run: per-op flags (blocks with several off blocks, blocks without any).  Same software pipeline as the
-// chain loops: the off block, the source x (unless it is the block just finished, which lives in registers) and,
-// at the first op of a block, its right-hand side are fetched one op ahead.
-template <bool FWD>
-__device__ __noinline__ void generic_run(const unsigned pos, const int n, const unsigned lvA, const unsigned xA, const unsigned BS)
-{
-    double h0 = 0, h1 = 0, h2 = 0, a0 = 0, a1 = 0, a2 = 0;
-    double m00, m01, m02, m10, m11, m12, m20, m21, m22, z0, z1, z2, q0, q1, q2;
-#define GEN_LOAD(REC)                                                                          \
-    do {                                                                                       \
-        const unsigned a_ = lvA + (unsigned)(REC).x * 8u;                                      \
-        const int y_ = (REC).z;                                                                \
-        lds_v2o<0>(a_, m00, m01);                                                              \
-        lds_v2o<16>(a_, m02, m10);                                                             \
-        lds_v2o<32>(a_, m11, m12);                                                             \
-        lds_v2o<48>(a_, m20, m21);                                                             \
-        m22 = lds_f64o<64>(a_);                                                                \
-        const unsigned s_ = xA + (unsigned)((y_ >> OP_SRC_SHIFT) & OP_BLK_MASK) * BS;          \
-        z0 = lds_f64o<0>(s_); z1 = lds_f64o<8>(s_); z2 = lds_f64o<16>(s_);                     \
-        const unsigned t_ = xA + (unsigned)(y_ & OP_BLK_MASK) * BS;                            \
-        q0 = lds_f64o<0>(t_); q1 = lds_f64o<8>(t_); q2 = lds_f64o<16>(t_);                     \
-    } while (0)
-    int4 r = lds_op(pos), rN = lds_op(pos + 16u);
-    GEN_LOAD(r);
-    for (int k = 0; k < n; k++) {
-        const int4 rNN = lds_op(pos + 16u * (unsigned)(k + 2)); // may run past the run: never used then
-        const int y = r.z;
-        const unsigned h_ = lvA + (unsigned)r.y * 8u;
-        const unsigned ta = xA + (unsigned)(y & OP_BLK_MASK) * BS;
-        if (y & OPF_FIRST) {
-            a0 = q0; a1 = q1; a2 = q2;
-            if (!FWD) { a0 *= lds_f64o<0>(h_); a1 *= lds_f64o<8>(h_); a2 *= lds_f64o<16>(h_); }
-        }
-        if (!(y & OPF_NOPULL)) {
-            if (y & OPF_PREV) { z0 = h0; z1 = h1; z2 = h2; }
-            if (FWD) {
-                a0 = fma(-m02, z2, fma(-m01, z1, fma(-m00, z0, a0)));
-                a1 = fma(-m12, z2, fma(-m11, z1, fma(-m10, z0, a1)));
-                a2 = fma(-m22, z2, fma(-m21, z1, fma(-m20, z0, a2)));
-            } else {
-                a0 = fma(-m20, z2, fma(-m10, z1, fma(-m00, z0, a0)));
-                a1 = fma(-m21, z2, fma(-m11, z1, fma(-m01, z0, a1)));
-                a2 = fma(-m22, z2, fma(-m12, z1, fma(-m02, z0, a2)));
-            }
-        }
-        double v10 = 0, v20 = 0, v21 = 0;
-        if (y & OPF_LAST) { v10 = lds_f64o<24>(h_); v20 = lds_f64o<32>(h_); v21 = lds_f64o<40>(h_); }
-        // the next op's values; its source or right-hand side may be the block this op is about to store, in
-        // which case PREV is set (source) or it is a different block (right-hand side): both safe to read now
-        GEN_LOAD(rN);
-        if (y & OPF_LAST) {
-            if (FWD) { h0 = a0; h1 = fma(v10, a0, a1); h2 = fma(v21, a1, fma(v20, a0, a2)); }
-            else { h2 = a2; h1 = fma(v21, a2, a1); h0 = fma(v20, a2, fma(v10, a1, a0)); }
-            sts_f64(ta, h0); sts_f64(ta + 8u, h1); sts_f64(ta + 16u, h2);
-        }
-        r = rN;
-        rN = rNN;
-    }
-#undef GEN_LOAD
-}
-
-template <bool FWD>
-__device__ __forceinline__ void walk_ops(unsigned pos, const unsigned lvA, const unsigned xA, const unsigned BS)
-{
-    for (;;) {
-        const int4 hdr = lds_op(pos);
-        const int n = hdr.x >> 1;
-        if (n == 0) break;
-        pos += 16u;
-        if (hdr.z == RUN_CHAIN) {
-            if (FWD) chain_fwd(pos, n, lvA, xA, BS);
-            else chain_bwd(pos, n, lvA, xA, BS);
-        } else generic_run<FWD>(pos, n, lvA, xA, BS);
-        pos += 16u * (unsigned)n;
-    }
-}
-
 template <bool DBG> // DBG: per-phase cycle counters (HDB_DEBUG_CLOCKS); a separate instantiation keeps them out of the product's registers
 __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T, const StaticLaunch L, const SolveCfg cfg)
 {
     extern __shared__ __align__(16) double smem_d[];
-    __shared__ int s_fail[2], s_flag[2];
+    __shared__ unsigned s_fail[2], s_failNF[2];
     const int tid = threadIdx.x;
     // The solver warp keeps its scheduler (SM sub-partition 0 = warps 0, 4, 8, ...) to itself: its shared-memory
     // loads would otherwise queue behind the global loads and stores of streaming warps in the same
@@ -1094,8 +811,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
     }
     if (tid < (int)(ZERO_BYTES / 8)) sts_f64(zeroA + 8u * tid, 0.0);
     if (tid < 2) {
-        s_fail[tid] = 0x7fffffff;
-        s_flag[tid] = 0;
+        s_fail[tid] = NO_FAIL_CASE;
+        s_failNF[tid] = NO_FAIL_CASE;
     }
     __syncthreads();
 
@@ -1362,8 +1079,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                 const double *pb = L.loads + ((size_t)model * L.nLC + c0) * dof + 2 * st;
                 double *orr = L.react ? L.react + ((size_t)model * L.nLC + c0) * dof + 2 * st : nullptr;
                 const int nFlat = nc * dof;
-                bool badLoad = false;
-                int failC = 0x7fffffff;
+                unsigned failNF = NO_FAIL_CASE, failC = NO_FAIL_CASE;
                 {
                     int g = (2 * st) % dof;
                     unsigned cOff = (unsigned)((2 * st) / dof) * 24u;
@@ -1409,7 +1125,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                             if (f < nFlat) {
                                 const double v0 = v[u].x, v1 = v[u].y;
                                 const unsigned b4 = fl >> (4 * u);
-                                badLoad |= !(fabs(v0) <= 1.7976931348623157e308) | !(fabs(v1) <= 1.7976931348623157e308);
+                                if (!(fabs(v0) <= 1.7976931348623157e308)) failNF = min(failNF, (unsigned)(c0 + f / dof)); // rare
+                                if (!(fabs(v1) <= 1.7976931348623157e308) && f + 1 < nFlat) failNF = min(failNF, (unsigned)(c0 + (f + 1) / dof));
                                 if (a0[u]) sts_f64(a0[u], v0);
                                 if (a1[u]) sts_f64(a1[u], v1);
                                 if (orr) {
@@ -1422,8 +1139,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                                     }
                                 }
                                 if (b4 & 10u) { // a load on a DOF without stiffness (model.go:424-437); rare
-                                    if ((b4 & 2u) && v0 != 0.0) failC = min(failC, c0 + f / dof);
-                                    if ((b4 & 8u) && v1 != 0.0) failC = min(failC, c0 + (f + 1) / dof);
+                                    if ((b4 & 2u) && v0 != 0.0) failC = min(failC, (unsigned)(c0 + f / dof));
+                                    if ((b4 & 8u) && v1 != 0.0) failC = min(failC, (unsigned)(c0 + (f + 1) / dof));
                                 }
                             }
                         }
@@ -1443,23 +1160,15 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_solve_pipe(const DevTopo T,
                     const double2 v = __ldcs(reinterpret_cast<const double2 *>(L.Lm + (size_t)model * T.nSlots + s));
                     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(lvB + (unsigned)s * 8u), "d"(v.x), "d"(v.y) : "memory");
                 }
-                if (badLoad) atomicMax(&s_flag[buf], 1);
-                if (failC != 0x7fffffff) atomicMin(&s_fail[buf], failC);
+                if (failNF != NO_FAIL_CASE) atomicMin(&s_failNF[buf], failNF);
+                if (failC != NO_FAIL_CASE) atomicMin(&s_fail[buf], failC);
                 TICK(8);
                 bar_load(NS);
                 TICK(9);
-                if (st == 0) { // status of this pass (model.go:424-437); passes of a model arrive in order
-                    int s = sOld;
-                    const int fc = s_fail[buf];
-                    if (s_flag[buf] && (s == HDB_STATUS_OK || s == HDB_STATUS_IGNORE_LOAD)) s = HDB_STATUS_NONFINITE;
-                    else if (s == HDB_STATUS_OK && fc != 0x7fffffff) s = HDB_STATUS_IGNORE_LOAD;
-                    if (s != sOld) L.status[model] = s;
-                    if (L.failCase) {
-                        const int old = pass == 0 ? -1 : L.failCase[model];
-                        L.failCase[model] = old >= 0 ? old : (fc != 0x7fffffff ? fc : -1);
-                    }
-                    s_fail[buf] = 0x7fffffff;
-                    s_flag[buf] = 0;
+                if (st == 0) { // status of this pass (solve_ops.cuh); passes of a model arrive in order
+                    merge_load_status(L, model, pass, sOld, s_failNF[buf], s_fail[buf]);
+                    s_fail[buf] = NO_FAIL_CASE;
+                    s_failNF[buf] = NO_FAIL_CASE;
                 }
                 TICK(10);
             }
@@ -1518,7 +1227,7 @@ bool solve_general_config(const DevTopo &T, int nLC, int smemOptin, int &casesPe
 __global__ void __launch_bounds__(GEN_THREADS) k_solve_general(const DevTopo T, const StaticLaunch L, const int cp)
 {
     extern __shared__ double xs[]; // [nPad][cp]
-    __shared__ int s_bad, s_failc;
+    __shared__ unsigned s_bad, s_failc; // first case of the pass with a non-finite load / a load on a DOF without stiffness
     const int model = blockIdx.x, tid = threadIdx.x, dof = T.dof, nB = T.nB;
     const double *lm = L.Lm + (size_t)model * T.nSlots;
     const double *ksf = L.Ksf + (size_t)model * T.nnzR;
@@ -1527,29 +1236,28 @@ __global__ void __launch_bounds__(GEN_THREADS) k_solve_general(const DevTopo T, 
     for (int pass = 0; pass < (nPass < 1 ? 1 : nPass); pass++) {
         const int c0 = pass * cp, nc = min(cp, L.nLC - c0);
         if (tid == 0) {
-            s_bad = 0;
-            s_failc = 0x7fffffff;
+            s_bad = NO_FAIL_CASE;
+            s_failc = NO_FAIL_CASE;
         }
         __syncthreads();
         // ---- load cases -> right-hand sides; checks of model.go:692-696 and 424-437; reactions start as -p ----
         const double *pb = L.loads + ((size_t)model * L.nLC + c0) * dof;
-        bool bad = false;
-        int failC = 0x7fffffff;
+        unsigned bad = NO_FAIL_CASE, failC = NO_FAIL_CASE;
         for (int idx = tid; idx < nc * dof; idx += GEN_THREADS) {
             const int c = idx / dof, g = idx - c * dof;
             const double v = pb[idx];
-            if (!(fabs(v) <= 1.7976931348623157e308)) bad = true;
+            if (!(fabs(v) <= 1.7976931348623157e308)) bad = min(bad, (unsigned)(c0 + c));
             const int xr = T.xrow[g];
             if (xr >= 0) xs[xr * cp + c] = v;
-            else if (xr == -2 && v != 0.0) failC = min(failC, c0 + c);
+            else if (xr == -2 && v != 0.0) failC = min(failC, (unsigned)(c0 + c));
             if (L.react) L.react[((size_t)model * L.nLC + c0) * dof + idx] = T.supIndex[g] >= 0 ? -v : 0.0;
         }
         for (int idx = tid; idx < T.nDummy * nc; idx += GEN_THREADS) {
             const int q = idx / nc, c = idx - q * nc;
             xs[T.dummyPos[q] * cp + c] = 0.0;
         }
-        if (bad) atomicMax(&s_bad, 1);
-        if (failC != 0x7fffffff) atomicMin(&s_failc, failC);
+        if (bad != NO_FAIL_CASE) atomicMin(&s_bad, bad);
+        if (failC != NO_FAIL_CASE) atomicMin(&s_failc, failC);
         __syncthreads();
         // ---- both substitutions: four lanes per load case share the off blocks of a column ----
         for (int cb = 0; cb < nc; cb += GEN_THREADS / GEN_SUB) { // uniform trip count for the whole block
@@ -1647,18 +1355,7 @@ __global__ void __launch_bounds__(GEN_THREADS) k_solve_general(const DevTopo T, 
             }
         }
         __syncthreads();
-        if (tid == 0) { // status of this pass, as in k_solve_pipe
-            const int sOld = L.status[model];
-            int st2 = sOld;
-            const int fc = s_failc;
-            if (s_bad && (st2 == HDB_STATUS_OK || st2 == HDB_STATUS_IGNORE_LOAD)) st2 = HDB_STATUS_NONFINITE;
-            else if (st2 == HDB_STATUS_OK && fc != 0x7fffffff) st2 = HDB_STATUS_IGNORE_LOAD;
-            if (st2 != sOld) L.status[model] = st2;
-            if (L.failCase) {
-                const int old = pass == 0 ? -1 : L.failCase[model];
-                L.failCase[model] = old >= 0 ? old : (fc != 0x7fffffff ? fc : -1);
-            }
-        }
+        if (tid == 0) merge_load_status(L, model, pass, L.status[model], s_bad, s_failc); // as in k_solve_pipe
         __syncthreads();
     }
 }
@@ -1684,6 +1381,11 @@ cudaError_t launch_solve_pipe(const DevTopo &T, const StaticLaunch &L, cudaStrea
     cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, dev);
     SolveCfg cfg;
     size_t smem = 0;
+    if (!(std::getenv("HDB_SOLVE_GENERAL") && atoi(std::getenv("HDB_SOLVE_GENERAL")))) { // the bulk-copy pipeline when the shapes allow it
+        bool taken = false;
+        cudaError_t e = launch_solve_bulk(T, L, st, optin, nSM, taken);
+        if (taken || e != cudaSuccess) return e;
+    }
     {
         const char *force = std::getenv("HDB_SOLVE_GENERAL"); // tests: the general kernel on a model the pipeline could take
         if ((force && atoi(force)) || !solve_config(T, L.nLC, optin, cfg.casesPerPass, smem)) return launch_solve_general(T, L, st, optin);

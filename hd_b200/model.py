@@ -17,6 +17,8 @@ import copy
 from dataclasses import dataclass, field
 from typing import List, Optional
 
+import numpy as np
+
 Gravity = 9.80665  # model.go:713
 
 
@@ -98,3 +100,28 @@ class ModalCase:
     def String(self) -> str:  # model.go:235-255
         from .report import modal_case_string
         return modal_case_string(self)
+
+
+class FlatModel:
+    """hd.Model flattened into the dense arrays the C ABI takes (include/hdb200.h: points[nP][2], beam nodes and
+    A, J, E per beam, pins[nB][6], supports[nP][3]).  An empty Pins slice means all rigid (model.go:344-346)."""
+
+    def __init__(self, points, beamN, sections, pins, supports):
+        self.points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
+        self.beamN = np.ascontiguousarray(beamN, dtype=np.int64).reshape(-1, 2)
+        self.sections = np.ascontiguousarray(sections, dtype=np.float64).reshape(-1, 3)
+        self.nP, self.nB = self.points.shape[0], self.beamN.shape[0]
+        if pins is None or len(pins) == 0:
+            pins = np.zeros((self.nB, 6), dtype=np.uint8)
+        self.pins = np.ascontiguousarray(pins, dtype=np.uint8).reshape(-1, 6)
+        self.supports = np.ascontiguousarray(supports, dtype=np.uint8).reshape(-1, 3)
+        self.dof = 3 * self.nP
+
+
+def flatten_model(m: Model) -> FlatModel:
+    pts = np.array([[p[0], p[1]] for p in m.Points], dtype=np.float64).reshape(-1, 2)
+    bn = np.array([[b.N[0], b.N[1]] for b in m.Beams], dtype=np.int64).reshape(-1, 2)
+    sec = np.array([[b.A, b.J, b.E] for b in m.Beams], dtype=np.float64).reshape(-1, 3)
+    pins = np.array([list(p) for p in m.Pins], dtype=np.uint8).reshape(-1, 6) if len(m.Pins) else None
+    sup = np.array([list(s) for s in m.Supports], dtype=np.uint8).reshape(-1, 3)
+    return FlatModel(pts, bn, sec, pins, sup)

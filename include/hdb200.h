@@ -188,7 +188,8 @@ int hdb_element_batch(hdb_topology *t, int32_t nModels, const double *sections, 
  * model.go:787).  Outputs ascending in Hz: nModes[nModels], hz[nModels][maxModes],
  * shapes[nModels][maxModes][nP][3] (unit 2-norm over 3*nP entries; sign is implementation-
  * defined as in LAPACK), status[nModels].  maxModes >= number of distinct free mass DOFs
- * (hdb_modal_mode_count). */
+ * (hdb_modal_mode_count).  hdb_modal_batch_dev synchronises `stream` once after uploading its mass tables (and when
+ * its scratch has to grow); the kernels themselves are enqueued without a further synchronisation. */
 int hdb_modal_mode_count(const hdb_topology *t, int32_t nMass, const int64_t *massN);
 int hdb_modal_batch(hdb_topology *t, int32_t nModels, const double *sections, int32_t nMass,
                     const int64_t *massN, const double *mass, int32_t maxModes, int32_t *nModes,
@@ -218,7 +219,8 @@ int hdb_buckling_batch_dev(hdb_topology *t, int32_t nModels, const double *secti
  * (device): intensities {qx, qy}; nodes[nN] (host), f[nModels][nLC][nN][3] (device, may be NULL when nN == 0): node
  * loads appended after the uniform loads.  loads[nModels][nLC][dof] (device) is bit-identical to flattening the
  * LoadNode list the reference would build (same order of additions).  Moves 16 bytes per loaded beam and case over
- * PCIe instead of 8*dof bytes per case. */
+ * PCIe instead of 8*dof bytes per case.  Unlike the other *_dev entries this one SYNCHRONISES `stream` before it
+ * returns (its per-call index tables are freed on return). */
 int hdb_uniform_loads_dev(hdb_topology *t, int32_t nModels, int32_t nLC, int32_t nU, const int32_t *ubeam,
                           const uint8_t *uproj, const double *q, int32_t nN, const int64_t *nodes, const double *f,
                           double *loads, void *stream);

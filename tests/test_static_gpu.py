@@ -295,6 +295,92 @@ def test_pattern_mismatch_is_flagged(oracle):
     t.close()
 
 
+def test_growing_batches_on_one_handle(oracle):
+    """INTEGRATION.md tells callers to create the topology once and reuse it: batches of 1, then 20, then 33, then 70
+    models on the same handle (the workspace of the first call is too small for the later ones)."""
+    N = 8
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    for nM in (1, 20, 33, 70, 5):
+        secs = frames.uniform_frame_sections(N, 11, nM)
+        loads = frames.uniform_frame_loads(N, 11, nM)
+        status, fail, disp, forces, react = t.static_batch(secs, loads)
+        assert not status.any()
+        ost, od, of, orr = oracle.static_batch(fm, secs, loads)
+        compare_rule(od, disp)
+        compare_rule(orr, react)
+        force_rule(of, forces)
+    t.close()
+
+
+@pytest.mark.parametrize("N,nM,nLC", [(8, 37, 20), (128, 150, 20), (16, 9, 45), (4, 3, 1)])
+def test_bulk_copy_kernel_matches_the_ld_st_kernel_bit_for_bit(oracle, monkeypatch, N, nM, nLC):
+    """k_solve_bulk (results staged in shared memory, bulk-copy stores, reactions written once) against k_solve_pipe
+    (HDB_SOLVE_LEGACY=1): same arithmetic in the same order, so every output is bit-identical."""
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    secs = frames.uniform_frame_sections(N, 5, nM)
+    loads = frames.uniform_frame_loads(N, 5, nM, nLC)
+    a = t.static_batch(secs, loads)
+    monkeypatch.setenv("HDB_SOLVE_LEGACY", "1")
+    b = t.static_batch(secs, loads)
+    monkeypatch.delenv("HDB_SOLVE_LEGACY")
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert not a[0].any()
+    t.close()
+
+
+@pytest.mark.parametrize("nnz", [0, 9, 64, 65, 400])
+def test_loads_on_supported_dofs(oracle, monkeypatch, nnz):
+    """Loads on supported DOFs enter the reactions only (model.go:478).  k_solve_bulk keeps the non-zero ones of an item in a
+    side list of 64 entries and reads p a second time when there are more: a few, exactly 64, 65 and many of them, against
+    k_solve_pipe bit for bit and against the oracle."""
+    N, nM, nLC = 8, 5, 20
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    secs = frames.uniform_frame_sections(N, 2, nM)
+    loads = frames.uniform_frame_loads(N, 2, nM, nLC)
+    sup = np.flatnonzero(fm.supports.reshape(-1))
+    rng = np.random.default_rng(nnz)
+    for mi in range(1, nM):  # model 0 keeps zero loads on its supports
+        flat = rng.choice(nLC * len(sup), size=min(nnz, nLC * len(sup)), replace=False)
+        loads[mi, flat // len(sup), sup[flat % len(sup)]] = rng.uniform(-1e4, 1e4, size=len(flat))
+    if nnz:
+        loads[1, 3, sup[0]] = -0.0  # a negative zero is a load too: -(-0) + (+0) keeps its sign rules
+    a = t.static_batch(secs, loads)
+    monkeypatch.setenv("HDB_SOLVE_LEGACY", "1")
+    b = t.static_batch(secs, loads)
+    monkeypatch.delenv("HDB_SOLVE_LEGACY")
+    assert not a[0].any()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+        assert np.array_equal(np.signbit(x), np.signbit(y))
+    ost, od, of, orr = oracle.static_batch(fm, secs, loads)
+    compare_rule(orr, a[4])
+    compare_rule(od, a[2])
+    t.close()
+
+
+def test_bulk_copy_kernel_with_pins_and_partial_outputs(oracle):
+    """released ends (out-of-line element), a subset of the outputs, and an odd case count."""
+    m, lcs, _ = fixtures.GOLDEN["model.String"]()
+    fm, t = topo_of(oracle, m)
+    nM = 40
+    secs = random_sections(fm, nM, seed=3)
+    base = np.stack([oracle.node_loads(fm.nP, lc.LoadNodes) for lc in lcs])
+    loads = np.tile(base, (nM, 4, 1))[:, :7] * np.linspace(0.5, 2.0, 7)[None, :, None]
+    full = t.static_batch(secs, loads)
+    assert not full[0].any()
+    ost, od, of, orr = oracle.static_batch(fm, secs, loads)
+    compare_rule(od, full[2])
+    compare_rule(orr, full[4])
+    force_rule(of, full[3])
+    for want in (("disp",), ("forces",), ("react",), ("disp", "react")):
+        part = t.static_batch(secs, loads, want)
+        for name, x, y in zip(("disp", "forces", "react"), part[2:], full[2:]):
+            if name in want:
+                assert np.array_equal(x, y), (want, name)
+    t.close()
+
+
 # ------------------------------------------------------------------ shapes and paths
 @pytest.mark.parametrize("nLC", [1, 7, 33, 70])
 def test_ragged_case_counts(oracle, nLC):
@@ -472,12 +558,13 @@ def test_unaligned_device_buffers_take_the_scalar_paths(oracle):
 
 def test_statuses_across_case_passes(oracle):
     """More load cases than one pass of the solve kernel holds (32): the offending case sits in the second or
-    third pass.  failCase = the first case with a load on a DOF without stiffness (model.go:424-437); a
-    non-finite load anywhere wins (assemblyNodeLoad rejects it before any solve, model.go:692-696)."""
+    third pass.  The reference stops at the FIRST failing case (model.go:415-437): status and failCase belong to the
+    smallest case index that has a non-finite load (assemblyNodeLoad, model.go:692-696) or a load on a DOF without
+    stiffness (model.go:424-437); in one and the same case the non-finite load is met first."""
     m, lcs, _ = fixtures.truss()          # every node is fully pinned: rotations carry no stiffness
     fm = oracle.flatten_model(m)
     t = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports)
-    nLC, nM = 70, 4
+    nLC, nM = 70, 6
     base = oracle.node_loads(fm.nP, lcs[0].LoadNodes)
     loads = np.tile(base, (nM, nLC, 1)) * np.linspace(0.5, 1.5, nLC)[None, :, None]
     rot = 3 * 1 + 2                      # rotation of node 1
@@ -485,18 +572,24 @@ def test_statuses_across_case_passes(oracle):
     loads[2, 69, rot] = 1.0              # third pass ...
     loads[2, 40, rot] = 1.0              # ... but an earlier one in the second: the first offender counts
     loads[3, 66, 0] = np.nan             # non-finite in the third pass
-    loads[3, 5, rot] = 7.0               # and an ignore-load in the first: non-finite still wins
+    loads[3, 5, rot] = 7.0               # and an ignore-load in the first: the earlier case counts
+    loads[4, 33, 1] = np.inf             # non-finite in the second pass
+    loads[4, 64, rot] = 7.0              # ignore-load later: the earlier case counts
+    loads[5, 50, rot] = 7.0              # both in the same case: assemblyNodeLoad fails first
+    loads[5, 50, 4] = -np.inf
     sec = np.tile(fm.sections, (nM, 1, 1))
     with np.errstate(all="ignore"):
         status, fail, disp, forces, react = t.static_batch(sec, loads)
-    assert list(status) == [_lib.STATUS_OK, _lib.STATUS_IGNORE_LOAD, _lib.STATUS_IGNORE_LOAD, _lib.STATUS_NONFINITE]
-    assert fail[1] == 45 and fail[2] == 40
+    assert list(status) == [_lib.STATUS_OK, _lib.STATUS_IGNORE_LOAD, _lib.STATUS_IGNORE_LOAD, _lib.STATUS_IGNORE_LOAD,
+                            _lib.STATUS_NONFINITE, _lib.STATUS_NONFINITE]
+    assert list(fail) == [-1, 45, 40, 5, 33, 50]
     ost, od, of, orr = oracle.static_batch(fm, sec[:1], loads[:1])
     assert ost[0] == oracle.OK
     compare_rule(od[0], disp[0])
     compare_rule(orr[0], react[0])
     # the cases before the offending one are complete and correct (model.go:415-437: earlier cases keep their results)
     compare_rule(od[0][:45], disp[1][:45])
+    compare_rule(od[0][:33], disp[4][:33])
     t.close()
 
 

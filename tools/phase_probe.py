@@ -5,9 +5,9 @@ if not os.environ.get("PROBE_NOCLK"):
     os.environ["HDB_DEBUG_CLOCKS"] = "1"
 import numpy as np, torch
 from hd_b200 import _lib, frames
-from oracle import hd_oracle as oracle
+from hd_b200.model import flatten_model
 N, M, nLC = 128, int(os.environ.get("PROBE_M", "4096")), 20
-fm = oracle.flatten_model(frames.uniform_frame(N))
+fm = flatten_model(frames.uniform_frame(N))
 sec = frames.uniform_frame_sections(N, 0, M); loads = frames.uniform_frame_loads(N, 0, M)
 t = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports)
 dev = torch.device("cuda:0")
@@ -16,8 +16,11 @@ dd = torch.empty((M, nLC, fm.nP, 3), dtype=torch.float64, device=dev)
 df = torch.empty((M, nLC, fm.nB, 6), dtype=torch.float64, device=dev)
 dr = torch.empty((M, nLC, fm.nP, 3), dtype=torch.float64, device=dev)
 st = torch.zeros((M,), dtype=torch.int32, device=dev); fc = torch.zeros((M,), dtype=torch.int32, device=dev)
-for name, (a, b, c) in {"all": (dd, df, dr), "disp only": (dd, None, None), "forces only": (None, df, None),
-                         "react only": (None, None, dr), "none": (None, None, None)}.items():
+cases = {"all": (dd, df, dr), "disp only": (dd, None, None), "forces only": (None, df, None),
+         "react only": (None, None, dr), "none": (None, None, None)}
+if os.environ.get("PROBE_ONLY"):
+    cases = {k: v for k, v in cases.items() if k in os.environ["PROBE_ONLY"].split(",")}
+for name, (a, b, c) in cases.items():
     for _ in range(2):
         t.set_profiling(1)
         sys.stderr.write(f"--- {name}\n"); sys.stderr.flush()
