@@ -1065,10 +1065,18 @@ int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections
         mptr.push_back((int32_t)midx.size());
     }
     const size_t per = (size_t)s * S.dof * sizeof(double);
-    int sbm = (int)std::max<size_t>(1, std::min<size_t>((size_t)nModels, ((size_t)768 << 20) / (2 * per)));
+    // the split pipeline (tridiagonalisation | all QL recurrences at once | rotations + shapes) needs per model: Q, the
+    // tridiagonal, and the log of the QL rotations
+    const bool split = modal_split_fits(s, t->smemOptin) && !std::getenv("HDB_MODAL_SINGLE");
+    size_t qDoubles = 0, rotCap = 0, maxSweeps = 0;
+    if (split) modal_split_scratch(s, qDoubles, rotCap, maxSweeps);
+    auto al256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t perSplit = split ? al256(qDoubles * 8) + al256((size_t)2 * s * 8) + al256(rotCap * 16) + al256(maxSweeps * 16) + 256 : 0;
+    const size_t perAll = 2 * per + (size_t)s * sizeof(double) + perSplit;
+    int sbm = (int)std::max<size_t>(1, std::min<size_t>((size_t)nModels, ((size_t)6 << 30) / perAll));
     sbm = std::min(sbm, t->subBatch);
     const size_t tabBytes = (dofs.size() + mptr.size() + std::max<size_t>(midx.size(), 1)) * sizeof(int32_t);
-    const size_t need = 2 * per * sbm + (size_t)sbm * s * sizeof(double) + tabBytes + 1024;
+    const size_t need = al256(2 * per * sbm) + al256((size_t)sbm * s * sizeof(double)) + al256(tabBytes) + perSplit * sbm + 4096;
     if (need > t->modalBytes) {
         if (t->modalBuf) {
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -1082,10 +1090,24 @@ int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections
     char *base = (char *)t->modalBuf;
     double *unitLoads = (double *)base;
     double *sol = (double *)(base + per * sbm);
-    double *msqrt = (double *)(base + 2 * per * sbm);
-    int32_t *dMassDof = (int32_t *)(base + 2 * per * sbm + (size_t)sbm * s * sizeof(double));
+    char *cur = base + al256(2 * per * sbm);
+    double *msqrt = (double *)cur;
+    cur += al256((size_t)sbm * s * sizeof(double));
+    int32_t *dMassDof = (int32_t *)cur;
     int32_t *dMptr = dMassDof + dofs.size();
     int32_t *dMidx = dMptr + mptr.size();
+    cur += al256(tabBytes);
+    double *qScratch = nullptr, *deScratch = nullptr;
+    double2 *rotLog = nullptr;
+    int4 *rotHdr = nullptr;
+    int32_t *rotSweeps = nullptr;
+    if (split) {
+        qScratch = (double *)cur; cur += al256(qDoubles * 8) * sbm;
+        deScratch = (double *)cur; cur += al256((size_t)2 * s * 8) * sbm;
+        rotLog = (double2 *)cur; cur += al256(rotCap * 16) * sbm;
+        rotHdr = (int4 *)cur; cur += al256(maxSweeps * 16) * sbm;
+        rotSweeps = (int32_t *)cur;
+    }
     CUDA_TRY(cudaMemcpyAsync(dMassDof, dofs.data(), dofs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(dMptr, mptr.data(), mptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (!midx.empty())
@@ -1104,6 +1126,10 @@ int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections
         M.hz = hz + (size_t)m0 * maxModes;
         M.shapes = shapes ? shapes + (size_t)m0 * maxModes * S.dof : nullptr;
         M.status = status + m0;
+        if (split) { // strides of the per-model scratch records are the aligned sizes above
+            M.qScratch = qScratch; M.deScratch = deScratch; M.rotLog = rotLog; M.rotHdr = rotHdr; M.rotSweeps = rotSweeps;
+            M.rotCap = (int)(al256(rotCap * 16) / 16); M.rotMaxSweeps = (int)(al256(maxSweeps * 16) / 16);
+        }
         {
             ProfScope ps(t, KIND_MODAL0, st);
             CUDA_TRY(launch_modal_loads(M, st));
@@ -1115,14 +1141,14 @@ int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections
         if (rc != HDB_OK) return rc;
         {
             ProfScope ps(t, KIND_MODAL0 + 1, st);
-            cudaError_t e = launch_modal_eigen(M, t->smemOptin, st);
+            cudaError_t e = split ? launch_modal_split(M, t->smemOptin, st) : launch_modal_eigen(M, t->smemOptin, st);
             if (e == cudaErrorInvalidConfiguration) {
                 set_error_detail("modal eigen kernel does not fit shared memory");
                 return HDB_ERR_UNSUPPORTED;
             }
             CUDA_TRY(e);
         }
-        count_launch(1);
+        count_launch(split ? 3 : 1);
     }
     return HDB_OK;
 }

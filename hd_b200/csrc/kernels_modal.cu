@@ -8,6 +8,7 @@
 //                   tql2 pair, parallelised over rows), Hz = 1/(2 pi sqrt(lambda)) ascending
 //                   (model.go:830, 846), shapes = K^-1[:,S] M^1/2 y as one dense FP64 contraction,
 //                   scaled to unit 2-norm over the 3*nP entries (what Dgeev returns, model.go:836-841).
+#include <cstdio>
 #include <cstdlib>
 #include <cmath>
 
@@ -78,13 +79,19 @@ __device__ __forceinline__ double block_sum(double v, double *red)
 // the transformations, implicit QL with accumulated vectors (tql2).  V[n][n] (element (i, j) at i + j * LD)
 // holds the symmetric matrix on entry and the eigenvectors (columns) on exit, d the eigenvalues.  Called by
 // every thread of a block of EIG_THREADS threads; returns non-zero if the QL iteration did not converge.
-__device__ __forceinline__ int sym_eig_smem(double *V, const int LD, const int n, double *d, double *e, double *cc, double *ss, double *red)
+// First half: Householder tridiagonalisation and accumulation of the transformations (tred2).  On exit V holds the
+// orthogonal Q with Q^T A Q = T, d the diagonal of T and e its subdiagonal shifted as tql2 wants it (e[i] couples i, i+1).
+__device__ __forceinline__ void sym_tridiag_smem(double *V, const int LD, const int n, double *d, double *e, double *red)
 {
     const int tid = threadIdx.x;
-    __shared__ double s_h, s_hh;
-    __shared__ int s_m, s_more, s_fail;
+#ifdef HDB_MODAL_CLOCKS
+    long long tc0 = clock64();
+#define MSTAMP(name) do { __syncthreads(); if (tid == 0 && blockIdx.x == 0) { long long t_ = clock64(); printf("[modal] %-12s %lld\n", name, t_ - tc0); tc0 = t_; } } while (0)
+#else
+#define MSTAMP(name) do {} while (0)
+#endif
+    __shared__ double s_h;
 #define VV(i, j) V[(i) + (size_t)(j) * LD]
-    if (tid == 0) s_fail = 0;
     __syncthreads();
     // ---- Householder reduction to tridiagonal form (tred2), lower triangle ----
     for (int j = tid; j < n; j += EIG_THREADS) d[j] = VV(n - 1, j);
@@ -157,6 +164,7 @@ __device__ __forceinline__ int sym_eig_smem(double *V, const int LD, const int n
         if (tid == 0) d[i] = s_h;
         __syncthreads();
     }
+    MSTAMP("tred2");
     // ---- accumulate the transformations ----
     for (int i = 0; i < n - 1; i++) {
         if (tid == 0) {
@@ -196,7 +204,21 @@ __device__ __forceinline__ int sym_eig_smem(double *V, const int LD, const int n
         e[n - 1] = 0.0;
     }
     __syncthreads();
+    MSTAMP("accumulate");
+#undef VV
+}
 
+// Second half: implicit QL with accumulated vectors (tql2) on the tridiagonal (d, e), rotating the columns of V.
+__device__ __forceinline__ int sym_ql_smem(double *V, const int LD, const int n, double *d, double *e, double *cc, double *ss, double *red)
+{
+    const int tid = threadIdx.x;
+#ifdef HDB_MODAL_CLOCKS
+    long long tc0 = clock64();
+#endif
+    __shared__ int s_fail;
+#define VV(i, j) V[(i) + (size_t)(j) * LD]
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
     // ---- implicit QL with accumulated vectors (tql2), producer / consumer.  The scalar recurrence of a sweep
     //      depends only on d and e, never on the vectors: thread 0 runs all sweeps back to back and leaves the
     //      rotations of each in a ring of QL_RING slots; warps 1.. apply them to the rows of V as they appear.
@@ -331,8 +353,18 @@ __device__ __forceinline__ int sym_eig_smem(double *V, const int LD, const int n
     }
 
     __syncthreads();
+    MSTAMP("ql");
     return s_fail;
 #undef VV
+}
+
+// Symmetric eigenproblem resident in shared memory: V[n][n] (element (i, j) at i + j * LD) holds the symmetric matrix on
+// entry and the eigenvectors (columns) on exit, d the eigenvalues.  Called by every thread of a block of EIG_THREADS
+// threads; returns non-zero if the QL iteration did not converge.
+__device__ __forceinline__ int sym_eig_smem(double *V, const int LD, const int n, double *d, double *e, double *cc, double *ss, double *red)
+{
+    sym_tridiag_smem(V, LD, n, d, e, red);
+    return sym_ql_smem(V, LD, n, d, e, cc, ss, red);
 }
 
 __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunch M, const int LD)
@@ -359,7 +391,15 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
     }
     __syncthreads();
 
+#ifdef HDB_MODAL_CLOCKS
+    long long tk0 = clock64();
+    if (tid == 0 && blockIdx.x == 0) printf("[modal] build B\n");
+#endif
     const int failed = sym_eig_smem(V, LD, n, d, e, cc, ss, red);
+#ifdef HDB_MODAL_CLOCKS
+    if (tid == 0 && blockIdx.x == 0) printf("[modal] eig total %lld\n", clock64() - tk0);
+    tk0 = clock64();
+#endif
 
     // ---- order: ascending Hz = descending lambda (stable on ties) ----
     for (int j = tid; j < n; j += EIG_THREADS) {
@@ -421,10 +461,18 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
         }
     }
     __syncthreads();
+#ifdef HDB_MODAL_CLOCKS
+    if (tid == 0 && blockIdx.x == 0) printf("[modal] shapes gemm %lld\n", clock64() - tk0);
+    tk0 = clock64();
+#endif
     for (int idx = tid; idx < nOut * M.dof; idx += EIG_THREADS) {
         const int r = idx / M.dof;
         out[idx] = out[idx] / sqrt(nrm[r]);
     }
+#ifdef HDB_MODAL_CLOCKS
+    __syncthreads();
+    if (tid == 0 && blockIdx.x == 0) printf("[modal] normalise %lld\n", clock64() - tk0);
+#endif
 #undef VV
 }
 
@@ -453,6 +501,405 @@ cudaError_t launch_modal_eigen(const ModalLaunch &M, int smemOptin, cudaStream_t
         if (e != cudaSuccess) return e;
     }
     k_modal_eigen<<<M.nModels, EIG_THREADS, smem, st>>>(M, LD);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// The split Modal pipeline (what hdb_modal_batch runs when its scratch fits): three kernels instead of k_modal_eigen.
+//
+//   k_modal_tridiag    CTA per model: B = M^1/2 (K^-1)_SS M^1/2, tred2, Q accumulated; Q, d, e -> global scratch.
+//   k_modal_ql_chain   the scalar QL recurrence of every model, ONE WARP per model and all models of the batch at the
+//                      same time.  The recurrence is a chain of dependent square roots (about 220 cycles a rotation,
+//                      3 M cycles a model at n = 130) that nothing inside a model can shorten; inside k_modal_eigen it
+//                      kept a whole SM (the shared-memory resident Q) waiting.  Here the chains of seven models share an
+//                      SM, and their rotations are logged to global memory: (cos, sin) pairs, one header per sweep.
+//   k_modal_finish     CTA per model: Q back into shared memory, the logged rotations applied row by row (a row is
+//                      independent of every other row: no barrier at all), frequencies, then the shapes as one
+//                      FP64 tensor-core contraction (mma.sync m8n8k4, SASS DMMA): out[r][g] = sum_j y_r[j] sol[j][g]
+//                      with the solution rows streamed through shared memory exactly once (cp.async, double buffered),
+//                      squared norms accumulated on the way, and a last in-place scaling pass over the L2-hot result.
+// ------------------------------------------------------------------------------------------------
+constexpr int CH_WARPS = 4; // models per block of the chain kernel
+
+__global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_tridiag(const ModalLaunch M, const int LD)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int n = M.s, tid = threadIdx.x, model = blockIdx.x;
+    double *V = sm;
+    double *d = V + (size_t)LD * n, *e = d + n, *red = e + n;
+#define VV(i, j) V[(i) + (size_t)(j) * LD]
+    const double *sol = M.sol + (size_t)model * n * M.dof;
+    const double *ms = M.msqrt + (size_t)model * n;
+    for (int idx = tid; idx < n * n; idx += EIG_THREADS) { // B, symmetrised
+        const int i = idx % n, j = idx / n;
+        const double bij = ms[i] * sol[(size_t)j * M.dof + M.massDof[i]];
+        const double bji = ms[j] * sol[(size_t)i * M.dof + M.massDof[j]];
+        VV(i, j) = 0.5 * (bij + bji);
+    }
+    __syncthreads();
+    sym_tridiag_smem(V, LD, n, d, e, red);
+    double *q = M.qScratch + (size_t)model * n * LD;
+    for (int idx = tid; idx < n * LD; idx += EIG_THREADS) q[idx] = V[idx];
+    double *de = M.deScratch + (size_t)model * 2 * n;
+    for (int j = tid; j < n; j += EIG_THREADS) {
+        de[j] = d[j];
+        de[n + j] = e[j];
+    }
+#undef VV
+}
+
+__global__ void __launch_bounds__(CH_WARPS * 32) k_modal_ql_chain(const ModalLaunch M)
+{
+    extern __shared__ __align__(16) double sm[]; // [CH_WARPS][2n]
+    const int n = M.s, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int model = blockIdx.x * CH_WARPS + w;
+    if (model >= M.nModels) return;
+    double *d = sm + (size_t)w * 2 * n, *e = d + n;
+    const double *de = M.deScratch + (size_t)model * 2 * n;
+    for (int j = lane; j < 2 * n; j += 32) d[j] = de[j];
+    __syncwarp();
+    double2 *rot = M.rotLog + (size_t)model * M.rotCap;
+    int4 *hdr = M.rotHdr + (size_t)model * M.rotMaxSweeps;
+    const double eps = 2.220446049250313e-16;
+    double f = 0.0, tst1 = 0.0;
+    int sweep = 0, off = 0, fail = 0;
+    for (int l = 0; l < n && !fail; l++) {
+        int m = l;
+        if (lane == 0) {
+            tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
+            while (m < n) {
+                if (fabs(e[m]) <= eps * tst1) break;
+                m++;
+            }
+            if (m >= n) m = n - 1;
+        }
+        m = __shfl_sync(0xffffffffu, m, 0);
+        if (m > l) {
+            int iter = 0, more = 0;
+            do {
+                iter++;
+                if (sweep >= M.rotMaxSweeps || off + (m - l) > M.rotCap) { fail = 1; break; } // uniform: the log is full
+                double g = 0.0, p = 0.0, r = 0.0, dl1 = 0.0, h = 0.0;
+                if (lane == 0) {
+                    g = d[l];
+                    p = (d[l + 1] - g) / (2.0 * e[l]);
+                    r = hypot(p, 1.0);
+                    if (p < 0) r = -r;
+                    d[l] = e[l] / (p + r);
+                    d[l + 1] = e[l] * (p + r);
+                    dl1 = d[l + 1];
+                    h = g - d[l];
+                }
+                h = __shfl_sync(0xffffffffu, h, 0);
+                for (int i = l + 2 + lane; i < n; i += 32) d[i] -= h;
+                __syncwarp();
+                if (lane == 0) {
+                    f += h;
+                    p = d[m];
+                    double c = 1.0, c2 = c, c3 = c;
+                    const double el1 = e[l + 1];
+                    double s = 0.0, s2 = 0.0;
+                    const unsigned dA = (unsigned)__cvta_generic_to_shared(d), eA = (unsigned)__cvta_generic_to_shared(e);
+                    double2 *rs = rot + off + (m - 1); // rotation of step i at rs[-i]: the log is written in the order it is applied
+                    double eiN, diN; // e[i], d[i] of the next step, loaded one step ahead
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(eiN) : "r"(eA + 8u * (unsigned)(m - 1)));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(diN) : "r"(dA + 8u * (unsigned)(m - 1)));
+                    for (int i = m - 1; i >= l; i--) {
+                        c3 = c2;
+                        c2 = c;
+                        s2 = s;
+                        const double ei = eiN, di = diN;
+                        if (i > l) {
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(eiN) : "r"(eA + 8u * (unsigned)(i - 1)));
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(diN) : "r"(dA + 8u * (unsigned)(i - 1)));
+                        }
+                        g = c * ei;
+                        h = c * p;
+                        // one reciprocal square root instead of a square root followed by a division, and the next p
+                        // computed off that chain (the tridiagonal entries are O(lambda): no overflow guard needed)
+                        const double q2 = fma(p, p, ei * ei);
+                        const double tp = fma(p, di, -ei * g); // = r * (c d[i] - s g)
+                        const double rinv = rsqrt(q2);
+                        r = q2 * rinv;
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(eA + 8u * (unsigned)(i + 1)), "d"(s * r) : "memory");
+                        s = ei * rinv;
+                        c = p * rinv;
+                        p = tp * rinv;
+                        asm volatile("st.shared.f64 [%0], %1;" ::"r"(dA + 8u * (unsigned)(i + 1)), "d"(h + s * (c * g + s * di)) : "memory");
+                        __stcg(rs - i, make_double2(c, s));
+                    }
+                    p = -s * s2 * c3 * el1 * e[l] / dl1;
+                    e[l] = s * p;
+                    d[l] = c * p;
+                    more = fabs(e[l]) > eps * tst1;
+                    if (iter > 60) {
+                        more = 0;
+                        fail = 1;
+                    }
+                    hdr[sweep] = make_int4(l, m, off, 0);
+                }
+                off += m - l;
+                sweep++;
+                more = __shfl_sync(0xffffffffu, more, 0);
+                fail = __shfl_sync(0xffffffffu, fail, 0);
+            } while (more);
+        }
+        if (lane == 0) {
+            d[l] = d[l] + f;
+            e[l] = 0.0;
+        }
+        __syncwarp();
+    }
+    double *dOut = M.deScratch + (size_t)model * 2 * n; // eigenvalues replace the diagonal
+    for (int j = lane; j < n; j += 32) dOut[j] = d[j];
+    if (lane == 0) M.rotSweeps[model] = fail ? -1 : sweep;
+}
+
+__device__ __forceinline__ void cp_async16(unsigned smem, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(g) : "memory");
+}
+__device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, const double a, const double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int SH_NT = 32;     // columns (DOFs) of one streamed tile of the solution rows
+constexpr int SH_LDB = 36;    // its leading dimension in shared memory: 4 mod 16, fragment loads hit distinct banks
+constexpr int SH_WARPS = EIG_THREADS / 32;
+
+__global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_finish(const ModalLaunch M, const int LD)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int n = M.s, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, model = blockIdx.x;
+    const int KP = (n + 3) & ~3; // contraction length padded to the k = 4 of the tensor-core shape
+    double *V = sm;                                  // [KP rows used][n] element (i, j) at i + j * LD; rows n..KP-1 are zero
+    double *d = V + (size_t)LD * n;                  // [n] eigenvalues
+    double *nrm = d + n;                             // [n] squared norms of the raw shapes
+    double *tile = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(nrm + n) + 15) & ~(uintptr_t)15); // [2][KP][SH_LDB] streamed solution rows (16-byte aligned: cp.async)
+    int *order = reinterpret_cast<int *>(tile + (size_t)2 * KP * SH_LDB); // [n]
+#define VV(i, j) V[(i) + (size_t)(j) * LD]
+    const double *sol = M.sol + (size_t)model * n * M.dof;
+    {
+        const double *q = M.qScratch + (size_t)model * n * LD;
+        for (int idx = tid; idx < n * LD; idx += EIG_THREADS) V[idx] = q[idx];
+        const double *de = M.deScratch + (size_t)model * 2 * n;
+        for (int j = tid; j < n; j += EIG_THREADS) {
+            d[j] = de[j];
+            nrm[j] = 0.0;
+        }
+    }
+    __syncthreads();
+    // ---- the logged QL rotations, applied to the rows of Q: thread = row.  The log is consumed front to back; it streams
+    //      through shared memory in chunks (cp.async by all threads, double buffered, in the region the shape tiles use
+    //      later), the sweep headers sit in shared memory too.  One barrier per chunk, none per sweep. ----
+    const int nSweeps = M.rotSweeps[model];
+    {
+        const double2 *rot = M.rotLog + (size_t)model * M.rotCap;
+        const int4 *hdrG = M.rotHdr + (size_t)model * M.rotMaxSweeps;
+        int4 *hdr = reinterpret_cast<int4 *>(tile);                                  // [nSweeps] (at most rotMaxSweeps)
+        const int hdrDoubles = 2 * M.rotMaxSweeps;
+        double2 *ring = reinterpret_cast<double2 *>(tile + hdrDoubles);              // [2][RC]
+        const int RC = (int)((((size_t)2 * KP * SH_LDB - hdrDoubles) / 4) & ~(size_t)3); // rotations per chunk
+        const unsigned ringA = (unsigned)__cvta_generic_to_shared(ring);
+        const int ns = nSweeps > 0 ? nSweeps : 0;
+        for (int k = tid; k < ns; k += EIG_THREADS) hdr[k] = hdrG[k];
+        __syncthreads();
+        const int total = ns > 0 ? hdr[ns - 1].z + (hdr[ns - 1].y - hdr[ns - 1].x) : 0;
+        const int nChunks = (total + RC - 1) / RC;
+        auto fetch = [&](int c) {
+            const int p0 = c * RC, cnt = min(RC, total - p0);
+            for (int q = tid; q < cnt; q += EIG_THREADS) cp_async16(ringA + (unsigned)(((c & 1) * RC + q) * 16), rot + p0 + q);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (nChunks > 0) fetch(0);
+        // walk state of this thread's row
+        const bool mine = tid < n;
+        double *vr = V + (mine ? tid : 0);
+        int k = 0, l = 0, i = -1;
+        double hk = 0.0;
+        if (ns > 0) {
+            const int4 h = hdr[0];
+            l = h.x;
+            i = h.y - 1;
+            hk = vr[(size_t)h.y * LD];
+        }
+        for (int c = 0; c < nChunks; c++) {
+            if (c + 1 < nChunks) {
+                fetch(c + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads(); // chunk c has landed for everybody
+            if (mine) {
+                const double2 *rc = ring + (size_t)(c & 1) * RC;
+                int left = min(RC, total - c * RC);
+                while (left > 0) {
+                    int run = min(left, i - l + 1);
+                    left -= run;
+                    for (; run >= 4; run -= 4, i -= 4, rc += 4) { // four steps at a time: their loads are issued before the first dependent store
+                        const double2 r0 = rc[0], r1 = rc[1], r2 = rc[2], r3 = rc[3];
+                        const double v0 = vr[(size_t)i * LD], v1 = vr[(size_t)(i - 1) * LD], v2 = vr[(size_t)(i - 2) * LD], v3 = vr[(size_t)(i - 3) * LD];
+                        vr[(size_t)(i + 1) * LD] = fma(r0.y, v0, r0.x * hk);
+                        hk = fma(r0.x, v0, -r0.y * hk);
+                        vr[(size_t)i * LD] = fma(r1.y, v1, r1.x * hk);
+                        hk = fma(r1.x, v1, -r1.y * hk);
+                        vr[(size_t)(i - 1) * LD] = fma(r2.y, v2, r2.x * hk);
+                        hk = fma(r2.x, v2, -r2.y * hk);
+                        vr[(size_t)(i - 2) * LD] = fma(r3.y, v3, r3.x * hk);
+                        hk = fma(r3.x, v3, -r3.y * hk);
+                    }
+                    for (; run > 0; run--, i--, rc++) {
+                        const double2 r0 = rc[0];
+                        const double v0 = vr[(size_t)i * LD];
+                        vr[(size_t)(i + 1) * LD] = fma(r0.y, v0, r0.x * hk);
+                        hk = fma(r0.x, v0, -r0.y * hk);
+                    }
+                    if (i < l) { // sweep finished: next one
+                        vr[(size_t)l * LD] = hk;
+                        if (++k < ns) {
+                            const int4 h = hdr[k];
+                            l = h.x;
+                            i = h.y - 1;
+                            hk = vr[(size_t)h.y * LD];
+                        }
+                    }
+                }
+            }
+            __syncthreads(); // everybody is done with this buffer before chunk c + 2 overwrites it
+        }
+    }
+    __syncthreads();
+    // ---- order: ascending Hz = descending lambda (stable on ties) ----
+    for (int j = tid; j < n; j += EIG_THREADS) {
+        const double lj = fabs(d[j]);
+        int rank = 0;
+        for (int i = 0; i < n; i++) {
+            const double li = fabs(d[i]);
+            if (li > lj || (li == lj && i < j)) rank++;
+        }
+        order[rank] = j;
+    }
+    __syncthreads();
+    const int nOut = min(n, M.maxModes);
+    for (int r = tid; r < nOut; r += EIG_THREADS) {
+        const double val = fabs(d[order[r]]);
+        M.hz[(size_t)model * M.maxModes + r] = 1. / (sqrt(val) * 2.0 * M_PI); // model.go:830
+    }
+    if (tid == 0) {
+        M.nModes[model] = nOut;
+        if (nSweeps < 0 && M.status[model] == HDB_STATUS_OK) M.status[model] = HDB_STATUS_EIGEN;
+    }
+    if (!M.shapes) return;
+
+    // ---- shapes: out[r][g] = sum_j V(j, order[r]) sol[j][g], on the FP64 tensor cores ----
+    // A fragment (8 modes x 4 j): lane holds A[lane / 4][lane % 4]; B fragment (4 j x 8 DOFs): lane holds B[lane % 4][lane / 4];
+    // C fragment (8 x 8): lane holds C[lane / 4][2 (lane % 4) + {0, 1}].  A warp owns mode tiles warp, warp + 8, ... and all
+    // four 8-DOF tiles of the streamed 32-DOF tile.
+    const int nMT = (nOut + 7) / 8, nGT = (M.dof + SH_NT - 1) / SH_NT;
+    const unsigned tileA = (unsigned)__cvta_generic_to_shared(tile);
+    auto stage = [&](int gt, int buf) { // solution rows j = 0..n-1, DOFs [gt * 32, gt * 32 + 32) -> tile[buf]; out-of-range = 0
+        const int g0 = gt * SH_NT;
+        const bool vec = ((M.dof & 1) == 0) && ((reinterpret_cast<uintptr_t>(sol) & 15) == 0);
+        for (int idx = tid; idx < KP * (SH_NT / 2); idx += EIG_THREADS) {
+            const int j = idx / (SH_NT / 2), c2 = (idx - j * (SH_NT / 2)) * 2, g = g0 + c2;
+            double *dst = tile + ((size_t)buf * KP + j) * SH_LDB + c2;
+            if (j < n && g + 1 < M.dof && vec) cp_async16(tileA + (unsigned)(((size_t)buf * KP + j) * SH_LDB + c2) * 8u, sol + (size_t)j * M.dof + g);
+            else {
+                dst[0] = (j < n && g < M.dof) ? sol[(size_t)j * M.dof + g] : 0.0;
+                dst[1] = (j < n && g + 1 < M.dof) ? sol[(size_t)j * M.dof + g + 1] : 0.0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double *out = M.shapes + (size_t)model * M.maxModes * M.dof;
+    stage(0, 0);
+    for (int gt = 0; gt < nGT; gt++) {
+        if (gt + 1 < nGT) {
+            stage(gt + 1, (gt + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const double *tb = tile + (size_t)(gt & 1) * KP * SH_LDB;
+        const int g0 = gt * SH_NT;
+        for (int mt = warp; mt < nMT; mt += SH_WARPS) {
+            const int rA = mt * 8 + (lane >> 2);                          // this lane's mode row of the A fragment
+            const double *ya = V + (size_t)order[rA < nOut ? rA : nOut - 1] * LD + (lane & 3);
+            double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+            const double *bb = tb + (size_t)(lane & 3) * SH_LDB + (lane >> 2);
+#pragma unroll 2
+            for (int k0 = 0; k0 < KP; k0 += 4) {
+                const double a = (k0 + (lane & 3) < n) ? ya[k0] : 0.0;
+                const double *bk = bb + (size_t)k0 * SH_LDB;
+#pragma unroll
+                for (int t = 0; t < 4; t++) dmma8x8x4(c[t][0], c[t][1], a, bk[8 * t]);
+            }
+            const int r = mt * 8 + (lane >> 2);
+            double sq = 0.0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int g = g0 + 8 * t + 2 * (lane & 3);
+                if (r < nOut) {
+                    if (g < M.dof) { out[(size_t)r * M.dof + g] = c[t][0]; sq = fma(c[t][0], c[t][0], sq); }
+                    if (g + 1 < M.dof) { out[(size_t)r * M.dof + g + 1] = c[t][1]; sq = fma(c[t][1], c[t][1], sq); }
+                }
+            }
+            sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+            if ((lane & 3) == 0 && r < nOut) nrm[r] += sq; // this warp alone owns mode tile mt: fixed order of additions
+        }
+        __syncthreads(); // the tile may be overwritten
+    }
+    // ---- unit 2-norm over all 3*nP entries (what Dgeev returns, model.go:836-841): the raw rows are still in L2 ----
+    for (int idx = tid; idx < nOut * M.dof; idx += EIG_THREADS) {
+        const int r = idx / M.dof;
+        out[idx] = out[idx] / sqrt(nrm[r]);
+    }
+#undef VV
+}
+
+static size_t finish_smem(int n, int &LD)
+{
+    LD = n | 1;
+    if ((LD & 3) == 1) LD += 2;
+    const int KP = (n + 3) & ~3;
+    if (LD < KP) LD = KP | 1;
+    return ((size_t)LD * n + 2 * (size_t)n + (size_t)2 * KP * SH_LDB) * sizeof(double) + (size_t)n * sizeof(int) + 80;
+}
+
+bool modal_split_fits(int n, int smemOptin)
+{
+    int LD;
+    return n >= 1 && finish_smem(n, LD) + 1024 <= (size_t)smemOptin;
+}
+
+void modal_split_scratch(int n, size_t &qDoubles, size_t &rotCap, size_t &maxSweeps)
+{
+    int LD;
+    finish_smem(n, LD);
+    qDoubles = (size_t)n * LD;
+    rotCap = (size_t)3 * n * n + 64;     // (cos, sin) pairs: QL needs about 1.6 sweeps of average length n / 2 per eigenvalue
+    maxSweeps = (size_t)8 * n + 8;
+}
+
+cudaError_t launch_modal_split(const ModalLaunch &M, int smemOptin, cudaStream_t st)
+{
+    if (M.nModels == 0) return cudaSuccess;
+    int LD;
+    const size_t smemF = finish_smem(M.s, LD);
+    const size_t smemT = ((size_t)LD * M.s + 2 * (size_t)M.s + EIG_THREADS / 32 + 8) * sizeof(double) + 64;
+    if (smemF + 1024 > (size_t)smemOptin) return cudaErrorInvalidConfiguration;
+    cudaError_t e;
+    if (smemT > 48 * 1024 && (e = cudaFuncSetAttribute(k_modal_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)) != cudaSuccess) return e;
+    if (smemF > 48 * 1024 && (e = cudaFuncSetAttribute(k_modal_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF)) != cudaSuccess) return e;
+    k_modal_tridiag<<<M.nModels, EIG_THREADS, smemT, st>>>(M, LD);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const size_t smemC = (size_t)CH_WARPS * 2 * M.s * sizeof(double);
+    if (smemC > 48 * 1024 && (e = cudaFuncSetAttribute(k_modal_ql_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC)) != cudaSuccess) return e;
+    k_modal_ql_chain<<<(M.nModels + CH_WARPS - 1) / CH_WARPS, CH_WARPS * 32, smemC, st>>>(M);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    k_modal_finish<<<M.nModels, EIG_THREADS, smemF, st>>>(M, LD);
     return cudaGetLastError();
 }
 

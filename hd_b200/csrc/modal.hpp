@@ -38,6 +38,13 @@ struct ModalLaunch {
     double *hz;               // device [nModels][maxModes]
     double *shapes;           // device [nModels][maxModes][dof] or NULL
     int32_t *status;          // device [nModels]
+    // scratch of the split pipeline (launch_modal_split), NULL for the single-kernel path
+    double *qScratch;         // device [nModels][s * LD] the orthogonal Q of the tridiagonalisation
+    double *deScratch;        // device [nModels][2 s] diagonal | subdiagonal of T; the eigenvalues replace the diagonal
+    double2 *rotLog;          // device [nModels][rotCap] (cos, sin) of every QL rotation, sweep after sweep
+    int4 *rotHdr;             // device [nModels][rotMaxSweeps] {l, m, offset into rotLog, 0} of every sweep
+    int32_t *rotSweeps;       // device [nModels] number of sweeps, -1 = QL did not converge / log full
+    int rotCap, rotMaxSweeps;
 };
 
 // ---- linear buckling (model.go:491-601): eigenvalues of (K^-1)_ff G_ff per (model, load case) ----
@@ -63,5 +70,9 @@ cudaError_t launch_modal_loads(const ModalLaunch &M, cudaStream_t st);
 // returns cudaErrorInvalidConfiguration when s is too large for the shared-memory resident eigen solver
 cudaError_t launch_modal_eigen(const ModalLaunch &M, int smemOptin, cudaStream_t st);
 int modal_max_s(int smemOptin);
+// the split pipeline: tridiagonalisation | QL recurrences of all models at once | rotations + tensor-core shapes
+bool modal_split_fits(int n, int smemOptin);
+void modal_split_scratch(int n, size_t &qDoubles, size_t &rotCap, size_t &maxSweeps);
+cudaError_t launch_modal_split(const ModalLaunch &M, int smemOptin, cudaStream_t st);
 
 } // namespace hdb
