@@ -672,11 +672,18 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_finish(const ModalLaun
 {
     extern __shared__ __align__(16) double sm[];
     const int n = M.s, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, model = blockIdx.x;
+#ifdef HDB_MODAL_CLOCKS
+    long long tf0 = clock64();
+#define FSTAMP(name) do { __syncthreads(); if (tid == 0 && blockIdx.x == 0) { long long t_ = clock64(); printf("[finish] %-12s %lld\n", name, t_ - tf0); tf0 = t_; } } while (0)
+#else
+#define FSTAMP(name) do {} while (0)
+#endif
     const int KP = (n + 3) & ~3; // contraction length padded to the k = 4 of the tensor-core shape
     double *V = sm;                                  // [KP rows used][n] element (i, j) at i + j * LD; rows n..KP-1 are zero
     double *d = V + (size_t)LD * n;                  // [n] eigenvalues
     double *nrm = d + n;                             // [n] squared norms of the raw shapes
-    double *tile = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(nrm + n) + 15) & ~(uintptr_t)15); // [2][KP][SH_LDB] streamed solution rows (16-byte aligned: cp.async)
+    double *tile = nrm + n + (((size_t)LD * n) & 1);  // [2][KP][SH_LDB] streamed solution rows, 16-byte aligned for cp.async (kept as
+                                                     // pointer arithmetic on sm: a cast through an integer would turn every access generic)
     int *order = reinterpret_cast<int *>(tile + (size_t)2 * KP * SH_LDB); // [n]
 #define VV(i, j) V[(i) + (size_t)(j) * LD]
     const double *sol = M.sol + (size_t)model * n * M.dof;
@@ -690,6 +697,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_finish(const ModalLaun
         }
     }
     __syncthreads();
+    FSTAMP("load Q");
     // ---- the logged QL rotations, applied to the rows of Q: thread = row.  The log is consumed front to back; it streams
     //      through shared memory in chunks (cp.async by all threads, double buffered, in the region the shape tiles use
     //      later), the sweep headers sit in shared memory too.  One barrier per chunk, none per sweep. ----
@@ -740,20 +748,23 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_finish(const ModalLaun
                     for (; run >= 4; run -= 4, i -= 4, rc += 4) { // four steps at a time: their loads are issued before the first dependent store
                         const double2 r0 = rc[0], r1 = rc[1], r2 = rc[2], r3 = rc[3];
                         const double v0 = vr[(size_t)i * LD], v1 = vr[(size_t)(i - 1) * LD], v2 = vr[(size_t)(i - 2) * LD], v3 = vr[(size_t)(i - 3) * LD];
-                        vr[(size_t)(i + 1) * LD] = fma(r0.y, v0, r0.x * hk);
-                        hk = fma(r0.x, v0, -r0.y * hk);
-                        vr[(size_t)i * LD] = fma(r1.y, v1, r1.x * hk);
-                        hk = fma(r1.x, v1, -r1.y * hk);
-                        vr[(size_t)(i - 1) * LD] = fma(r2.y, v2, r2.x * hk);
-                        hk = fma(r2.x, v2, -r2.y * hk);
-                        vr[(size_t)(i - 2) * LD] = fma(r3.y, v3, r3.x * hk);
-                        hk = fma(r3.x, v3, -r3.y * hk);
+                        // one dependent multiply-add per step: the products with the row's old entries do not wait for hk
+                        const double sv0 = r0.y * v0, cv0 = r0.x * v0, sv1 = r1.y * v1, cv1 = r1.x * v1;
+                        const double sv2 = r2.y * v2, cv2 = r2.x * v2, sv3 = r3.y * v3, cv3 = r3.x * v3;
+                        const double h1 = fma(-r0.y, hk, cv0);
+                        vr[(size_t)(i + 1) * LD] = fma(r0.x, hk, sv0);
+                        const double h2 = fma(-r1.y, h1, cv1);
+                        vr[(size_t)i * LD] = fma(r1.x, h1, sv1);
+                        const double h3 = fma(-r2.y, h2, cv2);
+                        vr[(size_t)(i - 1) * LD] = fma(r2.x, h2, sv2);
+                        vr[(size_t)(i - 2) * LD] = fma(r3.x, h3, sv3);
+                        hk = fma(-r3.y, h3, cv3);
                     }
                     for (; run > 0; run--, i--, rc++) {
                         const double2 r0 = rc[0];
                         const double v0 = vr[(size_t)i * LD];
-                        vr[(size_t)(i + 1) * LD] = fma(r0.y, v0, r0.x * hk);
-                        hk = fma(r0.x, v0, -r0.y * hk);
+                        vr[(size_t)(i + 1) * LD] = fma(r0.x, hk, r0.y * v0);
+                        hk = fma(-r0.y, hk, r0.x * v0);
                     }
                     if (i < l) { // sweep finished: next one
                         vr[(size_t)l * LD] = hk;
@@ -770,6 +781,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_finish(const ModalLaun
         }
     }
     __syncthreads();
+    FSTAMP("rotations");
     // ---- order: ascending Hz = descending lambda (stable on ties) ----
     for (int j = tid; j < n; j += EIG_THREADS) {
         const double lj = fabs(d[j]);
@@ -791,6 +803,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_finish(const ModalLaun
         if (nSweeps < 0 && M.status[model] == HDB_STATUS_OK) M.status[model] = HDB_STATUS_EIGEN;
     }
     if (!M.shapes) return;
+    FSTAMP("order, hz");
 
     // ---- shapes: out[r][g] = sum_j V(j, order[r]) sol[j][g], on the FP64 tensor cores ----
     // A fragment (8 modes x 4 j): lane holds A[lane / 4][lane % 4]; B fragment (4 j x 8 DOFs): lane holds B[lane % 4][lane / 4];
@@ -851,11 +864,16 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_finish(const ModalLaun
         }
         __syncthreads(); // the tile may be overwritten
     }
+    FSTAMP("shapes");
     // ---- unit 2-norm over all 3*nP entries (what Dgeev returns, model.go:836-841): the raw rows are still in L2 ----
-    for (int idx = tid; idx < nOut * M.dof; idx += EIG_THREADS) {
-        const int r = idx / M.dof;
-        out[idx] = out[idx] / sqrt(nrm[r]);
+    for (int r = tid; r < nOut; r += EIG_THREADS) nrm[r] = 1.0 / sqrt(nrm[r]);
+    __syncthreads();
+    for (int r = warp; r < nOut; r += SH_WARPS) { // a warp per mode row: no division per element
+        const double sc = nrm[r];
+        double *row = out + (size_t)r * M.dof;
+        for (int g = lane; g < M.dof; g += 32) row[g] *= sc;
     }
+    FSTAMP("normalise");
 #undef VV
 }
 
