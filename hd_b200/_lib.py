@@ -27,6 +27,8 @@ SYMBOLS = [
     "hdb_buckling_max_free", "hdb_buckling_batch", "hdb_buckling_batch_dev", "hdb_uniform_loads_dev",
     "hdb_host_alloc", "hdb_host_free", "hdb_set_profiling", "hdb_last_kernel_ms", "hdb_launch_count",
     "hdb_device_count", "hdb_error_string", "hdb_last_error_detail", "hdb_version",
+    "hdb_multi_create", "hdb_multi_destroy", "hdb_multi_device_count", "hdb_multi_shard", "hdb_multi_topology",
+    "hdb_multi_static_batch", "hdb_multi_static_batch_dev", "hdb_multi_synchronize", "hdb_multi_gather_summary",
 ]
 
 
@@ -95,6 +97,17 @@ def lib():
         L.hdb_set_profiling.argtypes = [vp, i32]
         L.hdb_last_kernel_ms.argtypes = [vp, vp, i32]
         L.hdb_launch_count.restype = i64
+        L.hdb_multi_create.argtypes = [i32, vp, i32, vp, vp, vp, C.POINTER(Options), i32, vp, C.POINTER(vp)]
+        L.hdb_multi_destroy.argtypes = [vp]
+        L.hdb_multi_destroy.restype = None
+        L.hdb_multi_device_count.argtypes = [vp]
+        L.hdb_multi_shard.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.hdb_multi_topology.argtypes = [vp, i32]
+        L.hdb_multi_topology.restype = vp
+        L.hdb_multi_static_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
+        L.hdb_multi_static_batch_dev.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.hdb_multi_synchronize.argtypes = [vp]
+        L.hdb_multi_gather_summary.argtypes = [vp, vp, vp, vp, i32, vp]
         L.hdb_error_string.argtypes = [i32]
         L.hdb_error_string.restype = C.c_char_p
         L.hdb_last_error_detail.restype = C.c_char_p
@@ -336,3 +349,85 @@ def pinned_empty(shape, dtype=np.float64):
                 pass
 
     return arr, _Owner(p)
+
+
+class MultiTopology:
+    """One process, several GPUs of one box (hdb_multi_*): contiguous model ranges per device, no data-path collective."""
+
+    def __init__(self, points, beamN, sections, pins, supports, devices, ordering=0):
+        L = lib()
+        self.points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
+        self.beams = beams_array(beamN, sections)
+        self.nP, self.nB = self.points.shape[0], self.beams.shape[0]
+        self.dof = 3 * self.nP
+        self.pins = None
+        if pins is not None and len(pins):
+            self.pins = np.ascontiguousarray(pins, dtype=np.uint8).reshape(self.nB, 6)
+        self.supports = np.ascontiguousarray(supports, dtype=np.uint8).reshape(self.nP, 3)
+        self.devices = np.ascontiguousarray(devices, dtype=np.int32)
+        opts = Options(device=-1, ordering=ordering)
+        h = C.c_void_p()
+        check(L.hdb_multi_create(self.nP, _np_ptr(self.points), self.nB, _np_ptr(self.beams), _np_ptr(self.pins),
+                                 _np_ptr(self.supports), C.byref(opts), len(self.devices), _np_ptr(self.devices), C.byref(h)),
+              "hdb_multi_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().hdb_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard(self, n_models, d):
+        a, b = C.c_int32(), C.c_int32()
+        check(lib().hdb_multi_shard(self._h, n_models, d, C.byref(a), C.byref(b)), "hdb_multi_shard")
+        return a.value, b.value
+
+    def static_batch(self, sections, loads, want=("disp", "forces", "react")):
+        """Host numpy in, host numpy out; every device works on its contiguous range of models."""
+        sections = np.ascontiguousarray(sections, dtype=np.float64).reshape(-1, self.nB, 3)
+        nM = sections.shape[0]
+        loads = np.ascontiguousarray(loads, dtype=np.float64).reshape(nM, -1, self.dof)
+        nLC = loads.shape[1]
+        disp = np.empty((nM, nLC, self.nP, 3)) if "disp" in want else None
+        forces = np.empty((nM, nLC, self.nB, 6)) if "forces" in want else None
+        react = np.empty((nM, nLC, self.nP, 3)) if "react" in want else None
+        status = np.zeros(nM, dtype=np.int32)
+        fail = np.zeros(nM, dtype=np.int32)
+        check(lib().hdb_multi_static_batch(self._h, nM, _np_ptr(sections), nLC, _np_ptr(loads), _np_ptr(disp), _np_ptr(forces),
+                                           _np_ptr(react), _np_ptr(status), _np_ptr(fail)), "hdb_multi_static_batch")
+        return status, fail, disp, forces, react
+
+    @staticmethod
+    def _ptr_array(items):
+        a = (C.c_void_p * len(items))()
+        for i, x in enumerate(items):
+            p = _ptr(x)
+            a[i] = p.value if p is not None else None
+        return a
+
+    def static_batch_dev(self, counts, sections, nLC, loads, disp, forces, react, status, fail, streams=None):
+        """Resident shards: lists (one entry per device) of device tensors / addresses; asynchronous."""
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        arr = lambda xs: None if xs is None else self._ptr_array(xs)
+        keep = [arr(x) for x in (sections, loads, disp, forces, react, status, fail)]
+        st = None if streams is None else (C.c_void_p * len(streams))(*streams)
+        check(lib().hdb_multi_static_batch_dev(self._h, _np_ptr(counts), keep[0], nLC, keep[1], keep[2], keep[3], keep[4], keep[5],
+                                               keep[6], st), "hdb_multi_static_batch_dev")
+
+    def synchronize(self):
+        check(lib().hdb_multi_synchronize(self._h), "hdb_multi_synchronize")
+
+    def gather_summary(self, counts, status, disp, nLC):
+        """NCCL all-gather of the per-shard reduced results: array [nDev][4] = failed, max |d|, models, 0."""
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        out = np.zeros((len(self.devices), 4))
+        check(lib().hdb_multi_gather_summary(self._h, _np_ptr(counts), self._ptr_array(status),
+                                             None if disp is None else self._ptr_array(disp), nLC, _np_ptr(out)),
+              "hdb_multi_gather_summary")
+        return out

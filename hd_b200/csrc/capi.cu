@@ -15,6 +15,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include "device_topo.hpp"
 #include "element.cuh"
@@ -40,6 +41,12 @@ void count_launch(int n) { g_launches += n; }
             return (e__ == cudaErrorMemoryAllocation) ? HDB_ERR_NOMEM : HDB_ERR_CUDA;          \
         }                                                                                     \
     } while (0)
+
+// NVTX range around a phase of a C-ABI call: shows up in Nsight Systems timelines, costs nothing without a tool
+struct Nvtx {
+    explicit Nvtx(const char *name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+};
 
 struct HostChunk {
     double *sec = nullptr, *loads = nullptr, *disp = nullptr, *forces = nullptr, *react = nullptr;
@@ -418,6 +425,7 @@ int hdb_topology_create(int32_t nP, const double *points, int32_t nB, const hdb_
     if (!t) return HDB_ERR_NOMEM;
     std::string detail;
     const int ordering = opts ? opts->ordering : 0;
+    Nvtx nv("hdb_topology_create (symbolic phase)");
     int rc = build_symbolic(nP, points, nB, beams, pins, supports, ordering == 2 ? 0 : ordering, t->S, detail);
     if (rc == HDB_OK && ordering == 2) { // automatic: keep the ordering whose factor is smaller
         Symbolic rcm;
@@ -703,12 +711,14 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
             count_launch(1);
         }
         {
+            Nvtx nv("hdb:assemble");
             ProfScope pr(t, KIND_ASSEMBLE, ps);
             CUDA_TRY(launch_assemble(t->D, L, ps));
         }
         count_launch(1);
         if (!solve) continue;
         {
+            Nvtx nv("hdb:factor");
             ProfScope pr(t, KIND_FACTOR, ps);
             CUDA_TRY(launch_factor(t->D, L, ps));
         }
@@ -717,6 +727,7 @@ static int static_enqueue(hdb_topology *t, int32_t nModels, const double *sectio
             CUDA_TRY(cudaStreamWaitEvent(st, t->evPrep[buf], 0));
         }
         {
+            Nvtx nv("hdb:solve+recover");
             ProfScope pr(t, KIND_SOLVE, st);
             CUDA_TRY(launch_solve_pipe(t->D, L, st));
         }
@@ -844,6 +855,7 @@ int hdb_static_batch(hdb_topology *t, int32_t nModels, const double *sections, i
         CUDA_TRY(cudaStreamSynchronize(nullptr));
         return HDB_OK;
     }
+    Nvtx nvAll("hdb_static_batch (host arrays)");
     // ---- host memory: chunked three-stage pipeline. copy-in, compute and copy-out each own a stream;
     //      NBUF device buffers rotate, so H2D(i+1), kernels(i) and D2H(i-1) overlap. ----
     const Symbolic &S = t->S;
@@ -870,6 +882,7 @@ int hdb_static_batch(hdb_topology *t, int32_t nModels, const double *sections, i
     for (int m0 = 0; m0 < nModels; m0 += t->chunkModels, it++) {
         HostChunk &c = t->chunk[it % NBUF];
         const int nm = std::min(t->chunkModels, nModels - m0);
+        Nvtx nvChunk("hdb:chunk H2D | kernels | D2H");
         if (it >= NBUF) CUDA_TRY(cudaStreamWaitEvent(t->sIn, c.evOut, 0)); // buffer is free again
         CUDA_TRY(cudaMemcpyAsync(c.sec, sections + (size_t)m0 * S.nB * 3, (size_t)nm * S.nB * 3 * sizeof(double),
                                  cudaMemcpyHostToDevice, t->sIn));
@@ -1036,6 +1049,7 @@ int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections
     if (rc != HDB_OK) return rc;
     if (nModels == 0) return HDB_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    Nvtx nvAll("hdb_modal_batch_dev");
     prof_reset(t);
     const Symbolic &S = t->S;
     std::vector<int32_t> dofs;
@@ -1140,6 +1154,7 @@ int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections
                             nullptr, nullptr, st, true);
         if (rc != HDB_OK) return rc;
         {
+            Nvtx nv("hdb:modal eigen");
             ProfScope ps(t, KIND_MODAL0 + 1, st);
             cudaError_t e = split ? launch_modal_split(M, t->smemOptin, st) : launch_modal_eigen(M, t->smemOptin, st);
             if (e == cudaErrorInvalidConfiguration) {

@@ -225,6 +225,35 @@ int hdb_uniform_loads_dev(hdb_topology *t, int32_t nModels, int32_t nLC, int32_t
                           const uint8_t *uproj, const double *q, int32_t nN, const int64_t *nodes, const double *f,
                           double *loads, void *stream);
 
+/* ---- several GPUs of one box from ONE process (a Go program is one process) ----
+ * hdb_multi_create runs the symbolic phase once per device (devices[nDev] = CUDA ordinals, NULL = 0 .. nDev-1; opts->device
+ * is ignored).  A batch is cut into contiguous model ranges, shard d = hdb_multi_shard(m, nModels, d) on device d; no
+ * collective sits on the data path (models are independent, model.go:926 has no cross-model state).
+ *   hdb_multi_static_batch       host arrays in the layout of hdb_static_batch; one host thread per device runs its range
+ *                                through that device's chunked H2D / kernels / D2H pipeline and writes straight into the
+ *                                caller's arrays.  Results are bit-identical to hdb_static_batch on one device.
+ *   hdb_multi_static_batch_dev   shards already resident: entry d of every pointer array is the array of shard d on
+ *                                device d (count[d] models); enqueues on streams[d] (NULL = default streams), no sync.
+ *   hdb_multi_gather_summary     the only NCCL use: all-gathers per-shard REDUCED results over NVLink — summary[nDev][4] =
+ *                                {failed models, largest |displacement| of the healthy ones, models, 0} — and returns them
+ *                                on the host.  Full results stay sharded: gathering them costs ~20x the solve.  NCCL is
+ *                                bound at run time (libnccl.so.2); HDB_ERR_UNSUPPORTED without it or with repeated devices. */
+typedef struct hdb_multi hdb_multi; /* opaque */
+int hdb_multi_create(int32_t nP, const double *points, int32_t nB, const hdb_beam *beams, const uint8_t *pins,
+                     const uint8_t *supports, const hdb_options *opts, int32_t nDev, const int32_t *devices, hdb_multi **out);
+void hdb_multi_destroy(hdb_multi *m);
+int32_t hdb_multi_device_count(const hdb_multi *m);
+int hdb_multi_shard(const hdb_multi *m, int32_t nModels, int32_t shard, int32_t *first, int32_t *count);
+hdb_topology *hdb_multi_topology(hdb_multi *m, int32_t shard); /* the per-device handle (owned by m) */
+int hdb_multi_static_batch(hdb_multi *m, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
+                           double *disp, double *forces, double *react, int32_t *status, int32_t *failCase);
+int hdb_multi_static_batch_dev(hdb_multi *m, const int32_t *count, const double *const *sections, int32_t nLC,
+                               const double *const *loads, double *const *disp, double *const *forces, double *const *react,
+                               int32_t *const *status, int32_t *const *failCase, void *const *streams);
+int hdb_multi_synchronize(hdb_multi *m);
+int hdb_multi_gather_summary(hdb_multi *m, const int32_t *count, const int32_t *const *status, const double *const *disp,
+                             int32_t nLC, double *summary);
+
 /* ---- pinned host memory for asynchronous batches (cgo: wrap with unsafe.Slice) ---- */
 int hdb_host_alloc(void **ptr, int64_t bytes);
 int hdb_host_free(void *ptr);
