@@ -11,7 +11,13 @@ the data path (models are independent); NCCL only reduces the status summary.
     python bench.py --impl reference --gpus N --steps K ...     CPU restatement of the reference's
                                                                algorithm on all host cores (Go is not
                                                                installable here)
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0).  Besides the contract's keys the line carries: `parity_max_rel` (eight strided models of
+the timed batch re-solved by the CPU oracle after the timed region), `e2e_uniform` (the same end-to-end step with the load
+cases built on the device from their line-load parameters, hdb_uniform_loads_dev: a third of the H2D bytes), `modal`
+(BASELINE.json config 4: 1024 x uniform_frame(64) modal cases, 130 modes each, device resident), `single` (configs 1 and 2:
+ONE model through Run, the launch-latency regime, next to the oracle and the reference's README figures) and, at N > 1,
+`single_process_multi_gpu` (hdb_multi_static_batch_dev driving all N GPUs from rank 0 alone).
+`--total-models T` fixes the whole job at T models (strong scaling, config 5: T = 65536) instead of 8192 per GPU.
 """
 from __future__ import annotations
 
@@ -150,6 +156,96 @@ def cpu_port(model, sections, loads, threads, literal=True):
     return dt
 
 
+def parity_check(model, sections, loads, d_disp, d_forces, d_react, n_check=8):
+    """Eight strided models of the timed batch against the CPU oracle: max |ours - oracle| / max |oracle| per array."""
+    from oracle import hd_oracle as oracle
+    M = sections.shape[0]
+    idx = np.unique(np.linspace(0, M - 1, n_check).astype(int))
+    fm = oracle.flatten_model(model)
+    ost, od, of, orr = oracle.static_batch(fm, sections[idx], loads[idx])
+    assert not ost.any()
+    worst = 0.0
+    for got, exp in ((d_disp, od), (d_forces, of), (d_react, orr)):
+        g = got[idx].cpu().numpy()
+        for k in range(len(idx)):
+            worst = max(worst, float(np.abs(g[k] - exp[k]).max() / np.abs(exp[k]).max()))
+    return worst, [int(i) for i in idx]
+
+
+def modal_leg(local_rank, steps=3, N=64, M=1024):
+    """BASELINE.json config 4 inside the same run (and therefore the same clock record): device-resident modal batch."""
+    import torch
+    from hd_b200 import _lib, frames
+    from hd_b200.model import flatten_model
+    fm = flatten_model(frames.uniform_frame(N))
+    sections = frames.uniform_frame_sections(N, 0, M)
+    massN, mass = frames.uniform_frame_masses(N, 0, M)
+    dev = torch.device("cuda", local_rank)
+    topo = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports, device=local_rank)
+    s = topo.modal_mode_count(massN)
+    d_sec, d_mass = torch.from_numpy(sections).to(dev), torch.from_numpy(mass).to(dev)
+    d_n = torch.zeros((M,), dtype=torch.int32, device=dev)
+    d_hz = torch.zeros((M, s), dtype=torch.float64, device=dev)
+    d_sh = torch.zeros((M, s, fm.nP, 3), dtype=torch.float64, device=dev)
+    d_st = torch.zeros((M,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        topo.modal_batch_dev(M, d_sec, massN, d_mass, s, d_n, d_hz, d_sh, d_st, stream)
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum().item()) == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        topo.modal_batch_dev(M, d_sec, massN, d_mass, s, d_n, d_hz, d_sh, d_st, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # parity of a few models against the oracle's non-symmetric solve of K^-1 M (frequencies, 1e-9)
+    from oracle import hd_oracle as oracle
+    ost, on, ohz, _ = oracle.modal_batch(oracle.flatten_model(frames.uniform_frame(N)), sections[:3], massN, mass[:3])
+    hz = d_hz[:3].cpu().numpy()
+    rel = float((np.abs(hz[:, :s] - ohz[:, :s]) / ohz[:, :s]).max())
+    nFree = topo.info.nFree
+    flops = 4 * nFree * 5 * s + 28 * s ** 3 / 3 + 2 * fm.dof * s * s + 3 * fm.dof * s  # SURVEY.md 8(d)
+    value = M / (ms * 1e-3)
+    topo.close()
+    del d_sh
+    return {"metric": "modal solves/s (130 modes, uniform_frame(64))", "value": value, "ms_per_step": ms, "models": M, "modes": s,
+            "hz_max_rel_vs_oracle": rel,
+            "fp64": {"algorithmic_mflop_per_solve": flops / 1e6, "achieved_tflops": value * flops / 1e12, "peak_tflops": 36.86,
+                     "peak_source": "tools/fp64_microbench.cu on this pool's B200 (DFMA)", "frac": value * flops / 1e12 / 36.86}}
+
+
+def single_leg():
+    """BASELINE.json configs 1 and 2: ONE model through Run (static, 20 cases, + its modal case): the launch-latency regime.
+    ms per Run for the GPU path (topology create + symbolic phase + kernels + copies every call, as hd.Run rebuilds everything
+    every call), the CPU oracle, and the reference's published figure where it has one."""
+    from hd_b200 import api, frames
+    from oracle import hd_oracle as oracle
+    out = {}
+
+    def time_it(fn, reps):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return 1e3 * (time.perf_counter() - t0) / reps
+
+    for name, ic, published in (("bench_cantilever(8)", 8, 0.807288), ("bench_cantilever(128)", 128, 105.636607)):
+        m, lcs, mcs = frames.bench_cantilever(ic)
+        gpu = time_it(lambda: api.Run(None, m.clone(), [type(l)(LoadNodes=l.LoadNodes) for l in lcs], [type(c)(ModalMasses=c.ModalMasses) for c in mcs]), 5)
+        cpu = time_it(lambda: oracle.run(m.clone(), lcs, mcs), 3 if ic > 32 else 10)
+        out[name] = {"gpu_ms_per_run": gpu, "oracle_ms_per_run": cpu, "go_readme_ms_per_run": published,
+                     "what": "hd.Run: LinearStatic over 20 load cases + one modal case (mod/split_test.go:93-124)"}
+    m = frames.uniform_frame(128)
+    lcs = frames.uniform_frame_load_cases(m, 128, 0, 20)
+    gpu = time_it(lambda: api.Run(None, m.clone(), [type(l)(LoadNodes=l.LoadNodes) for l in lcs], []), 5)
+    cpu = time_it(lambda: oracle.run(m.clone(), lcs, []), 3)
+    out["uniform_frame(128)"] = {"gpu_ms_per_run": gpu, "oracle_ms_per_run": cpu, "go_readme_ms_per_run": None,
+                                 "what": "hd.Run: LinearStatic over 20 load cases, one model (BASELINE.json config 2)"}
+    return out
+
+
 def modal_main(args, rank, local_rank, world):
     """Auxiliary line for BASELINE.json config 4: ModalCases on a batch of 1024 uniform_frame(64) models,
     one modal case each, 130 modes per model (frequencies + shapes). Not the driver's headline metric."""
@@ -224,6 +320,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="models in the CPU baseline sample (0 = auto)")
     ap.add_argument("--workload", default="static", choices=["static", "modal"],
                     help="static = the headline LinearStatic batch (default); modal = BASELINE.json config 4 (auxiliary line)")
+    ap.add_argument("--total-models", type=int, default=0, help="strong scaling: the whole job has this many models (config 5: 65536)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the modal / single-model / multi-GPU-in-one-process legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -235,6 +333,9 @@ def main():
     if args.workload == "modal":
         return modal_main(args, rank, local_rank, world)
     N, nLC, M = args.bays, args.cases, args.models_per_gpu
+    strong = args.total_models > 0
+    if strong:
+        M = (args.total_models + world - 1) // world
 
     from hd_b200 import frames
     from hd_b200.model import flatten_model
@@ -246,7 +347,8 @@ def main():
     config = {"workload": workload, "models_per_gpu": M, "n_bays": N, "load_cases": nLC, "dof": dof,
               "bytes_per_solve": b_in + b_out,
               "l2_policy": f"working set per step {(b_in + b_out) * M / 1e9:.2f} GB per GPU >> 126 MB L2, no flush needed",
-              "parallelism": f"models sharded over {world} rank(s), no data-path collective"}
+              "parallelism": f"models sharded over {world} rank(s), no data-path collective",
+              "scaling": "strong" if strong else "weak"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -343,6 +445,10 @@ def main():
     ms = float(t_ms.item())
     value = world * M * args.steps / (ms * 1e-3)
 
+    # ---- the timed batch is correct: eight strided models against the CPU oracle (after the timed region) ----
+    parity, parity_idx = parity_check(model, sections, loads, d_disp, d_forces, d_react)
+    assert parity <= 1e-9, f"parity lost: {parity}"
+
     # ---- e2e: the public C-ABI call with pinned HOST buffers; H2D and D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
@@ -373,7 +479,89 @@ def main():
         e2e = {"value": world * M * e_steps / float(t_e.item()), "unit": UNIT, "h2d_bytes_per_step": int(M * b_in),
                "d2h_bytes_per_step": int(M * (b_out + 8)), "steps": e_steps,
                "path": "hdb_static_batch on cudaHostAlloc buffers: chunked H2D -> 3 kernels -> D2H, three streams"}
+        # the same step with the load cases built on the device from their parameters (mod.LoadUniform on the device,
+        # hdb_uniform_loads_dev): H2D carries sections + line loads + the lateral force instead of dense load vectors
+        e2e_u = None
+        try:
+            q, fx = frames.uniform_frame_load_params(N, rank * M, M, nLC)
+            qq = np.zeros((M, nLC, N, 2))
+            qq[..., 1] = q
+            ff = np.zeros((M, nLC, 1, 3))
+            ff[:, :, 0, 0] = fx
+            h_q, h_f = pinned(qq.shape), pinned(ff.shape)
+            h_q[...] = qq
+            h_f[...] = ff
+            ubeam = np.array([frames.girder_index(i) for i in range(1, N + 1)], dtype=np.int32)
+            uproj = np.ones(N, dtype=np.uint8)
+            d_q, d_f = torch.empty(qq.shape, dtype=torch.float64, device=dev), torch.empty(ff.shape, dtype=torch.float64, device=dev)
+            t_q, t_f, t_sec = torch.from_numpy(h_q), torch.from_numpy(h_f), torch.from_numpy(h_sec)
+            t_disp, t_forces, t_react = torch.from_numpy(h_disp), torch.from_numpy(h_forces), torch.from_numpy(h_react)
+
+            def step_u():
+                d_sec.copy_(t_sec, non_blocking=True)
+                d_q.copy_(t_q, non_blocking=True)
+                d_f.copy_(t_f, non_blocking=True)
+                topo.uniform_loads_dev(M, nLC, ubeam, uproj, d_q, [1], d_f, d_loads, stream)
+                topo.static_batch_dev(M, d_sec, nLC, d_loads, d_disp, d_forces, d_react, d_status, d_fail, stream)
+                t_disp.copy_(d_disp, non_blocking=True)
+                t_forces.copy_(d_forces, non_blocking=True)
+                t_react.copy_(d_react, non_blocking=True)
+                torch.cuda.synchronize()
+            react_ref = h_react.copy()
+            step_u()
+            assert np.array_equal(h_react, react_ref), "device-built loads differ from the host-built ones"
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                step_u()
+            dtu = time.perf_counter() - t0
+            t_u = torch.tensor([dtu], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_u, op=dist.ReduceOp.MAX)
+            e2e_u = {"value": world * M * e_steps / float(t_u.item()), "unit": UNIT,
+                     "h2d_bytes_per_step": int(sections.nbytes + qq.nbytes + ff.nbytes), "d2h_bytes_per_step": int(M * b_out),
+                     "path": "pinned sections + line-load parameters -> hdb_uniform_loads_dev -> hdb_static_batch_dev -> pinned results"}
+        except Exception as ex:  # the headline does not depend on this leg
+            e2e_u = {"error": repr(ex)}
         del keep
+
+    # ---- one process driving every GPU of the box (hdb_multi_*), rank 0 alone; the other ranks wait at the barrier ----
+    spmg = None
+    if world > 1 and not args.no_extras:
+        barrier()
+        if rank == 0:
+            try:
+                mt = _lib.MultiTopology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports, list(range(world)))
+                mm = min(M, 2048)
+                bufs = []
+                for d in range(world):
+                    dv = torch.device("cuda", d)
+                    bufs.append(dict(sec=torch.from_numpy(sections[:mm]).to(dv), loads=torch.from_numpy(loads[:mm]).to(dv),
+                                     disp=torch.empty((mm, nLC, nP, 3), dtype=torch.float64, device=dv),
+                                     forces=torch.empty((mm, nLC, nB, 6), dtype=torch.float64, device=dv),
+                                     react=torch.empty((mm, nLC, nP, 3), dtype=torch.float64, device=dv),
+                                     st=torch.zeros((mm,), dtype=torch.int32, device=dv), fc=torch.zeros((mm,), dtype=torch.int32, device=dv)))
+                col = lambda k: [b[k] for b in bufs]
+                run = lambda: mt.static_batch_dev([mm] * world, col("sec"), nLC, col("loads"), col("disp"), col("forces"), col("react"), col("st"), col("fc"))
+                for _ in range(3):
+                    run()
+                mt.synchronize()
+                t0 = time.perf_counter()
+                reps = 10
+                for _ in range(reps):
+                    run()
+                mt.synchronize()
+                dts = time.perf_counter() - t0
+                summ = mt.gather_summary([mm] * world, col("st"), col("disp"), nLC)
+                same = all(torch.equal(bufs[0]["react"].cpu(), b["react"].cpu()) for b in bufs[1:])
+                spmg = {"value": world * mm * reps / dts, "unit": UNIT, "models_per_gpu": mm, "devices": world, "timing": "host clock around 10 enqueue rounds + device sync",
+                        "nccl_summary": {"failed": float(summ[:, 0].sum()), "max_abs_disp": float(summ[:, 1].max()), "models": float(summ[:, 2].sum())},
+                        "shards_identical": bool(same)}
+                mt.close()
+                del bufs
+            except Exception as ex:
+                spmg = {"error": repr(ex)}
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -382,9 +570,9 @@ def main():
 
     # ---- roofline of the dominant kernel (k_solve_pipe) ----
     peaks, peak_src = measured_peaks()
-    names = ["k_assemble", "k_factor", "k_solve_pipe"]
     sub = int(os.environ.get("HDB_SUB_BATCH", "8192"))
     n_launch = args.steps * ((M + sub - 1) // sub)
+    names = ["k_assemble_quad", "k_factor", "k_solve_bulk"]
     roof = None
     if len(kernel_ms) >= 3 and kernel_ms[2] > 0:
         per_launch_models = M * args.steps / n_launch
@@ -394,8 +582,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get("k_solve_pipe_dram_bytes_per_launch")
-        roof = {"bound": "hbm", "kernel": "k_solve_pipe", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                traffic = json.load(f).get("k_solve_bulk_dram_bytes_per_launch")
+        roof = {"bound": "hbm", "kernel": "k_solve_bulk", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                 "launch_ms": dur * 1e3, "models_per_launch": per_launch_models,
                 "kernel_ms_total": dict(zip(names, kernel_ms)), "kernel_share": {n: k / sum(kernel_ms) for n, k in zip(names, kernel_ms)}}
@@ -414,11 +602,24 @@ def main():
                "tuned_note": "same oracle with the reaction scan replaced by per-row lists (bit-identical results)",
                "go_published": "README.md:63 BenchmarkRun/__128: 9.47 runs/s (static+modal, cantilever, unknown amd64, 1 core)"}
 
+    extras = {}
+    if not args.no_extras and world == 1:
+        try:
+            extras["modal"] = modal_leg(local_rank)
+        except Exception as ex:
+            extras["modal"] = {"error": repr(ex)}
+        try:
+            extras["single"] = single_leg()
+        except Exception as ex:
+            extras["single"] = {"error": repr(ex)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches), "failed_models": int(bad.item()), "numa_bound_cpus": int(numa_cpus),
-            "hbm_frac_whole_step": value / world * (b_in + b_out) / 1e9 / peaks["hbm_gbs"]}
+            "hbm_frac_whole_step": value / world * (b_in + b_out) / 1e9 / peaks["hbm_gbs"],
+            "parity_max_rel": parity, "parity_models": parity_idx, "e2e_uniform": e2e_u if not args.no_e2e else None,
+            "single_process_multi_gpu": spmg}
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
