@@ -532,7 +532,7 @@ def main():
         if rank == 0:
             try:
                 mt = _lib.MultiTopology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports, list(range(world)))
-                mm = min(M, 2048)
+                mm = M
                 bufs = []
                 for d in range(world):
                     dv = torch.device("cuda", d)

@@ -157,3 +157,110 @@ func (t *Topology) UniformLoadsDev(nModels, nLC int, beams []int32, projection [
 		C.int32_t(len(nodes)), pn, (*C.double)(f), (*C.double)(loads), nil)
 	return errOf(rc, "hdb_uniform_loads_dev")
 }
+
+// CheckModel is checkInputData of check.go:12-109, 223-397 restated in the library (hosts that keep the reference's
+// own check.go do not need it).  A non-nil error carries the library's list of findings.
+func CheckModel(points [][2]float64, beams []Beam, pins [][6]bool, supports [][3]bool) error {
+	msg := make([]byte, 4096)
+	var pp *C.double
+	var pb *C.hdb_beam
+	var ps *C.uint8_t
+	if len(points) > 0 {
+		pp = (*C.double)(unsafe.Pointer(&points[0][0]))
+	}
+	if len(beams) > 0 {
+		pb = (*C.hdb_beam)(unsafe.Pointer(&beams[0]))
+	}
+	if len(supports) > 0 {
+		ps = (*C.uint8_t)(unsafe.Pointer(&supports[0][0]))
+	}
+	rc := C.hdb_check_model(C.int32_t(len(points)), pp, C.int32_t(len(beams)), pb, C.int32_t(len(pins)), b2u(pins),
+		C.int32_t(len(supports)), ps, (*C.char)(unsafe.Pointer(&msg[0])), C.int32_t(len(msg)))
+	if rc == 0 {
+		return nil
+	}
+	return fmt.Errorf("%s", C.GoString((*C.char)(unsafe.Pointer(&msg[0]))))
+}
+
+// LoadNode mirrors hd.LoadNode (model.go:304-315), 32 bytes, pointer-free.
+type LoadNode struct {
+	N      int
+	Forces [3]float64
+}
+
+// ModalMass mirrors hd.ModalMass (model.go:294-301), 16 bytes, pointer-free.
+type ModalMass struct {
+	N    int
+	Mass float64
+}
+
+// CheckLoads is LoadCase.checkInputData (check.go:127-163).
+func CheckLoads(nP int, loads []LoadNode) error {
+	msg := make([]byte, 2048)
+	var p *C.hdb_load_node
+	if len(loads) > 0 {
+		p = (*C.hdb_load_node)(unsafe.Pointer(&loads[0]))
+	}
+	if rc := C.hdb_check_loads(C.int32_t(nP), C.int32_t(len(loads)), p, (*C.char)(unsafe.Pointer(&msg[0])), C.int32_t(len(msg))); rc != 0 {
+		return fmt.Errorf("%s", C.GoString((*C.char)(unsafe.Pointer(&msg[0]))))
+	}
+	return nil
+}
+
+// CheckModal is ModalCase.checkInputData (check.go:411-452).
+func CheckModal(nP int, supports [][3]bool, masses []ModalMass) error {
+	msg := make([]byte, 2048)
+	var p *C.hdb_modal_mass
+	var ps *C.uint8_t
+	if len(masses) > 0 {
+		p = (*C.hdb_modal_mass)(unsafe.Pointer(&masses[0]))
+	}
+	if len(supports) > 0 {
+		ps = (*C.uint8_t)(unsafe.Pointer(&supports[0][0]))
+	}
+	if rc := C.hdb_check_modal(C.int32_t(nP), C.int32_t(len(supports)), ps, C.int32_t(len(masses)), p,
+		(*C.char)(unsafe.Pointer(&msg[0])), C.int32_t(len(msg))); rc != 0 {
+		return fmt.Errorf("%s", C.GoString((*C.char)(unsafe.Pointer(&msg[0]))))
+	}
+	return nil
+}
+
+// Multi drives several GPUs of one box from this one process (hdb_multi_*): contiguous model ranges per device.
+type Multi struct{ h *C.hdb_multi }
+
+// NewMulti runs the symbolic phase once per device; devices are CUDA ordinals.
+func NewMulti(points [][2]float64, beams []Beam, pins [][6]bool, supports [][3]bool, devices []int32) (*Multi, error) {
+	m := &Multi{}
+	rc := C.hdb_multi_create(C.int32_t(len(points)), (*C.double)(unsafe.Pointer(&points[0][0])), C.int32_t(len(beams)),
+		(*C.hdb_beam)(unsafe.Pointer(&beams[0])), b2u(pins), (*C.uint8_t)(unsafe.Pointer(&supports[0][0])), nil,
+		C.int32_t(len(devices)), (*C.int32_t)(unsafe.Pointer(&devices[0])), &m.h)
+	if err := errOf(rc, "hdb_multi_create"); err != nil {
+		return nil, err
+	}
+	runtime.SetFinalizer(m, func(m *Multi) { m.Close() })
+	return m, nil
+}
+
+// Close releases every per-device handle.
+func (m *Multi) Close() {
+	if m.h != nil {
+		C.hdb_multi_destroy(m.h)
+		m.h = nil
+	}
+}
+
+// StaticBatch is Topology.StaticBatch over all devices: host slices in, host slices out, one host thread per device
+// inside the library, results bit-identical to one device.
+func (m *Multi) StaticBatch(nModels, nLC int, sections, loads, disp, forces, react []float64, status, failCase []int32) error {
+	p := func(s []float64) *C.double {
+		if len(s) == 0 {
+			return nil
+		}
+		return (*C.double)(unsafe.Pointer(&s[0]))
+	}
+	rc := C.hdb_multi_static_batch(m.h, C.int32_t(nModels), p(sections), C.int32_t(nLC), p(loads), p(disp), p(forces), p(react),
+		(*C.int32_t)(unsafe.Pointer(&status[0])), (*C.int32_t)(unsafe.Pointer(&failCase[0])))
+	runtime.KeepAlive(sections)
+	runtime.KeepAlive(loads)
+	return errOf(rc, "hdb_multi_static_batch")
+}

@@ -237,3 +237,21 @@ def test_compute_refuses_without_gpu(oracle):
     with pytest.raises(_lib.HdbError):
         t.assemble_batch(fm.sections[None])
     t.close()
+
+
+def test_go_sources_bind_only_exported_symbols():
+    """The Go front cannot be compiled here (no toolchain): at least every C function it names must be one the header
+    declares and the library exports, and every exported entry point of the reference must be present in go/hd."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "hdb200.h")).read()
+    for rel in ("go/hdb200/hdb200.go", "go/hd/hd.go"):
+        src = open(os.path.join(root, rel)).read()
+        for name in set(re.findall(r"C\.(hdb_[a-z_0-9]+)\(", src)):
+            assert name in _lib.SYMBOLS and re.search(r"\b%s\(" % name, header), (rel, name)
+        assert src.count("{") == src.count("}") and src.count("(") == src.count(")"), rel
+    front = open(os.path.join(root, "go/hd/hd.go")).read()
+    for sig in ("func Run(out io.Writer, m *Model, lcs []LoadCase, mcs []ModalCase) error",
+                "func LinearStatic(out io.Writer, m *Model, lcs ...*LoadCase) (err error)",
+                "func Modal(out io.Writer, m *Model, mc *ModalCase) (err error)", "func RunBatch(", "func RunBatchMulti("):
+        assert sig in front, sig
