@@ -1273,15 +1273,14 @@ int hdb_buckling_batch_dev(hdb_topology *t, int32_t nModels, const double *secti
         CUDA_TRY(cudaMemsetAsync(status, 0, (size_t)nModels * sizeof(int32_t), st));
         return HDB_OK;
     }
-    if (s > buckling_max_s(t->smemOptin)) {
-        set_error_detail("hdb_buckling_batch: too many free DOFs for the shared-memory resident eigen solver");
-        return HDB_ERR_UNSUPPORTED;
-    }
     if ((rc = ensure_buckling_tables(t)) != HDB_OK) return rc;
     const size_t per = (size_t)s * S.dof * sizeof(double);
-    int sbm = (int)std::max<size_t>(1, std::min<size_t>((size_t)nModels, ((size_t)768 << 20) / (2 * per)));
+    // models whose three s x s work matrices do not fit shared memory keep them in a global scratch record per (model, case)
+    const size_t scrD = buckling_scratch_doubles(s, S.nB, t->smemOptin);
+    const size_t perAll = 2 * per + scrD * sizeof(double) * (size_t)nLC;
+    int sbm = (int)std::max<size_t>(1, std::min<size_t>((size_t)nModels, ((size_t)4 << 30) / perAll));
     sbm = std::min(sbm, t->subBatch);
-    const size_t need = 2 * per * sbm + 1024;
+    const size_t need = perAll * sbm + 1024;
     if (need > t->modalBytes) {
         if (t->modalBuf) {
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -1294,6 +1293,7 @@ int hdb_buckling_batch_dev(hdb_topology *t, int32_t nModels, const double *secti
     }
     double *unitLoads = (double *)t->modalBuf;
     double *sol = (double *)((char *)t->modalBuf + per * sbm);
+    double *gscr = scrD ? (double *)((char *)t->modalBuf + 2 * per * sbm) : nullptr;
     for (int m0 = 0; m0 < nModels; m0 += sbm) {
         const int nm = std::min(sbm, nModels - m0);
         CUDA_TRY(launch_unit_loads(unitLoads, nm, s, S.dof, t->bkFreeDof, st));
@@ -1313,7 +1313,7 @@ int hdb_buckling_batch_dev(hdb_topology *t, int32_t nModels, const double *secti
         B.status = status + m0;
         {
             ProfScope ps(t, KIND_MODAL0 + 1, st);
-            cudaError_t e = launch_buckling_eigen(B, t->smemOptin, st);
+            cudaError_t e = launch_buckling_eigen(B, t->smemOptin, st, gscr);
             if (e == cudaErrorInvalidConfiguration) {
                 set_error_detail("buckling eigen kernel does not fit shared memory");
                 return HDB_ERR_UNSUPPORTED;

@@ -943,15 +943,17 @@ cudaError_t launch_unit_loads(double *loads, int nModels, int s, int dof, const 
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(EIG_THREADS, 1) k_buckling_eigen(const BucklingLaunch P, const int LD)
+__global__ void __launch_bounds__(EIG_THREADS, 1) k_buckling_eigen(const BucklingLaunch P, const int LD, double *gscr)
 {
     extern __shared__ __align__(16) double sm[];
     const int n = P.s, tid = threadIdx.x;
     const int model = blockIdx.x / P.nLC, lc = blockIdx.x - model * P.nLC;
-    double *A = sm;                  // S, then its Cholesky factor C (lower), element (i, j) at i + j * LD
+    // the three n x n work matrices live in shared memory when they fit (gscr == NULL) and otherwise in a global scratch
+    // record of this block (models with more than ~95 free DOFs: slower, L2 / HBM resident, same code)
+    double *A = gscr ? gscr + (size_t)blockIdx.x * 3 * LD * n : sm; // S, then its Cholesky factor C (lower), element (i, j) at i + j * LD
     double *Gm = A + (size_t)LD * n; // G, then B = C^T G C, then the eigenvectors Y
     double *Tm = Gm + (size_t)LD * n; // G C, then X = C Y
-    double *d = Tm + (size_t)LD * n;
+    double *d = gscr ? sm : Tm + (size_t)LD * n;
     double *e = d + n, *cc = e + n, *ss = cc + n; // cc: ring of QL rotations, QL_RING slots of 2n
     double *red = cc + (size_t)2 * QL_RING * n;   // [EIG_THREADS/32 + 8]
     double *ax = red + EIG_THREADS / 32 + 8; // [nB] axial force of every beam
@@ -1095,16 +1097,30 @@ int buckling_max_s(int smemOptin)
     return n;
 }
 
-cudaError_t launch_buckling_eigen(const BucklingLaunch &B, int smemOptin, cudaStream_t st)
+// shared memory of a block without the three work matrices (global-scratch path)
+static size_t buckling_smem_small(int n, int nB)
+{
+    return (2 * (size_t)n + 2 * (size_t)QL_RING * n + EIG_THREADS / 32 + 8 + nB) * sizeof(double) + (size_t)n * sizeof(int) + 64;
+}
+
+size_t buckling_scratch_doubles(int n, int nB, int smemOptin)
+{ // per (model, case) block; 0 = the matrices fit shared memory
+    int LD;
+    if (buckling_smem(n, nB, LD) + 1024 <= (size_t)smemOptin) return 0;
+    return (size_t)3 * LD * n;
+}
+
+cudaError_t launch_buckling_eigen(const BucklingLaunch &B, int smemOptin, cudaStream_t st, double *gscr)
 {
     int LD;
-    const size_t smem = buckling_smem(B.s, B.nB, LD);
+    size_t smem = buckling_smem(B.s, B.nB, LD);
+    if (gscr) smem = buckling_smem_small(B.s, B.nB);
     if (smem + 1024 > (size_t)smemOptin) return cudaErrorInvalidConfiguration;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_buckling_eigen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_buckling_eigen<<<B.nModels * B.nLC, EIG_THREADS, smem, st>>>(B, LD);
+    k_buckling_eigen<<<B.nModels * B.nLC, EIG_THREADS, smem, st>>>(B, LD, gscr);
     return cudaGetLastError();
 }
 

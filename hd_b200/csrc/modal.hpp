@@ -63,7 +63,9 @@ struct BucklingLaunch {
 };
 // loads[nModels][s][dof] = unit load on free DOF i in case i
 cudaError_t launch_unit_loads(double *loads, int nModels, int s, int dof, const int32_t *freeDof, cudaStream_t st);
-cudaError_t launch_buckling_eigen(const BucklingLaunch &B, int smemOptin, cudaStream_t st);
+// gscr: NULL (work matrices in shared memory) or nModels * nLC records of buckling_scratch_doubles() doubles
+cudaError_t launch_buckling_eigen(const BucklingLaunch &B, int smemOptin, cudaStream_t st, double *gscr);
+size_t buckling_scratch_doubles(int n, int nB, int smemOptin);
 int buckling_max_s(int smemOptin);
 
 cudaError_t launch_modal_loads(const ModalLaunch &M, cudaStream_t st);

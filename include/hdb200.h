@@ -42,8 +42,9 @@ enum {
     HDB_ERR_NO_DEVICE = -2,   /* no CUDA device: the product has no CPU path           */
     HDB_ERR_CUDA = -3,        /* CUDA runtime error (hdb_last_error_detail)            */
     HDB_ERR_NOMEM = -4,
-    HDB_ERR_UNSUPPORTED = -5, /* too large for a shared-memory resident kernel: modal / buckling eigen solves (limits in
-                               * DESIGN.md section 8); LinearStatic only above ~28 k padded DOFs per load case */
+    HDB_ERR_UNSUPPORTED = -5, /* too large for a shared-memory resident kernel: the modal eigen solve above ~160 mass DOFs
+                               * (DESIGN.md section 8), LinearStatic only above ~28 k padded DOFs per load case; also
+                               * hdb_multi_gather_summary without NCCL */
     HDB_ERR_INPUT = -6,       /* topology rejected (what check.go rejects for shared data) */
     HDB_ERR_SMALL_BUFFER = -7
 };
@@ -205,7 +206,9 @@ int hdb_modal_batch_dev(hdb_topology *t, int32_t nModels, const double *sections
  * K^-1 G (model.go:578), shapes[maxOut][nP][3] (unit 2-norm, sign free) or NULL.  The reference takes the real
  * eigenvalues of the dense non-symmetric H = K^-1 G; here the same eigenvalues come from the symmetric
  * C^T G C with (K^-1)_ff = C C^T, which needs a stable (positive definite) model: otherwise HDB_STATUS_EIGEN.
- * The free DOF count must not exceed hdb_buckling_max_free() (shared-memory resident solver). */
+ * Up to hdb_buckling_max_free() free DOFs the eigen solver keeps its work matrices in shared memory; larger models
+ * (uniform_frame(128): 387) run the same code on a global scratch record per (model, case): slower, no size limit
+ * other than memory. */
 int hdb_buckling_max_free(hdb_topology *t);
 int hdb_buckling_batch(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *forces,
                        int32_t amount, int32_t maxOut, int32_t *nOut, double *factors, double *shapes, int32_t *status);

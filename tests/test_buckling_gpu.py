@@ -105,3 +105,29 @@ def test_tension_gives_no_factor(oracle):
     assert rc == oracle.OK and not bst.any() and nOut[0, 0] == len(ofac)
     np.testing.assert_allclose(fac[0, 0, :len(ofac)], ofac, rtol=TOL)
     t.close()
+
+
+@pytest.mark.parametrize("N", [32, 128])
+def test_buckling_beyond_shared_memory(oracle, N):
+    """uniform_frame(32) has 99 free DOFs, uniform_frame(128) 387 (BASELINE.json's size): the three s x s work matrices of
+    the eigen kernel no longer fit shared memory and live in a global scratch record per (model, case).  Factors against the
+    oracle's non-symmetric solve of K^-1 G (model.go:491-601) at 1e-9 (cond(K_ff) = 25)."""
+    fm = oracle.flatten_model(frames.uniform_frame(N))
+    nM = 2
+    secs = frames.uniform_frame_sections(N, 9, nM)
+    loads = frames.uniform_frame_loads(N, 9, nM, 1)
+    t = _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports)
+    assert t.info.nFree > t.buckling_max_free()
+    status, fail, disp, forces, react = t.static_batch(secs, loads)
+    assert not status.any()
+    bst, nOut, fac, shp = t.buckling_batch(secs, forces, 3)
+    assert not bst.any()
+    for i in range(nM if N <= 32 else 1):  # the oracle's dense 774 x 774 non-symmetric eigen solve takes a while
+        fmi = oracle.flatten_model(frames.uniform_frame(N))
+        fmi.sections[:] = secs[i]
+        rc, ofac, oshp = oracle.buckling(fmi, forces[i, 0], 3)
+        assert rc == oracle.OK and nOut[i, 0] == len(ofac) == 3
+        np.testing.assert_allclose(fac[i, 0, :3], ofac, rtol=TOL)
+        for r in range(3):
+            _shape_close(shp[i, 0, r], oshp[r], 1e-6, f"frame {N} model {i} mode {r}")
+    t.close()

@@ -21,23 +21,37 @@ def topo_of(oracle, m, **kw):
     return fm, _lib.Topology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports, **kw)
 
 
-def compare_rule(exp, act, eps=EPS, floor=1e-3):
-    """mod.Compare (mod/compare.go:28-66): relative difference per component, absolute when the expected
-    value is exactly 0.  Components that are round-off of a mathematically zero quantity (a mid-span
-    rotation of a symmetric case, ...) have no meaningful relative error: anything below `floor` times the
-    largest value of the same kind (translations / rotations, forces / moments) in the same load case is
-    measured against that scale instead."""
+PARITY_LOG = []  # one record per compare_rule call: printed at the end of the session (conftest.py)
+
+
+def compare_rule(exp, act, eps=EPS, floor=1e-3, max_floor_frac=0.02, what=""):
+    """mod.Compare (mod/compare.go:28-66): relative difference per component, absolute when the expected value is exactly
+    0.  The PURE rule is evaluated first and its worst error recorded; a component that fails it is an EXCEPTION and is
+    accepted only if (a) it is below `floor` times the largest value of the same kind (translations / rotations, forces /
+    moments) in the same load case — round-off of a mathematically zero quantity, e.g. the mid-span rotation of a symmetric
+    case — and passes when measured against that scale, and (b) the exceptions stay below `max_floor_frac` of the
+    components.  The count and both worst errors go to PARITY_LOG."""
     exp, act = np.asarray(exp, dtype=float), np.asarray(act, dtype=float)
     assert exp.shape == act.shape
     z = exp == 0.0
     assert np.all(np.abs(act[z]) <= eps), np.abs(act[z]).max()
+    den = np.abs(exp)
+    den[z] = 1.0
+    pure = np.abs(exp - act) / den
+    exc = (pure > eps) & ~z
     scale = np.empty_like(exp)
     scale[..., :2] = np.abs(exp[..., :2]).max(axis=(-1, -2), keepdims=True)
     scale[..., 2:] = np.abs(exp[..., 2:]).max(axis=(-1, -2), keepdims=True)
-    den = np.maximum(np.abs(exp), floor * scale)
-    den[den == 0] = 1.0
-    rel = np.abs(exp - act) / den
-    assert rel[~z].size == 0 or rel[~z].max() <= eps, rel[~z].max()
+    small = np.abs(exp) < floor * scale
+    assert not np.any(exc & ~small), ("component above the floor fails the pure rule", float(pure[exc & ~small].max()))
+    floored = np.abs(exp - act)[exc] / (floor * scale[exc]) if exc.any() else np.zeros(0)
+    assert floored.size == 0 or floored.max() <= eps, float(floored.max())
+    rec = {"what": what, "n": int(exp.size), "exceptions": int(exc.sum()), "worst_pure_rel_without_exceptions":
+           float(pure[~exc & ~z].max()) if np.any(~exc & ~z) else 0.0, "worst_pure_rel_of_exceptions": float(pure[exc].max()) if exc.any() else 0.0,
+           "worst_exception_against_floor": float(floored.max()) if floored.size else 0.0}
+    PARITY_LOG.append(rec)
+    assert exc.mean() <= max_floor_frac, rec
+    return rec
 
 
 def force_rule(exp, act, eps=EPS):
@@ -132,8 +146,8 @@ def test_static_uniform_frame_vs_oracle(oracle, N, nM):
     assert not status.any() and np.all(fail == -1)
     ost, od, of, orr = oracle.static_batch(fm, secs, loads)
     assert not ost.any()
-    compare_rule(od, disp)
-    compare_rule(orr, react)
+    compare_rule(od, disp, what=f"uniform_frame({N}) x {nM} disp")
+    compare_rule(orr, react, what=f"uniform_frame({N}) x {nM} react")
     force_rule(of, forces)
     t.close()
 
@@ -149,10 +163,11 @@ def test_static_bench_cantilever_vs_oracle(oracle, ic):
     assert not status.any()
     rc, od, of, orr, _ = oracle.linear_static(fm, loads[0])
     assert rc == 0
-    eps = 1e-9 if ic <= 8 else 1e-8
-    compare_rule(od, disp[0], eps)
-    compare_rule(orr, react[0], eps)
-    force_rule(of, forces[0], eps)
+    # cond(K_ff) = 1.7e5 at ic = 8 and 2.8e7 at ic = 32 (LU with pivoting and Cholesky agree to
+    # 2.2e-11 there): 1e-9 holds for both
+    compare_rule(od, disp[0], 1e-9, what=f"bench_cantilever({ic}) disp")
+    compare_rule(orr, react[0], 1e-9, what=f"bench_cantilever({ic}) react")
+    force_rule(of, forces[0], 1e-9)
     t.close()
 
 
