@@ -212,13 +212,29 @@ int hdb_multi_static_batch_dev(hdb_multi *m, const int32_t *count, const double 
                                int32_t *const *failCase, void *const *streams)
 {
     if (!m || !count || !sections || !status || nLC < 0 || (nLC > 0 && !loads)) return HDB_ERR_ARG;
-    for (size_t d = 0; d < m->topo.size(); d++) {
-        if (count[d] <= 0) continue;
-        const int rc = hdb_static_batch_dev(m->topo[d], count[d], sections[d], nLC, loads ? loads[d] : nullptr, disp ? disp[d] : nullptr,
-                                            forces ? forces[d] : nullptr, react ? react[d] : nullptr, status[d],
-                                            failCase ? failCase[d] : nullptr, streams ? streams[d] : nullptr);
-        if (rc != HDB_OK) return rc;
+    const int nDev = (int)m->topo.size();
+    std::vector<int> rc(nDev, HDB_OK);
+    std::vector<std::string> detail(nDev);
+    auto enqueue = [&](int d) {
+        if (count[d] <= 0) return;
+        rc[d] = hdb_static_batch_dev(m->topo[d], count[d], sections[d], nLC, loads ? loads[d] : nullptr, disp ? disp[d] : nullptr,
+                                     forces ? forces[d] : nullptr, react ? react[d] : nullptr, status[d],
+                                     failCase ? failCase[d] : nullptr, streams ? streams[d] : nullptr);
+        if (rc[d] != HDB_OK) detail[d] = hdb_last_error_detail();
+    };
+    // one host thread per device: enqueueing a step takes a few hundred microseconds of host time per device, which one
+    // thread would serialise in front of eight GPUs that need 1.5 ms for it
+    if (nDev == 1) enqueue(0);
+    else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < nDev; d++) th.emplace_back(enqueue, d);
+        for (auto &t : th) t.join();
     }
+    for (int d = 0; d < nDev; d++)
+        if (rc[d] != HDB_OK) {
+            set_error_detail("device " + std::to_string(m->dev[d]) + ": " + detail[d]);
+            return rc[d];
+        }
     return HDB_OK;
 }
 
