@@ -22,7 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "solve_ops.cuh"
+#include "bulk_ops.cuh"
 
 namespace hdb {
 
@@ -50,65 +50,6 @@ struct BulkCfg {
     unsigned oDt, oBb, oRp, oRl, oEl, oPm, oGm, oSlot, oLvm, oXs, lvmBytes, xsBytes, BS, ZB;
     int dbg; // HDB_BULK_DBG (debug instantiation only): 1 = no bulk stores, 2 = no fence, 4 = forces without arithmetic
 };
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ unsigned long long l2_policy_evict_first()
-{
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_last()
-{
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-// results are written once and not read again by this kernel: they should not push the prefetched inputs out of L2
-__device__ __forceinline__ void bulk_store(void *gdst, unsigned ssrc, unsigned bytes, unsigned long long pol)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(ssrc), "r"(bytes), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_prefetch_l2(const void *g, unsigned bytes, unsigned long long pol)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(g), "r"(bytes), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void lds_v2s32(unsigned a, int &x, int &y) { asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a)); }
-__device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory"); }
-__device__ __forceinline__ double2 ldg_v2_stream(const double *p)
-{ // read once more at most: no L1 allocation
-    double2 v;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ bool elect_one()
-{ // one lane of the (converged) warp, as a warp-uniform predicate
-    unsigned pred;
-    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
-    return pred != 0u;
-}
-__device__ __forceinline__ bool is_finite(double v) { return fabs(v) <= 1.7976931348623157e308; }
-
-// prefetch a run into L2 in pieces the instruction accepts (size: multiple of 16)
-__device__ __forceinline__ void prefetch_run(const void *p, size_t bytes, unsigned long long pol)
-{
-    const char *q = reinterpret_cast<const char *>(p);
-    const size_t head = (16 - (reinterpret_cast<uintptr_t>(q) & 15)) & 15;
-    if (bytes <= head + 16) return;
-    q += head;
-    bytes = (bytes - head) & ~(size_t)15;
-    while (bytes) {
-        const unsigned n = bytes > (1u << 20) ? (1u << 20) : (unsigned)bytes;
-        bulk_prefetch_l2(q, n, pol);
-        q += n;
-        bytes -= n;
-    }
-}
 
 static size_t align16b(size_t b) { return (b + 15) & ~(size_t)15; }
 
@@ -158,19 +99,6 @@ bool solve_bulk_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPa
         }
     }
     return false;
-}
-
-// a beam with released ends: the condensed element is dense (feBeam2d.go:58-137).  Out of line, arguments by value and
-// the result stored straight to the staging slot, so that the caller keeps no local array
-static __device__ __noinline__ void pinned_forces_to_slot(const BeamCoef cf, const uint32_t pm, const double gc, const double gs, const double u0,
-                                                          const double u1, const double u2, const double u3, const double u4, const double u5,
-                                                          const unsigned sl)
-{
-    double uu[6] = {u0, u1, u2, u3, u4, u5}, oo[6];
-    beam_forces_pinned(cf, pm, gc, gs, uu, oo);
-    sts_v2f64(sl, oo[0], oo[1]);
-    sts_v2f64(sl + 16u, oo[2], oo[3]);
-    sts_v2f64(sl + 32u, oo[4], oo[5]);
 }
 
 // Work of the worker warps comes in PAIRS of chunks: the load cases of an item are split into a first half A and a
