@@ -26,6 +26,24 @@ __device__ __forceinline__ void bulk_store(void *gdst, unsigned ssrc, unsigned b
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(ssrc), "r"(bytes), "l"(pol) : "memory");
 }
+// bulk copy global -> shared; its bytes complete a phase of the mbarrier (one arrival expected per phase)
+__device__ __forceinline__ void bulk_load(unsigned sdst, const void *gsrc, unsigned bytes, unsigned mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned mbar, unsigned parity) // does not block
+{
+    unsigned done;
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    return done != 0u;
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done) // try_wait suspends the thread for a while when the phase is not complete
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
