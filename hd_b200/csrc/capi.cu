@@ -323,8 +323,8 @@ static int ensure_workspace(hdb_topology *t, size_t models)
     }
     for (int i = 0; i < 2; i++) {
         CUDA_TRY(cudaMalloc(&t->Wbuf[i], (size_t)t->S.nSlots * ld * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&t->Lmbuf[i], (size_t)t->S.nSlots * ld * sizeof(double) + 16)); // + 16: the solve kernel's bulk copies cover whole 16-byte pairs
-        CUDA_TRY(cudaMalloc(&t->Ksfbuf[i], std::max<size_t>(1, ld * (size_t)t->S.nnzR) * sizeof(double) + 16));
+        CUDA_TRY(cudaMalloc(&t->Lmbuf[i], (size_t)t->S.nSlots * ld * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&t->Ksfbuf[i], std::max<size_t>(1, ld * (size_t)t->S.nnzR) * sizeof(double)));
     }
     if (!assemble_fits_smem(t->D, t->smemOptin))
         CUDA_TRY(cudaMalloc(&t->keScratch, ld * (size_t)t->S.nB * KE_LD * sizeof(double)));
@@ -757,13 +757,15 @@ static void debug_report_clocks(hdb_topology *t, int nModels)
                  blk / models, sol / models);
     static const char *namesPipe[11] = {"Ksf/section loads issued", "-", "disp + Ksf, coefficients -> smem", "(barrier)", "react", "forces", "(barrier)", "factor gather issue",
                                         "load cases", "(barrier)", "status"};
-    static const char *namesBulk[11] = {"disp", "(reaction block ready)", "react", "forces", "-", "(step barriers)", "rest of the load cases", "(barrier)", "-", "-", "-"};
+    static const char *namesBulk[11] = {"coefficients + Ksf -> smem", "(barrier)", "react", "forces", "disp", "(barrier)", "load cases + factor", "(barrier)", "-", "-", "-"};
     const char *leg = std::getenv("HDB_SOLVE_LEGACY");
     const char **names = (leg && atoi(leg)) ? namesPipe : namesBulk;
     std::fprintf(stderr, "[hdb]  ");
     for (int k = 0; k < 11; k++) std::fprintf(stderr, " %s %.0f |", names[k], ph[k] / models);
     std::fprintf(stderr, "\n");
-    if (!(leg && atoi(leg))) std::fprintf(stderr, "[hdb]   helper warp: reaction block -> smem %.0f\n", ph[16] / models);
+    if (!(leg && atoi(leg)))
+        std::fprintf(stderr, "[hdb]   disp units: loads %.0f | wait slots %.0f | stores to slot %.0f | fence + issue %.0f || react units: items %.0f | wait slots %.0f | zero + stores %.0f | fence + issue %.0f || helper tables %.0f\n",
+                     ph[8] / models, ph[9] / models, ph[10] / models, ph[11] / models, ph[12] / models, ph[13] / models, ph[14] / models, ph[15] / models, ph[16] / models);
 }
 
 int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
