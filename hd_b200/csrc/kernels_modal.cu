@@ -208,6 +208,211 @@ __device__ __forceinline__ void sym_tridiag_smem(double *V, const int LD, const 
 #undef VV
 }
 
+// The same reduction for the split pipeline's k_modal_tridiag (a block of TRI_THREADS threads, nothing else resident),
+// rearranged around what a block pays for, barriers and strided shared-memory walks:
+//  * V holds the FULL symmetric matrix and the rank-2 update keeps both triangles (the two products are added without
+//    contraction, so V(k, j) and V(j, k) stay bit-identical): the matrix-vector product and the update walk rows, lanes
+//    on consecutive rows, instead of jumping a column stride wherever the triangle runs out;
+//  * four threads per row or column (a quarter of the k range each, two shuffles), so the dependent chain of a step is
+//    i / 4 long; with LD = 12 (mod 16) both the row walk V(j, k) and the column walk V(k, j) of a warp's 8 x 4 threads
+//    fall into 16 distinct 8-byte bank slots, two lanes each: the two wavefronts a 256-byte warp access needs anyway;
+//  * three barriers per elimination step instead of twelve: every thread derives g, h and the last component of the
+//    Householder vector from the (uniform) squared norm; p = A v / h and v.p come out of one pass (the block sum that
+//    follows is also the barrier behind p); the correction q = p - (v.p / 2h) v is applied on the fly in the update; the
+//    owners of row i - 1 write the next step's vector (double-buffered) and its squared norm while they update it;
+//  * one barrier per accumulation step: the vectors are not divided by h beforehand (g / h multiplies them), and the
+//    column that tred2 zeroes after use is instead written analytically (it is the unit vector minus its update).
+// The norm is taken without tred2's scaling by sum |v|: B's entries are displacements per unit mass force, far from the
+// ends of the double range.  Results agree with tred2's to rounding (the tests compare frequencies with the oracle's
+// non-symmetric solve at 1e-9).  On exit as sym_tridiag_smem: V = Q, d = diagonal, e = subdiagonal shifted for tql2.
+constexpr int TRI_THREADS = 512;
+__device__ __forceinline__ double block_sum_tri(double v, double *red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads(); // red[] may still be read from the previous call
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < TRI_THREADS / 32; w++) s += red[w];
+    return s;
+}
+// w: n doubles of work space (the second vector buffer, then the diagonal)
+__device__ __forceinline__ void sym_tridiag_full(double *V, const int LD, const int n, double *d, double *e, double *w, double *red)
+{
+    const int tid = threadIdx.x, q4 = tid & 3, rl = tid >> 2;
+    constexpr int RPT = TRI_THREADS / 4; // rows (columns) per trip
+    __shared__ double s_sigma;
+#define VV(i, j) V[(i) + (size_t)(j) * LD]
+    __syncthreads();
+    double *cur = d, *nxt = w; // the vector being eliminated lives in [0, i) of one of them; d[i..n) collects the h of the steps
+    double part = 0.0;
+    for (int j = tid; j < n - 1; j += TRI_THREADS) {
+        const double t = VV(n - 1, j);
+        cur[j] = t;
+        part = fma(t, t, part);
+    }
+    double sigma = block_sum_tri(part, red);
+    for (int i = n - 1; i > 0; i--) {
+        if (sigma == 0.0) { // nothing to eliminate in this row (uniform)
+            if (tid == 0) {
+                e[i] = cur[i - 1];
+                d[i] = 0.0;
+            }
+            part = 0.0;
+            for (int j = tid; j < i; j += TRI_THREADS) {
+                const double t = VV(i - 1, j);
+                nxt[j] = t;
+                if (j < i - 1) part = fma(t, t, part);
+                VV(i, j) = 0.0;
+                VV(j, i) = 0.0;
+            }
+            sigma = block_sum_tri(part, red);
+        } else {
+            const double f = cur[i - 1];
+            double g = sqrt(sigma);
+            if (f > 0) g = -g;
+            const double h = sigma - f * g, vlast = f - g;
+            // p = A v / h over the leading i x i block, and v . p
+            double fpart = 0.0;
+            for (int j0 = 0; j0 < i; j0 += RPT) { // uniform trip count: the shuffles need the whole warp
+                const int j = j0 + rl;
+                double gs = 0.0;
+                if (j < i) { // four independent partial sums, their loads issued together: a thread's own chain is the critical path
+                    double g1 = 0.0, g2 = 0.0, g3 = 0.0;
+                    int k = q4;
+                    for (; k + 12 < i; k += 16) {
+                        const double a0 = VV(j, k), a1 = VV(j, k + 4), a2 = VV(j, k + 8), a3 = VV(j, k + 12);
+                        const double v0 = cur[k], v1 = cur[k + 4], v2 = cur[k + 8], v3 = k + 12 == i - 1 ? vlast : cur[k + 12];
+                        gs = fma(a0, v0, gs); g1 = fma(a1, v1, g1); g2 = fma(a2, v2, g2); g3 = fma(a3, v3, g3);
+                    }
+                    for (; k < i; k += 4) gs = fma(VV(j, k), k == i - 1 ? vlast : cur[k], gs);
+                    gs = (gs + g1) + (g2 + g3);
+                }
+                gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+                gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+                if (j < i && q4 == 0) {
+                    const double pj = gs / h;
+                    e[j] = pj;
+                    fpart = fma(pj, j == i - 1 ? vlast : cur[j], fpart);
+                }
+            }
+            const double hh = block_sum_tri(fpart, red) / (h + h); // (its barriers: p is complete)
+            if (tid == 0) {
+                e[i] = g;
+                d[i] = h;
+            }
+            // A -= v q^T + q v^T with q = p - hh v, both triangles; row i - 1 of the result is the next vector
+            double spart = 0.0;
+            for (int k0 = 0; k0 < i; k0 += RPT) {
+                const int k = k0 + rl;
+                if (k < i) {
+                    const double vk = k == i - 1 ? vlast : cur[k], qk = fma(-hh, vk, e[k]);
+                    auto upd = [&](const int j, const double x, const double vj, const double ej) {
+                        const double qj = fma(-hh, vj, ej);
+                        return __dsub_rn(x, __dadd_rn(__dmul_rn(vj, qk), __dmul_rn(qj, vk)));
+                    };
+                    int j = q4;
+                    for (; j + 12 < i; j += 16) { // four elements at a time, loads first
+                        const double x0 = VV(k, j), x1 = VV(k, j + 4), x2 = VV(k, j + 8), x3 = VV(k, j + 12);
+                        const double v0 = cur[j], v1 = cur[j + 4], v2 = cur[j + 8], v3 = j + 12 == i - 1 ? vlast : cur[j + 12];
+                        const double e0 = e[j], e1 = e[j + 4], e2 = e[j + 8], e3 = e[j + 12];
+                        const double n0 = upd(j, x0, v0, e0), n1 = upd(j + 4, x1, v1, e1), n2 = upd(j + 8, x2, v2, e2), n3 = upd(j + 12, x3, v3, e3);
+                        VV(k, j) = n0; VV(k, j + 4) = n1; VV(k, j + 8) = n2; VV(k, j + 12) = n3;
+                        if (k == i - 1) {
+                            nxt[j] = n0; nxt[j + 4] = n1; nxt[j + 8] = n2;
+                            spart = fma(n0, n0, spart); spart = fma(n1, n1, spart); spart = fma(n2, n2, spart);
+                            if (j + 12 < i - 1) {
+                                nxt[j + 12] = n3;
+                                spart = fma(n3, n3, spart);
+                            }
+                        }
+                    }
+                    for (; j < i; j += 4) {
+                        const double nv = upd(j, VV(k, j), j == i - 1 ? vlast : cur[j], e[j]);
+                        VV(k, j) = nv;
+                        if (k == i - 1 && j < i - 1) {
+                            nxt[j] = nv;
+                            spart = fma(nv, nv, spart);
+                        }
+                    }
+                }
+                if (k0 <= i - 1 && i - 1 < k0 + RPT) { // the trip that holds row i - 1: its four owners sum the next squared norm
+                    spart += __shfl_xor_sync(0xffffffffu, spart, 1);
+                    spart += __shfl_xor_sync(0xffffffffu, spart, 2);
+                    if (k == i - 1 && q4 == 0) s_sigma = spart;
+                }
+            }
+            for (int j = tid; j < i; j += TRI_THREADS) {
+                VV(j, i) = j == i - 1 ? vlast : cur[j]; // the Householder vector, for the accumulation below
+                VV(i, j) = 0.0;
+            }
+            __syncthreads();
+            sigma = s_sigma;
+        }
+        double *t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    // ---- accumulate the transformations: Q = H(1) ... H(n-1) built up from the identity, leading block by leading block ----
+    __syncthreads();
+#ifdef HDB_MODAL_CLOCKS
+    if (tid == 0 && blockIdx.x == 0) printf("[tridiag] reduction done at %lld\n", clock64());
+#endif
+    for (int j = tid; j < n; j += TRI_THREADS) {
+        w[j] = VV(j, j); // the diagonal of T (neither vector buffer is needed any more)
+        VV(j, j) = 1.0;
+    }
+    __syncthreads();
+    for (int i = 0; i < n - 1; i++) {
+        const double h = d[i + 1];
+        for (int j0 = 0; j0 <= i; j0 += RPT) { // four threads per column; column i is still the unit vector
+            const int j = j0 + rl;
+            double gs = 0.0;
+            if (j < i) {
+                double g1 = 0.0, g2 = 0.0, g3 = 0.0;
+                int k = q4;
+                for (; k + 12 <= i; k += 16) {
+                    const double a0 = VV(k, i + 1), a1 = VV(k + 4, i + 1), a2 = VV(k + 8, i + 1), a3 = VV(k + 12, i + 1);
+                    const double b0 = VV(k, j), b1 = VV(k + 4, j), b2 = VV(k + 8, j), b3 = VV(k + 12, j);
+                    gs = fma(a0, b0, gs); g1 = fma(a1, b1, g1); g2 = fma(a2, b2, g2); g3 = fma(a3, b3, g3);
+                }
+                for (; k <= i; k += 4) gs = fma(VV(k, i + 1), VV(k, j), gs);
+                gs = (gs + g1) + (g2 + g3);
+            }
+            gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+            gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+            if (j < i) {
+                const double gh = h != 0.0 ? gs / h : 0.0;
+                int k = q4;
+                for (; k + 12 <= i; k += 16) {
+                    const double a0 = VV(k, i + 1), a1 = VV(k + 4, i + 1), a2 = VV(k + 8, i + 1), a3 = VV(k + 12, i + 1);
+                    const double b0 = VV(k, j), b1 = VV(k + 4, j), b2 = VV(k + 8, j), b3 = VV(k + 12, j);
+                    VV(k, j) = fma(-gh, a0, b0); VV(k + 4, j) = fma(-gh, a1, b1); VV(k + 8, j) = fma(-gh, a2, b2); VV(k + 12, j) = fma(-gh, a3, b3);
+                }
+                for (; k <= i; k += 4) VV(k, j) = fma(-gh, VV(k, i + 1), VV(k, j));
+            } else if (j == i) {
+                const double gh = h != 0.0 ? VV(i, i + 1) / h : 0.0;
+                for (int k = q4; k <= i; k += 4) VV(k, i) = fma(-gh, VV(k, i + 1), k == i ? 1.0 : 0.0); // (overwrites the vector of the step before)
+            }
+        }
+        __syncthreads();
+    }
+#ifdef HDB_MODAL_CLOCKS
+    if (tid == 0 && blockIdx.x == 0) printf("[tridiag] accumulation done at %lld\n", clock64());
+#endif
+    for (int k = tid; k < n - 1; k += TRI_THREADS) VV(k, n - 1) = 0.0; // the last vector's column: the unit vector
+    for (int j = tid; j < n; j += TRI_THREADS) d[j] = w[j];
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < n; i++) e[i - 1] = e[i]; // tql2 prologue
+        e[n - 1] = 0.0;
+    }
+    __syncthreads();
+#undef VV
+}
+
 // Second half: implicit QL with accumulated vectors (tql2) on the tridiagonal (d, e), rotating the columns of V.
 __device__ __forceinline__ int sym_ql_smem(double *V, const int LD, const int n, double *d, double *e, double *cc, double *ss, double *red)
 {
@@ -521,27 +726,43 @@ cudaError_t launch_modal_eigen(const ModalLaunch &M, int smemOptin, cudaStream_t
 // ------------------------------------------------------------------------------------------------
 constexpr int CH_WARPS = 4; // models per block of the chain kernel
 
-__global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_tridiag(const ModalLaunch M, const int LD)
+__global__ void __launch_bounds__(TRI_THREADS, 1) k_modal_tridiag(const ModalLaunch M, const int LD, const int LDT)
 {
     extern __shared__ __align__(16) double sm[];
     const int n = M.s, tid = threadIdx.x, model = blockIdx.x;
-    double *V = sm;
-    double *d = V + (size_t)LD * n, *e = d + n, *red = e + n;
-#define VV(i, j) V[(i) + (size_t)(j) * LD]
+    double *V = sm; // [n][n], element (i, j) at i + j * LDT
+    double *d = V + (size_t)LDT * n, *e = d + n, *w = e + n, *red = w + n;
+#define VV(i, j) V[(i) + (size_t)(j) * LDT]
     const double *sol = M.sol + (size_t)model * n * M.dof;
     const double *ms = M.msqrt + (size_t)model * n;
-    for (int idx = tid; idx < n * n; idx += EIG_THREADS) { // B, symmetrised
+#ifdef HDB_MODAL_CLOCKS
+    if (tid == 0 && blockIdx.x == 0) printf("[tridiag] start at %lld\n", clock64());
+#endif
+    for (int idx = tid; idx < n * n; idx += TRI_THREADS) { // B, symmetrised (both triangles: bij + bji commutes)
         const int i = idx % n, j = idx / n;
         const double bij = ms[i] * sol[(size_t)j * M.dof + M.massDof[i]];
         const double bji = ms[j] * sol[(size_t)i * M.dof + M.massDof[j]];
-        VV(i, j) = 0.5 * (bij + bji);
+        VV(i, j) = i <= j ? 0.5 * (bij + bji) : 0.5 * (bji + bij);
     }
     __syncthreads();
-    sym_tridiag_smem(V, LD, n, d, e, red);
-    double *q = M.qScratch + (size_t)model * n * LD;
-    for (int idx = tid; idx < n * LD; idx += EIG_THREADS) q[idx] = V[idx];
+#ifdef HDB_MODAL_CLOCKS
+    if (tid == 0 && blockIdx.x == 0) printf("[tridiag] B built at %lld\n", clock64());
+#endif
+    sym_tridiag_full(V, LDT, n, d, e, w, red);
+#ifdef HDB_MODAL_CLOCKS
+    if (tid == 0 && blockIdx.x == 0) printf("[tridiag] tridiagonal form at %lld\n", clock64());
+#endif
+    double *q = M.qScratch + (size_t)model * n * LD; // the finish kernel's layout: column stride LD
+    for (int idx = tid; idx < n * n; idx += TRI_THREADS) {
+        const int i = idx % n, j = idx / n;
+        q[i + (size_t)j * LD] = VV(i, j);
+    }
+#ifdef HDB_MODAL_CLOCKS
+    __syncthreads();
+    if (tid == 0 && blockIdx.x == 0) printf("[tridiag] Q stored at %lld\n", clock64());
+#endif
     double *de = M.deScratch + (size_t)model * 2 * n;
-    for (int j = tid; j < n; j += EIG_THREADS) {
+    for (int j = tid; j < n; j += TRI_THREADS) {
         de[j] = d[j];
         de[n + j] = e[j];
     }
@@ -886,10 +1107,17 @@ static size_t finish_smem(int n, int &LD)
     return ((size_t)LD * n + 2 * (size_t)n + (size_t)2 * KP * SH_LDB) * sizeof(double) + (size_t)n * sizeof(int) + 80;
 }
 
+static size_t tridiag_smem(int n, int &LDT)
+{
+    LDT = (n + 15) / 16 * 16 + 12; // = 12 (mod 16): see sym_tridiag_full
+    if (LDT - 16 >= n) LDT -= 16;
+    return ((size_t)LDT * n + 3 * (size_t)n + TRI_THREADS / 32 + 8) * sizeof(double) + 64;
+}
+
 bool modal_split_fits(int n, int smemOptin)
 {
-    int LD;
-    return n >= 1 && finish_smem(n, LD) + 1024 <= (size_t)smemOptin;
+    int LD, LDT;
+    return n >= 1 && finish_smem(n, LD) + 1024 <= (size_t)smemOptin && tridiag_smem(n, LDT) + 1024 <= (size_t)smemOptin;
 }
 
 void modal_split_scratch(int n, size_t &qDoubles, size_t &rotCap, size_t &maxSweeps)
@@ -906,12 +1134,13 @@ cudaError_t launch_modal_split(const ModalLaunch &M, int smemOptin, cudaStream_t
     if (M.nModels == 0) return cudaSuccess;
     int LD;
     const size_t smemF = finish_smem(M.s, LD);
-    const size_t smemT = ((size_t)LD * M.s + 2 * (size_t)M.s + EIG_THREADS / 32 + 8) * sizeof(double) + 64;
-    if (smemF + 1024 > (size_t)smemOptin) return cudaErrorInvalidConfiguration;
+    int LDT;
+    const size_t smemT = tridiag_smem(M.s, LDT);
+    if (smemF + 1024 > (size_t)smemOptin || smemT + 1024 > (size_t)smemOptin) return cudaErrorInvalidConfiguration;
     cudaError_t e;
     if (smemT > 48 * 1024 && (e = cudaFuncSetAttribute(k_modal_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT)) != cudaSuccess) return e;
     if (smemF > 48 * 1024 && (e = cudaFuncSetAttribute(k_modal_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF)) != cudaSuccess) return e;
-    k_modal_tridiag<<<M.nModels, EIG_THREADS, smemT, st>>>(M, LD);
+    k_modal_tridiag<<<M.nModels, TRI_THREADS, smemT, st>>>(M, LD, LDT);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     const size_t smemC = (size_t)CH_WARPS * 2 * M.s * sizeof(double);
     if (smemC > 48 * 1024 && (e = cudaFuncSetAttribute(k_modal_ql_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC)) != cudaSuccess) return e;
