@@ -335,7 +335,11 @@ def main():
     N, nLC, M = args.bays, args.cases, args.models_per_gpu
     strong = args.total_models > 0
     if strong:
-        M = (args.total_models + world - 1) // world
+        from hd_b200 import _lib
+        if args.total_models % world:
+            raise SystemExit("--total-models must be a multiple of the number of ranks")
+        first, M = _lib.shard_range(args.total_models, world, rank)  # the library's contiguous-range rule; == (rank * M, M)
+        assert first == rank * M
 
     from hd_b200 import frames
     from hd_b200.model import flatten_model

@@ -29,6 +29,7 @@ SYMBOLS = [
     "hdb_device_count", "hdb_error_string", "hdb_last_error_detail", "hdb_version",
     "hdb_multi_create", "hdb_multi_destroy", "hdb_multi_device_count", "hdb_multi_shard", "hdb_multi_topology",
     "hdb_multi_static_batch", "hdb_multi_static_batch_dev", "hdb_multi_synchronize", "hdb_multi_gather_summary",
+    "hdb_shard_range",
 ]
 
 
@@ -102,6 +103,7 @@ def lib():
         L.hdb_multi_destroy.restype = None
         L.hdb_multi_device_count.argtypes = [vp]
         L.hdb_multi_shard.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32)]
+        L.hdb_shard_range.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
         L.hdb_multi_topology.argtypes = [vp, i32]
         L.hdb_multi_topology.restype = vp
         L.hdb_multi_static_batch.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
@@ -319,6 +321,13 @@ class Topology:
         ms = np.zeros(8, dtype=np.float32)
         n = check(lib().hdb_last_kernel_ms(self._h, _np_ptr(ms), 8), "hdb_last_kernel_ms")
         return ms[:n].tolist()
+
+
+def shard_range(n_models: int, n_shards: int, shard: int):
+    """(first, count) of shard `shard` of `n_shards`: the library's contiguous-range rule (hdb_shard_range); needs no GPU."""
+    first, count = C.c_int32(0), C.c_int32(0)
+    check(lib().hdb_shard_range(n_models, n_shards, shard, C.byref(first), C.byref(count)), "hdb_shard_range")
+    return first.value, count.value
 
 
 def launch_count() -> int:

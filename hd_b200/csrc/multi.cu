@@ -160,6 +160,13 @@ void hdb_multi_destroy(hdb_multi *m)
 
 int32_t hdb_multi_device_count(const hdb_multi *m) { return m ? (int32_t)m->topo.size() : 0; }
 
+int hdb_shard_range(int32_t nModels, int32_t nShards, int32_t shard, int32_t *first, int32_t *count)
+{
+    if (nModels < 0 || nShards < 1 || shard < 0 || shard >= nShards || !first || !count) return HDB_ERR_ARG;
+    shard_range(nModels, nShards, shard, *first, *count);
+    return HDB_OK;
+}
+
 int hdb_multi_shard(const hdb_multi *m, int32_t nModels, int32_t shard, int32_t *first, int32_t *count)
 {
     if (!m || nModels < 0 || shard < 0 || shard >= (int32_t)m->topo.size() || !first || !count) return HDB_ERR_ARG;

@@ -247,6 +247,9 @@ int hdb_multi_create(int32_t nP, const double *points, int32_t nB, const hdb_bea
 void hdb_multi_destroy(hdb_multi *m);
 int32_t hdb_multi_device_count(const hdb_multi *m);
 int hdb_multi_shard(const hdb_multi *m, int32_t nModels, int32_t shard, int32_t *first, int32_t *count);
+/* the same rule without a handle (no device needed): shard d of nShards gets a contiguous range, the first nModels % nShards
+ * shards one model more; what a one-rank-per-GPU host (bench.py under torchrun) uses for its own range */
+int hdb_shard_range(int32_t nModels, int32_t nShards, int32_t shard, int32_t *first, int32_t *count);
 hdb_topology *hdb_multi_topology(hdb_multi *m, int32_t shard); /* the per-device handle (owned by m) */
 int hdb_multi_static_batch(hdb_multi *m, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
                            double *disp, double *forces, double *react, int32_t *status, int32_t *failCase);
