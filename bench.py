@@ -533,6 +533,11 @@ def main():
     spmg = None
     if world > 1 and not args.no_extras:
         barrier()
+        # the other ranks must not wait inside an NCCL barrier here: its kernel spins on their GPUs, which this leg uses too
+        # (two processes time-slice a GPU); they block on the host store instead
+        store = dist.distributed_c10d._get_default_store()
+        if rank != 0:
+            store.wait(["single_process_leg_done"])
         if rank == 0:
             try:
                 mt = _lib.MultiTopology(fm.points, fm.beamN, fm.sections, fm.pins, fm.supports, list(range(world)))
@@ -565,6 +570,7 @@ def main():
                 del bufs
             except Exception as ex:
                 spmg = {"error": repr(ex)}
+            store.set("single_process_leg_done", "1")
         barrier()
 
     if rank != 0:
