@@ -617,7 +617,22 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
         order[rank] = j;
     }
     __syncthreads();
-    const int nOut = min(n, M.maxModes);
+    // A zero eigenvalue is not a mode: the reference skips it (model.go:818-834).  A mass row whose masses sum to exactly 0 N
+    // is a zero column of K^-1 M there (an exact zero after Dgeev's balancing); here it is a zero row and column of B whose
+    // eigenvalue comes out as round-off (the reflectors mix it in), one of the smallest in magnitude: B is positive
+    // semi-definite, real modes have lambda = 1 / omega^2 far above round-off.  So as many of the last (smallest |lambda|)
+    // entries as there are such rows are dropped, and any exact zero after them.
+    __shared__ int s_nz;
+    if (tid == 0) {
+        int nz = n;
+        const double *msq = M.msqrt + (size_t)model * n;
+        for (int i = 0; i < n; i++)
+            if (msq[i] == 0.0) nz--;
+        while (nz > 0 && d[order[nz - 1]] == 0.0) nz--;
+        s_nz = nz;
+    }
+    __syncthreads();
+    const int nOut = min(s_nz, M.maxModes);
     for (int r = tid; r < nOut; r += EIG_THREADS) {
         const double val = fabs(d[order[r]]);
         M.hz[(size_t)model * M.maxModes + r] = 1. / (sqrt(val) * 2.0 * M_PI); // model.go:830
@@ -629,18 +644,12 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
     if (!M.shapes) return;
 
     // ---- shapes: raw[r][g] = sum_j sol[j][g] * y_r[j]; unit 2-norm over all 3*nP entries ----
-    double *nrm = e; // reuse: squared norms per output mode
-    for (int r = tid; r < n; r += EIG_THREADS) nrm[r] = 0.0;
-    __syncthreads();
     constexpr int MT = 8;
     double *out = M.shapes + (size_t)model * M.maxModes * M.dof;
     for (int r0 = 0; r0 < nOut; r0 += MT) {
         int col[MT];
 #pragma unroll
         for (int q = 0; q < MT; q++) col[q] = order[min(r0 + q, nOut - 1)];
-        double sq[MT];
-#pragma unroll
-        for (int q = 0; q < MT; q++) sq[q] = 0.0;
         for (int g = tid; g < M.dof; g += EIG_THREADS) {
             double acc[MT];
 #pragma unroll
@@ -652,17 +661,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
             }
 #pragma unroll
             for (int q = 0; q < MT; q++)
-                if (r0 + q < nOut) {
-                    out[(size_t)(r0 + q) * M.dof + g] = acc[q];
-                    sq[q] = fma(acc[q], acc[q], sq[q]);
-                }
-        }
-#pragma unroll
-        for (int q = 0; q < MT; q++) {
-            double v = sq[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((tid & 31) == 0 && r0 + q < nOut) atomicAdd(&nrm[r0 + q], v);
+                if (r0 + q < nOut) out[(size_t)(r0 + q) * M.dof + g] = acc[q];
         }
     }
     __syncthreads();
@@ -670,9 +669,15 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_eigen(const ModalLaunc
     if (tid == 0 && blockIdx.x == 0) printf("[modal] shapes gemm %lld\n", clock64() - tk0);
     tk0 = clock64();
 #endif
-    for (int idx = tid; idx < nOut * M.dof; idx += EIG_THREADS) {
-        const int r = idx / M.dof;
-        out[idx] = out[idx] / sqrt(nrm[r]);
+    // unit 2-norm: a warp per mode sums the squares in a fixed order (bit-reproducible run to run), then scales
+    for (int r = tid >> 5; r < nOut; r += EIG_THREADS / 32) {
+        double *row = out + (size_t)r * M.dof;
+        double v = 0.0;
+        for (int g = tid & 31; g < M.dof; g += 32) v = fma(row[g], row[g], v);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const double nr = sqrt(v);
+        for (int g = tid & 31; g < M.dof; g += 32) row[g] = row[g] / nr;
     }
 #ifdef HDB_MODAL_CLOCKS
     __syncthreads();
@@ -1014,7 +1019,22 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) k_modal_finish(const ModalLaun
         order[rank] = j;
     }
     __syncthreads();
-    const int nOut = min(n, M.maxModes);
+    // A zero eigenvalue is not a mode: the reference skips it (model.go:818-834).  A mass row whose masses sum to exactly 0 N
+    // is a zero column of K^-1 M there (an exact zero after Dgeev's balancing); here it is a zero row and column of B whose
+    // eigenvalue comes out as round-off (the reflectors mix it in), one of the smallest in magnitude: B is positive
+    // semi-definite, real modes have lambda = 1 / omega^2 far above round-off.  So as many of the last (smallest |lambda|)
+    // entries as there are such rows are dropped, and any exact zero after them.
+    __shared__ int s_nz;
+    if (tid == 0) {
+        int nz = n;
+        const double *msq = M.msqrt + (size_t)model * n;
+        for (int i = 0; i < n; i++)
+            if (msq[i] == 0.0) nz--;
+        while (nz > 0 && d[order[nz - 1]] == 0.0) nz--;
+        s_nz = nz;
+    }
+    __syncthreads();
+    const int nOut = min(s_nz, M.maxModes);
     for (int r = tid; r < nOut; r += EIG_THREADS) {
         const double val = fabs(d[order[r]]);
         M.hz[(size_t)model * M.maxModes + r] = 1. / (sqrt(val) * 2.0 * M_PI); // model.go:830

@@ -124,3 +124,42 @@ def test_modal_edge_cases(oracle):
     m, lcs, mcs = fixtures.g_beam()
     assert api.Run(None, m, lcs, mcs) is None
     assert lcs[0].Reactions is not None and len(mcs[0].Result) == 2
+
+
+def test_modal_zero_mass_is_not_a_mode(oracle):
+    """A listed mass of exactly 0 N gives exactly zero eigenvalues of K^-1 M; the reference skips them
+    (model.go:818-834) instead of reporting an infinite frequency."""
+    N, nM = 4, 3
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    secs = frames.uniform_frame_sections(N, 7, nM)
+    massN, mass = frames.uniform_frame_masses(N, 7, nM)
+    mass = mass.copy()
+    mass[1, 2] = 0.0
+    status, nModes, hz, shapes = t.modal_batch(secs, massN, mass)
+    assert not status.any()
+    ost, on, ohz, oshapes = oracle.modal_batch(fm, secs, massN, mass)
+    assert not ost.any() and np.array_equal(on, nModes), (on, nModes)
+    assert nModes[1] < nModes[0] == nModes[2]
+    for mi in range(nM):
+        k = int(nModes[mi])
+        assert np.all(np.isfinite(hz[mi, :k]))
+        rel = np.abs(hz[mi, :k] - ohz[mi, :k]) / ohz[mi, :k]
+        assert rel.max() <= 1e-9, (mi, rel.max())
+    t.close()
+
+
+def test_modal_single_kernel_path_is_reproducible(oracle, monkeypatch):
+    """The one-kernel fallback (HDB_MODAL_SINGLE=1): same frequencies as the split pipeline at 1e-12, and its shapes are
+    bit-identical run to run (norms summed in a fixed order, no floating-point atomics)."""
+    N, nM = 8, 4
+    fm, t = topo_of(oracle, frames.uniform_frame(N))
+    secs = frames.uniform_frame_sections(N, 3, nM)
+    massN, mass = frames.uniform_frame_masses(N, 3, nM)
+    _, n0, hz0, sh0 = t.modal_batch(secs, massN, mass)
+    monkeypatch.setenv("HDB_MODAL_SINGLE", "1")
+    _, n1, hz1, sh1 = t.modal_batch(secs, massN, mass)
+    _, n2, hz2, sh2 = t.modal_batch(secs, massN, mass)
+    assert np.array_equal(n0, n1) and np.array_equal(n1, n2)
+    assert np.array_equal(hz1, hz2) and np.array_equal(sh1, sh2)
+    assert np.max(np.abs(hz1 - hz0) / hz0) <= 1e-12
+    t.close()
