@@ -44,6 +44,12 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
     while (!done) // try_wait suspends the thread for a while when the phase is not complete
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_wait_sleep(unsigned mbar, unsigned parity) // try_wait may put the warp to sleep until the phase completes
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }

@@ -47,7 +47,9 @@ struct BulkCfg {
     int stagger; // cycles by which blocks 1, 2, 3 (mod 4) start later than block 0: see the kernel
     // byte offsets of the shared-memory regions from the start of dynamic shared memory, computed on the host: as kernel
     // parameters they are constant-bank operands, not registers that live through every loop
-    unsigned oDt, oBb, oRp, oRl, oEl, oPm, oGm, oSlot, oLvm, oXs, lvmBytes, xsBytes, BS, ZB;
+    unsigned oDt, oBb, oRp, oRl, oEl, oPm, oGm, oLand, oSlot, oLvm, oXs, lvmBytes, xsBytes, BS, ZB;
+    unsigned landBytes; // one landing slot
+    unsigned magicCh; // the same for the row chunks of a case; 0 = one chunk
     int dbg; // HDB_BULK_DBG (debug instantiation only): 1 = no bulk stores, 2 = no fence, 4 = forces without arithmetic
 };
 
@@ -67,6 +69,7 @@ static size_t bulk_idx_bytes(const DevTopo &T)
     b += align16b((size_t)std::max(T.nSup * T.rWidth, 1) * 4);     //   fixed-width reaction rows
     b += align16b((size_t)T.nB * 4);                               // pin masks
     b += align16b((size_t)T.nB * 24);                              // geometry
+    b += (size_t)NW * align16b((size_t)T.rChunk * 8);              // landing slots: the load stage's third buffer per worker warp, one row chunk
     b += (size_t)NU * SLOT_BYTES;                                  // staging slots
     return b;
 }
@@ -91,7 +94,7 @@ bool solve_bulk_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPa
     if (cp < 1) cp = 1;
     for (; cp >= 1; cp--) {
         const size_t bytes = bulk_smem_bytes(T, cp);
-        if (bytes + 2048 <= (size_t)smemOptin) {
+        if (bytes + 512 <= (size_t)smemOptin) {
             if ((unsigned long long)cp * T.nB * (unsigned long long)T.nB >= (1ull << 32)) return false; // multiply-high division
             casesPerPass = cp;
             smemBytes = bytes;
@@ -112,6 +115,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
     // loads on SUPPORTED DOFs enter the reactions only (model.go:478) and are almost always zero: the load stage records
     // the non-zero ones here, (case << 16 | DOF, value), so that the recovery stage need not read p again.  More than PCAP
     // of them in one item: its reactions read p from global memory a second time.
+    __shared__ __align__(8) unsigned long long s_mbar[NW][3]; // a worker warp's three landing buffers: the bulk copy has arrived
     __shared__ unsigned s_pcnt[2], s_pkey[2][PCAP];
     __shared__ double s_pval[2][PCAP];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
         const int zb = (3 * CSP + 1) & ~1;
         sts_f64(xs0 + (unsigned)(k / zb) * xsBytes + ZB + 8u * (unsigned)(k % zb), 0.0);
     }
+    if (tid < 3 * NW) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[0][0]) + 8u * (unsigned)tid) : "memory");
     if (tid < 2) {
         s_failNF[tid] = NOFAIL;
         s_failIG[tid] = NOFAIL;
@@ -218,6 +223,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
         __syncwarp();
     };
 
+    unsigned landPhase = 0; // parity bits of this warp's three landing buffers
     for (int i = 0; i < nIt + 2; i++) {
         const unsigned buf = (unsigned)(i & 1);
         const unsigned lvB = lvm0 + buf * lvmBytes, xsB = xs0 + buf * xsBytes;
@@ -360,14 +366,12 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                             const int t = tBeg + lane + 32 * r;
                             le[r] = (unsigned)lds_s32(rlA + 4u * (unsigned)(t < tEnd ? t : tBeg));
                         }
-                        double vA[3] = {0.0, 0.0, 0.0}, vB[3] = {0.0, 0.0, 0.0};
 #pragma unroll
                         for (int r = 0; r < 3; r++) {
                             rp_[r] = tBeg + lane + 32 * r < tEnd ? (le[r] & 0xffffu) : 0xffffffffu;
                             si_[r] = le[r] >> 16;
                             rA[r] = 0.0;
                             rB[r] = 0.0;
-                            if (reread && rp_[r] != 0xffffffffu) { vA[r] = __ldcs(pA + rp_[r]); vB[r] = __ldcs(pB + rp_[r]); }
                         }
                         if (tEnd > tBeg)
                             for (int w = 0; w < RW; w++) {
@@ -388,10 +392,13 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                                     rB[r] = fma(kv[r], x1[r], rB[r]);
                                 }
                             }
+                        if (reread) { // the side list overflowed: p is read a second time (without a load the sum is the result as it stands)
 #pragma unroll
-                        for (int r = 0; r < 3; r++) {
-                            rA[r] = -vA[r] + rA[r]; // -(+0) + acc is acc, bit for bit
-                            rB[r] = -vB[r] + rB[r];
+                            for (int r = 0; r < 3; r++)
+                                if (rp_[r] != 0xffffffffu) {
+                                    rA[r] = -__ldcs(pA + rp_[r]) + rA[r];
+                                    rB[r] = -__ldcs(pB + rp_[r]) + rB[r];
+                                }
                         }
                         if (DBG) { double sink = rA[0] + rB[0]; if (sink == 1.2345e-300) tPh[15]++; const long long t_ = clock64(); tPh[12] += t_ - tq; tq = t_; }
                         slots_free();
@@ -547,22 +554,22 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                 if (wt == 0) asm volatile("ld.global.s32 %0, [%1];" : "=r"(sOld) : "l"(L.status + model) : "memory");
                 const double *pb = L.loads + ((size_t)model * L.nLC + c0) * dof;
                 unsigned failNF = NOFAIL, failIG = NOFAIL;
-                // row-chunk pairs, one per warp and round; the six 16-byte loads of the next pair are in flight while
-                // this one is scattered
-                const int stepC = NW / nCh, stepJ = NW - stepC * nCh, cStart = sw / nCh, jStart = sw - cStart * nCh;
-                auto issue = [&](int u, int cA, int j, double2 (&pn)[6]) {
-                    while (j >= nCh) { j -= nCh; cA++; }
-                    const int g0 = j * chD, nE = min(chD, dof - g0);
-                    const bool ok = u < nRowU;
-                    const double *qA = pb + (size_t)(ok ? cA : 0) * dof + (ok ? g0 : 0);
-                    const double *qB = qA + (size_t)((ok && cA + halfC < nc) ? halfC : 0) * dof;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const int p2 = 2 * (lane + 32 * k);
-                        const bool in = ok && p2 < nE;
-                        pn[k] = in ? ldg_v2_stream(qA + p2) : make_double2(0.0, 0.0);
-                        pn[3 + k] = in ? ldg_v2_stream(qB + p2) : make_double2(0.0, 0.0);
+                // Row chunk u = (case u / nCh, chunk u % nCh), warp sw takes u = sw, sw + NW, ...  The chunks arrive by bulk copies
+                // global -> shared (no load instruction, no register: the load/store unit's queue of outstanding misses is what
+                // limits a block's plain loads) into a ring of three buffers per warp - its two staging slots, idle in this
+                // stage, and a landing slot - so that two or three chunks per warp are in flight while one is scattered.
+                const int nSU = nc * nCh;
+                const int stepC = NW / nCh, stepJ = NW - stepC * nCh;
+                const unsigned mb0 = (unsigned)__cvta_generic_to_shared(&s_mbar[sw][0]);
+                const unsigned ring[3] = {slotA, slotB, smA + cfg.oLand + (unsigned)sw * cfg.landBytes};
+                int uI = sw, cI = cfg.magicCh ? (int)__umulhi((unsigned)sw, cfg.magicCh) : sw, jI = sw - cI * nCh; // next chunk to request
+                auto request = [&](int r) {
+                    if (uI < nSU && elect_one()) {
+                        const int g0 = jI * chD;
+                        bulk_load(ring[r], pb + (size_t)cI * dof + g0, (unsigned)min(chD, dof - g0) * 8u, mb0 + 8u * (unsigned)r);
                     }
+                    uI += NW; cI += stepC; jI += stepJ;
+                    if (jI >= nCh) { jI -= nCh; cI++; }
                 };
                 auto not_free = [&](int t, double v, int c, int g) { // rare: a DOF that is not free carries a load
                     if ((t & 2) && v != 0.0) failIG = min(failIG, (unsigned)(c0 + c)); // no stiffness (model.go:424-437)
@@ -574,36 +581,56 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                         }
                     }
                 };
-                double2 p0[6];
-                issue(sw, cStart, jStart, p0);
-                for (int u = sw, cA = cStart, j = jStart; u < nRowU; u += NW, cA += stepC, j += stepJ) {
-                    if (j >= nCh) { j -= nCh; cA++; }
-                    const int g0 = j * chD, nE = min(chD, dof - g0);
-                    const bool hasB = cA + halfC < nc;
-                    double2 pv[6];
+                int cS = cI, jS = jI; // chunk being scattered
 #pragma unroll
-                    for (int k = 0; k < 6; k++) pv[k] = p0[k];
-                    issue(u + NW, cA + stepC, j + stepJ, p0);
-                    const unsigned xA = xsB + (unsigned)cA * 24u, xBo = hasB ? (unsigned)halfC * 24u : 0u;
+                for (int r = 0; r < 3; r++) request(r);
+                for (int u = sw; u < nSU;) {
 #pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const int p2 = 2 * (lane + 32 * k);
-                        if (p2 < nE) {
-                            int tt[2];
-                            lds_v2s32(dtA + 4u * (unsigned)(g0 + p2), tt[0], tt[1]);
-                            const double a[2] = {pv[k].x, pv[k].y}, b[2] = {pv[3 + k].x, pv[3 + k].y};
-                            if (!is_finite(a[0]) || !is_finite(a[1])) failNF = min(failNF, (unsigned)(c0 + cA));
-                            if (hasB && (!is_finite(b[0]) || !is_finite(b[1]))) failNF = min(failNF, (unsigned)(c0 + cA + halfC));
+                    for (int r = 0; r < 3; r++) {
+                        if (u < nSU) {
+                            mbar_wait_sleep(mb0 + 8u * (unsigned)r, (landPhase >> r) & 1u); // (try_wait: the warp sleeps until the copy has landed)
+                            landPhase ^= 1u << r;
+                            const int g0 = jS * chD, nE = min(chD, dof - g0);
+                            const unsigned xA = xsB + (unsigned)cS * 24u;
+                            // All six loads first, then straight-line integer code: a warp on its own runs dependent instructions one
+                            // latency after the other.  Non-finite values are found by the largest |high word| of the lane's six values
+                            // (exponent all ones), loads on DOFs that are not free by OR-ing the value bits under the DOF's flag
+                            // mask; one compare and one vote per chunk decide whether the rare paths run at all.
+                            int tt[3][2];
+                            double a[3][2];
 #pragma unroll
-                            for (int h = 0; h < 2; h++) {
-                                if (!(tt[h] & 1)) {
-                                    sts_f64(xA + (unsigned)tt[h], a[h]);
-                                    if (hasB) sts_f64(xA + (unsigned)tt[h] + xBo, b[h]);
-                                } else if (tt[h] & 6) {
-                                    not_free(tt[h], a[h], cA, g0 + p2 + h);
-                                    if (hasB) not_free(tt[h], b[h], cA + halfC, g0 + p2 + h);
+                            for (int k = 0; k < 3; k++) {
+                                const int p2 = 2 * (lane + 32 * k), pc = p2 < nE ? p2 : 0;
+                                lds_v2o<0>(ring[r] + 8u * (unsigned)pc, a[k][0], a[k][1]);
+                                lds_v2s32(dtA + 4u * (unsigned)(g0 + pc), tt[k][0], tt[k][1]);
+                            }
+                            unsigned hmax = 0u, rare = 0u;
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                const bool in = 2 * (lane + 32 * k) < nE;
+#pragma unroll
+                                for (int h = 0; h < 2; h++) {
+                                    const int t = in ? tt[k][h] : 1; // past the end of the row: not free, nothing to check
+                                    const unsigned hi = (unsigned)__double2hiint(a[k][h]), lo = (unsigned)__double2loint(a[k][h]);
+                                    hmax = max(hmax, in ? (hi & 0x7fffffffu) : 0u);
+                                    rare |= (hi | lo) & ((t & 6) ? 0xffffffffu : 0u);
+                                    if (!(t & 1)) sts_f64(xA + (unsigned)t, a[k][h]);
                                 }
                             }
+                            if (hmax >= 0x7ff00000u) failNF = min(failNF, (unsigned)(c0 + cS));
+                            if (__any_sync(0xffffffffu, rare != 0u)) { // a DOF that is not free carries a load
+#pragma unroll
+                                for (int k = 0; k < 3; k++) {
+                                    const int p2 = 2 * (lane + 32 * k);
+#pragma unroll
+                                    for (int h = 0; h < 2; h++)
+                                        if (p2 < nE && (tt[k][h] & 6)) not_free(tt[k][h], a[k][h], cS, g0 + p2 + h);
+                                }
+                            }
+                            __syncwarp(); // every lane has read the buffer: the next chunk may land in it
+                            request(r);
+                            u += NW; cS += stepC; jS += stepJ;
+                            if (jS >= nCh) { jS -= nCh; cS++; }
                         }
                     }
                 }
@@ -658,6 +685,8 @@ cudaError_t launch_solve_bulk(const DevTopo &T, const StaticLaunch &L, cudaStrea
         cfg.oEl = o; o += al((size_t)std::max(T.nSup * T.rWidth, 1) * 4);
         cfg.oPm = o; o += al((size_t)T.nB * 4);
         cfg.oGm = o; o += al((size_t)T.nB * 24);
+        cfg.landBytes = al((size_t)T.rChunk * 8);
+        cfg.oLand = o; o += (unsigned)NW * cfg.landBytes;
         cfg.oSlot = o; o += (unsigned)NU * SLOT_BYTES;
         cfg.lvmBytes = (unsigned)cfg.s.lvmDoubles * 8u;
         cfg.xsBytes = (unsigned)cfg.s.xsDoubles * 8u;
@@ -668,6 +697,7 @@ cudaError_t launch_solve_bulk(const DevTopo &T, const StaticLaunch &L, cudaStrea
         if ((size_t)o != smem) return cudaErrorInvalidConfiguration; // the two layouts (bulk_idx_bytes) disagree
     }
     cfg.magicNB = T.nB > 1 ? (unsigned)((1ull << 32) / (unsigned)T.nB) + 1u : 0u;
+    cfg.magicCh = T.rNCh > 1 ? (unsigned)((1ull << 32) / (unsigned)T.rNCh) + 1u : 0u;
     cfg.prefetchL2 = 1;
     if (const char *e = std::getenv("HDB_BULK_PREFETCH")) cfg.prefetchL2 = atoi(e);
     cfg.stagger = 8000;
