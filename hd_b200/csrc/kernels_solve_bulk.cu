@@ -37,7 +37,6 @@ constexpr unsigned NOFAIL = NO_FAIL_CASE;
 constexpr int NU = NW + NH_WARPS;                    // unit warps: workers + helpers
 constexpr int PCAP = 64;                             // non-zero loads on supported DOFs kept per item
 constexpr int NH = (BULK_THREADS / 32 / 4 - 1) * 32; // helper threads: warps 4, 8, 12
-__device__ __forceinline__ void bar_coef() { asm volatile("bar.sync 4, %0;" ::"r"(NWT + NH) : "memory"); }
 __device__ __forceinline__ void bar_tables() { asm volatile("bar.sync 3, %0;" ::"r"(NWT + NH) : "memory"); } // workers + helpers
 
 struct BulkCfg {
@@ -224,6 +223,11 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
     };
 
     unsigned landPhase = 0; // parity bits of this warp's three landing buffers
+    // reactions: unit warp uw keeps to row chunk rJ0 (chunks rJ0, rJ0 + NU, ... when there are more chunks than unit warps) and
+    // takes the case pairs rC0, rC0 + rCStep, ... there
+    const bool rSpread = NU >= nCh;
+    const int rJ0 = rSpread ? uw % nCh : uw, rJStep = rSpread ? nCh : NU;
+    const int rC0 = rSpread ? uw / nCh : 0, rCStep = rSpread ? (NU - rJ0 + nCh - 1) / nCh : 1;
     for (int i = 0; i < nIt + 2; i++) {
         const unsigned buf = (unsigned)(i & 1);
         const unsigned lvB = lvm0 + buf * lvmBytes, xsB = xs0 + buf * xsBytes;
@@ -321,133 +325,6 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                                 if (hasB) __stcs(reinterpret_cast<double2 *>(gB + 64 * k), make_double2(dB[k][0], dB[k][1]));
                             }
                     }
-                TICK(0);
-                bar_tables(); // the helpers' reaction block is complete; everybody has read the side list's count
-                TICK(1);
-                if (!worker && hx == 0) s_pcnt[buf] = 0; // the load stage of item i starts a new list after the next barrier
-                // ---- reactions R = -p + K[r, free] d (model.go:470-489), written once: zero rows, then K d on the supported DOFs
-                //      of the chunk, then -p where p is not zero (side list; read from global memory only if it overflowed) ----
-                if (L.react) {
-                    const bool reread = pCnt > (unsigned)PCAP;
-                    for (int u = uw, cA = cStartU, j = jStartU; u < nRowU; u += NU, cA += stepCU, j += stepJU) {
-                        if (j >= nCh) { j -= nCh; cA++; }
-                        const int g0 = j * chD, nE = min(chD, dof - g0);
-                        const bool hasB = cA + halfC < nc;
-                        const int tBeg = lds_s32(rpA + 4u * (unsigned)j), tEnd = lds_s32(rpA + 4u * (unsigned)j + 4u);
-                        const double *pA = L.loads + rowBase + (size_t)cA * dof + g0;
-                        const double *pB = pA + (size_t)(hasB ? halfC : 0) * dof;
-                        const unsigned xA = xsB + (unsigned)cA * 24u, oB = hasB ? offB : 0u;
-                        // K d of up to 96 supported DOFs of the chunk first, into registers: the previous pair's copies drain meanwhile
-                        double rA[3], rB[3];
-                        unsigned rp_[3];
-                        long long tq = DBG ? clock64() : 0;
-                        auto react_item = [&](int t, double &oa, double &ob) {
-                            const unsigned e = (unsigned)lds_s32(rlA + 4u * (unsigned)t);
-                            const unsigned pos = e & 0xffffu, si = e >> 16;
-                            double vA = 0.0, vB = 0.0;
-                            if (reread) { vA = __ldcs(pA + pos); vB = __ldcs(pB + pos); }
-                            double accA = 0.0, accB = 0.0;
-                            for (int w = 0; w < RW; w++) {
-                                const unsigned en = (unsigned)lds_s32(elA + 4u * (si * (unsigned)RW + (unsigned)w));
-                                const double kv = lds_f64(ksA + (en >> 16) * 8u);
-                                const unsigned xa = xA + (en & 0xffffu) * 8u;
-                                accA = fma(kv, lds_f64(xa), accA);
-                                accB = fma(kv, lds_f64(xa + oB), accB);
-                            }
-                            oa = -vA + accA; // -(+0) + acc is acc, bit for bit
-                            ob = -vB + accB;
-                            return pos;
-                        };
-                        // the three rounds level by level: the shared-memory loads are ordered asm statements, so a round written
-                        // out on its own would wait for its three dependent levels before the next one starts
-                        unsigned le[3], si_[3];
-#pragma unroll
-                        for (int r = 0; r < 3; r++) {
-                            const int t = tBeg + lane + 32 * r;
-                            le[r] = (unsigned)lds_s32(rlA + 4u * (unsigned)(t < tEnd ? t : tBeg));
-                        }
-#pragma unroll
-                        for (int r = 0; r < 3; r++) {
-                            rp_[r] = tBeg + lane + 32 * r < tEnd ? (le[r] & 0xffffu) : 0xffffffffu;
-                            si_[r] = le[r] >> 16;
-                            rA[r] = 0.0;
-                            rB[r] = 0.0;
-                        }
-                        if (tEnd > tBeg)
-                            for (int w = 0; w < RW; w++) {
-                                unsigned en[3];
-#pragma unroll
-                                for (int r = 0; r < 3; r++) en[r] = (unsigned)lds_s32(elA + 4u * (si_[r] * (unsigned)RW + (unsigned)w));
-                                double kv[3], x0[3], x1[3];
-#pragma unroll
-                                for (int r = 0; r < 3; r++) {
-                                    kv[r] = lds_f64(ksA + (en[r] >> 16) * 8u);
-                                    const unsigned xa = xA + (en[r] & 0xffffu) * 8u;
-                                    x0[r] = lds_f64(xa);
-                                    x1[r] = lds_f64(xa + oB);
-                                }
-#pragma unroll
-                                for (int r = 0; r < 3; r++) {
-                                    rA[r] = fma(kv[r], x0[r], rA[r]);
-                                    rB[r] = fma(kv[r], x1[r], rB[r]);
-                                }
-                            }
-                        if (reread) { // the side list overflowed: p is read a second time (without a load the sum is the result as it stands)
-#pragma unroll
-                            for (int r = 0; r < 3; r++)
-                                if (rp_[r] != 0xffffffffu) {
-                                    rA[r] = -__ldcs(pA + rp_[r]) + rA[r];
-                                    rB[r] = -__ldcs(pB + rp_[r]) + rB[r];
-                                }
-                        }
-                        if (DBG) { double sink = rA[0] + rB[0]; if (sink == 1.2345e-300) tPh[15]++; const long long t_ = clock64(); tPh[12] += t_ - tq; tq = t_; }
-                        slots_free();
-                        if (DBG) { const long long t_ = clock64(); tPh[13] += t_ - tq; tq = t_; }
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            sts_v2f64(slotA + 16u * (unsigned)(lane + 32 * k), 0.0, 0.0);
-                            sts_v2f64(slotB + 16u * (unsigned)(lane + 32 * k), 0.0, 0.0);
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int r = 0; r < 3; r++)
-                            if (rp_[r] != 0xffffffffu) {
-                                sts_f64(slotA + 8u * rp_[r], rA[r]);
-                                sts_f64(slotB + 8u * rp_[r], rB[r]);
-                            }
-                        for (int t = tBeg + lane + 96; t < tEnd; t += 32) { // a chunk with more than 96 supported DOFs
-                            double oa, ob;
-                            const unsigned pos = react_item(t, oa, ob);
-                            sts_f64(slotA + 8u * pos, oa);
-                            sts_f64(slotB + 8u * pos, ob);
-                        }
-                        if (pCnt != 0u && !reread) { // rare: non-zero loads on supported DOFs of this item
-                            __syncwarp();
-                            for (unsigned q = (unsigned)lane; q < pCnt; q += 32u) {
-                                const unsigned key = s_pkey[buf][q];
-                                const int c = (int)(key >> 16), g = (int)(key & 0xffffu) - g0;
-                                if (g >= 0 && g < nE && (c == cA || (hasB && c == cA + halfC))) {
-                                    const unsigned a = (c == cA ? slotA : slotB) + 8u * (unsigned)g;
-                                    sts_f64(a, -s_pval[buf][q] + lds_f64(a));
-                                }
-                            }
-                        }
-                        if (DBG) { const long long t_ = clock64(); tPh[14] += t_ - tq; tq = t_; }
-                        double *gA = L.react + rowBase + (size_t)cA * dof + g0;
-                        commit_pair(gA, (unsigned)nE * 8u, gA + (size_t)halfC * dof, hasB ? (unsigned)nE * 8u : 0u);
-                        if (DBG) { const long long t_ = clock64(); tPh[15] += t_ - tq; tq = t_; }
-                    }
-                }
-                TICK(2);
-                if (cfg.prefetchL2 == 3 && i < nIt && sw == 0 && lane < 2) { // late prefetch of the next item's inputs
-                    const int passN = i % cfg.s.nPass;
-                    const int modelN = (int)blockIdx.x + (i / cfg.s.nPass) * (int)gridDim.x;
-                    const int ncN = min(CSP, L.nLC - passN * CSP);
-                    if (lane == 0) prefetch_run(L.loads + ((size_t)modelN * L.nLC + passN * CSP) * dof, (size_t)ncN * dof * 8, l2_policy_evict_last());
-                    if (lane == 1 && passN == 0) prefetch_run(L.Lm + (size_t)modelN * T.nSlots, (size_t)T.nSlots * 8, l2_policy_evict_last());
-                }
-                // ---- beam end forces s = k (T Zo), model.go:455-468: lane = (case, beam) item of the first half of the cases
-                //      and the same beam in the second half, 48 bytes each ----
                 if (L.forces) {
                     // beam coefficients of the model (element.cuh; the divisions are why they are tabulated once per item)
                     for (int b = worker ? wt : nB; b < nB; b += NWT) {
@@ -463,7 +340,134 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                         const unsigned a = lvB + (unsigned)b * 8u; // component-major: conflict-free
                         sts_f64(a, cf.EFL); sts_f64(a + cs, cf.EJL3); sts_f64(a + 2u * cs, cf.EJL2); sts_f64(a + 3u * cs, cf.EJL);
                     }
-                    bar_coef(); // the table is complete
+                }
+                TICK(0);
+                bar_tables(); // the helpers' reaction block and the workers' coefficient table are complete; everybody has read the side list's count
+                TICK(1);
+                if (!worker && hx == 0) s_pcnt[buf] = 0; // the load stage of item i starts a new list after the next barrier
+                // ---- reactions R = -p + K[r, free] d (model.go:470-489), written once: zero rows, then K d on the supported DOFs
+                //      of the chunk, then -p where p is not zero (side list; read from global memory only if it overflowed) ----
+                if (L.react) {
+                    // A warp keeps to ONE row chunk j (rJ0; several when there are more chunks than warps) and takes its share of
+                    // the case pairs there: the chunk's supported DOFs, their positions and the entries of their reaction rows
+                    // are read once per item instead of once per unit, and the staging slots need their zeros only once (a unit
+                    // overwrites exactly the positions the unit before it wrote).
+                    const bool reread = pCnt > (unsigned)PCAP;
+                    for (int j = rJ0; j < nCh; j += rJStep) {
+                        const int g0 = j * chD, nE = min(chD, dof - g0);
+                        const int tBeg = lds_s32(rpA + 4u * (unsigned)j), tEnd = lds_s32(rpA + 4u * (unsigned)j + 4u);
+                        unsigned le[3], rp_[3];
+#pragma unroll
+                        for (int r = 0; r < 3; r++) {
+                            const int t = tBeg + lane + 32 * r;
+                            le[r] = (unsigned)lds_s32(rlA + 4u * (unsigned)(t < tEnd ? t : tBeg));
+                        }
+#pragma unroll
+                        for (int r = 0; r < 3; r++) rp_[r] = tBeg + lane + 32 * r < tEnd ? (le[r] & 0xffffu) : 0xffffffffu;
+                        unsigned row_[3]; // first entry of the DOF's reaction row
+#pragma unroll
+                        for (int r = 0; r < 3; r++) row_[r] = elA + 4u * (le[r] >> 16) * (unsigned)RW;
+                        bool clean = false; // the slots hold zeros wherever this chunk has no supported DOF
+                        for (int cA = rC0; cA < halfC; cA += rCStep) {
+                            const bool hasB = cA + halfC < nc;
+                            const double *pA = L.loads + rowBase + (size_t)cA * dof + g0;
+                            const double *pB = pA + (size_t)(hasB ? halfC : 0) * dof;
+                            const unsigned xA = xsB + (unsigned)cA * 24u, oB = hasB ? offB : 0u;
+                            // K d of up to 96 supported DOFs of the chunk first, into registers: the previous pair's copies drain meanwhile
+                            double rA[3] = {0.0, 0.0, 0.0}, rB[3] = {0.0, 0.0, 0.0};
+                            auto react_item = [&](int t, double &oa, double &ob) {
+                                const unsigned e = (unsigned)lds_s32(rlA + 4u * (unsigned)t);
+                                const unsigned pos = e & 0xffffu, si = e >> 16;
+                                double vA = 0.0, vB = 0.0;
+                                if (reread) { vA = __ldcs(pA + pos); vB = __ldcs(pB + pos); }
+                                double accA = 0.0, accB = 0.0;
+                                for (int w = 0; w < RW; w++) {
+                                    const unsigned en = (unsigned)lds_s32(elA + 4u * (si * (unsigned)RW + (unsigned)w));
+                                    const double kv = lds_f64(ksA + (en >> 16) * 8u);
+                                    const unsigned xa = xA + (en & 0xffffu) * 8u;
+                                    accA = fma(kv, lds_f64(xa), accA);
+                                    accB = fma(kv, lds_f64(xa + oB), accB);
+                                }
+                                oa = -vA + accA; // -(+0) + acc is acc, bit for bit
+                                ob = -vB + accB;
+                                return pos;
+                            };
+                            if (tEnd > tBeg)
+                                for (int w = 0; w < RW; w++) { // the three rounds level by level (the shared-memory loads are ordered asm statements)
+                                    unsigned en[3];
+#pragma unroll
+                                    for (int r = 0; r < 3; r++) en[r] = (unsigned)lds_s32(row_[r] + 4u * (unsigned)w);
+                                    double kv[3], x0[3], x1[3];
+#pragma unroll
+                                    for (int r = 0; r < 3; r++) {
+                                        kv[r] = lds_f64(ksA + (en[r] >> 16) * 8u);
+                                        const unsigned xa = xA + (en[r] & 0xffffu) * 8u;
+                                        x0[r] = lds_f64(xa);
+                                        x1[r] = lds_f64(xa + oB);
+                                    }
+#pragma unroll
+                                    for (int r = 0; r < 3; r++) {
+                                        rA[r] = fma(kv[r], x0[r], rA[r]);
+                                        rB[r] = fma(kv[r], x1[r], rB[r]);
+                                    }
+                                }
+                            if (reread) { // the side list overflowed: p is read a second time (without a load the sum is the result as it stands)
+#pragma unroll
+                                for (int r = 0; r < 3; r++)
+                                    if (rp_[r] != 0xffffffffu) {
+                                        rA[r] = -__ldcs(pA + rp_[r]) + rA[r];
+                                        rB[r] = -__ldcs(pB + rp_[r]) + rB[r];
+                                    }
+                            }
+                            slots_free();
+                            if (!clean) {
+#pragma unroll
+                                for (int k = 0; k < 3; k++) {
+                                    sts_v2f64(slotA + 16u * (unsigned)(lane + 32 * k), 0.0, 0.0);
+                                    sts_v2f64(slotB + 16u * (unsigned)(lane + 32 * k), 0.0, 0.0);
+                                }
+                                __syncwarp();
+                                clean = true;
+                            }
+#pragma unroll
+                            for (int r = 0; r < 3; r++)
+                                if (rp_[r] != 0xffffffffu) {
+                                    sts_f64(slotA + 8u * rp_[r], rA[r]);
+                                    sts_f64(slotB + 8u * rp_[r], rB[r]);
+                                }
+                            for (int t = tBeg + lane + 96; t < tEnd; t += 32) { // a chunk with more than 96 supported DOFs
+                                double oa, ob;
+                                const unsigned pos = react_item(t, oa, ob);
+                                sts_f64(slotA + 8u * pos, oa);
+                                sts_f64(slotB + 8u * pos, ob);
+                            }
+                            if (pCnt != 0u && !reread) { // rare: non-zero loads on supported DOFs of this item
+                                __syncwarp();
+                                for (unsigned q = (unsigned)lane; q < pCnt; q += 32u) {
+                                    const unsigned key = s_pkey[buf][q];
+                                    const int c = (int)(key >> 16), g = (int)(key & 0xffffu) - g0;
+                                    if (g >= 0 && g < nE && (c == cA || (hasB && c == cA + halfC))) {
+                                        const unsigned a = (c == cA ? slotA : slotB) + 8u * (unsigned)g;
+                                        sts_f64(a, -s_pval[buf][q] + lds_f64(a));
+                                    }
+                                }
+                            }
+                            double *gA = L.react + rowBase + (size_t)cA * dof + g0;
+                            commit_pair(gA, (unsigned)nE * 8u, gA + (size_t)halfC * dof, hasB ? (unsigned)nE * 8u : 0u);
+                        }
+                    }
+                }
+                TICK(2);
+                if (cfg.prefetchL2 == 3 && i < nIt && sw == 0 && lane < 2) { // late prefetch of the next item's inputs
+                    const int passN = i % cfg.s.nPass;
+                    const int modelN = (int)blockIdx.x + (i / cfg.s.nPass) * (int)gridDim.x;
+                    const int ncN = min(CSP, L.nLC - passN * CSP);
+                    if (lane == 0) prefetch_run(L.loads + ((size_t)modelN * L.nLC + passN * CSP) * dof, (size_t)ncN * dof * 8, l2_policy_evict_last());
+                    if (lane == 1 && passN == 0) prefetch_run(L.Lm + (size_t)modelN * T.nSlots, (size_t)T.nSlots * 8, l2_policy_evict_last());
+                }
+                // ---- beam end forces s = k (T Zo), model.go:455-468: lane = (case, beam) item of the first half of the cases
+                //      and the same beam in the second half, 48 bytes each ----
+                if (L.forces) {
                     double *out = L.forces + ((size_t)model * L.nLC + c0) * nB * 6;
                     const int nItA = halfC * nB, nItB = (nc - halfC) * nB, nFU = (nItA + 31) / 32;
                     for (int u = uw; u < nFU; u += NU) {
