@@ -205,13 +205,13 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
 
     const int uw = worker ? sw : NW + (warp >> 2) - 1; // unit-warp index: workers, then helpers
     const unsigned slotA = slot0 + (unsigned)uw * SLOT_BYTES, slotB = slotA + CHUNK_BYTES;
-    const unsigned long long polOut = l2_policy_evict_first();
     // hand both staging slots of this warp to the bulk-copy engine: generic-proxy writes ordered before the async-proxy
     // reads, then one elected lane issues the copies
     auto commit_pair = [&](double *gA, unsigned bytesA, double *gB, unsigned bytesB) {
         if (!(DBG && (cfg.dbg & 2))) fence_async_smem();
         __syncwarp();
         if (elect_one() && !(DBG && (cfg.dbg & 1))) {
+            const unsigned long long polOut = l2_policy_evict_first(); // (made here: two registers less across every loop of the kernel)
             bulk_store(gA, slotA, bytesA, polOut);
             if (bytesB) bulk_store(gB, slotB, bytesB, polOut);
             bulk_commit();
@@ -367,6 +367,12 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                         unsigned row_[3]; // first entry of the DOF's reaction row
 #pragma unroll
                         for (int r = 0; r < 3; r++) row_[r] = elA + 4u * (le[r] >> 16) * (unsigned)RW;
+                        const bool hoist = RW <= 3; // rows of up to three entries (a column or a girder end): the entries stay in registers
+                        unsigned en_[3][3];
+#pragma unroll
+                        for (int w = 0; w < 3; w++)
+#pragma unroll
+                            for (int r = 0; r < 3; r++) en_[w][r] = (hoist && w < RW) ? (unsigned)lds_s32(row_[r] + 4u * (unsigned)w) : 0u;
                         bool clean = false; // the slots hold zeros wherever this chunk has no supported DOF
                         for (int cA = rC0; cA < halfC; cA += rCStep) {
                             const bool hasB = cA + halfC < nc;
@@ -392,7 +398,25 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                                 ob = -vB + accB;
                                 return pos;
                             };
-                            if (tEnd > tBeg)
+                            if (tEnd > tBeg && hoist) {
+#pragma unroll
+                                for (int w = 0; w < 3; w++)
+                                    if (w < RW) {
+                                        double kv[3], x0[3], x1[3];
+#pragma unroll
+                                        for (int r = 0; r < 3; r++) {
+                                            kv[r] = lds_f64(ksA + (en_[w][r] >> 16) * 8u);
+                                            const unsigned xa = xA + (en_[w][r] & 0xffffu) * 8u;
+                                            x0[r] = lds_f64(xa);
+                                            x1[r] = lds_f64(xa + oB);
+                                        }
+#pragma unroll
+                                        for (int r = 0; r < 3; r++) {
+                                            rA[r] = fma(kv[r], x0[r], rA[r]);
+                                            rB[r] = fma(kv[r], x1[r], rB[r]);
+                                        }
+                                    }
+                            } else if (tEnd > tBeg)
                                 for (int w = 0; w < RW; w++) { // the three rounds level by level (the shared-memory loads are ordered asm statements)
                                     unsigned en[3];
 #pragma unroll
