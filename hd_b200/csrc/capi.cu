@@ -324,7 +324,7 @@ static int ensure_workspace(hdb_topology *t, size_t models)
     for (int i = 0; i < 2; i++) {
         CUDA_TRY(cudaMalloc(&t->Wbuf[i], (size_t)t->S.nSlots * ld * sizeof(double)));
         CUDA_TRY(cudaMalloc(&t->Lmbuf[i], (size_t)t->S.nSlots * ld * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&t->Ksfbuf[i], std::max<size_t>(1, ld * (size_t)t->S.nnzR) * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&t->Ksfbuf[i], std::max<size_t>(1, ld * (size_t)t->S.nnzR) * sizeof(double) + 16)); // + 16: the solve kernel's bulk copy of a model's block covers whole 16-byte pairs
     }
     if (!assemble_fits_smem(t->D, t->smemOptin))
         CUDA_TRY(cudaMalloc(&t->keScratch, ld * (size_t)t->S.nB * KE_LD * sizeof(double)));

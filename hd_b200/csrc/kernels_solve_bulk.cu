@@ -75,7 +75,7 @@ static size_t bulk_idx_bytes(const DevTopo &T)
 
 static size_t bulk_lvm_doubles(const DevTopo &T)
 {
-    size_t d = std::max<size_t>((size_t)T.nSlots, (size_t)T.nB * 4 + (size_t)T.nnzR + 1);
+    size_t d = std::max<size_t>((size_t)T.nSlots, (size_t)T.nB * 4 + (size_t)T.nnzR + 4); // + the odd doubles of the 16-byte bulk copy and the padding zero
     return (d + 1) & ~(size_t)1;
 }
 
@@ -86,7 +86,7 @@ static size_t bulk_smem_bytes(const DevTopo &T, int cp)
 
 bool solve_bulk_config(const DevTopo &T, int nLC, int smemOptin, int &casesPerPass, size_t &smemBytes)
 {
-    if (T.dof % 2 || T.dof >= 65536 || T.rWidth > 8 || T.nnzR >= 65535 || T.nSup >= 65535 || T.rChunk <= 0) return false;
+    if (T.dof % 2 || T.dof >= 65536 || T.rWidth > 8 || T.nnzR >= 65534 || T.nSlots % 2 || T.nSup >= 65535 || T.rChunk <= 0) return false;
     if (bulk_xs_doubles(T, 32) >= 65535) return false; // reaction rows keep xs offsets in 16 bits (units of 8 bytes)
     int cp = nLC < 32 ? nLC : 32;
     if (const char *e = std::getenv("HDB_CASES_PER_PASS")) cp = std::min(cp, atoi(e));
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
     // the non-zero ones here, (case << 16 | DOF, value), so that the recovery stage need not read p again.  More than PCAP
     // of them in one item: its reactions read p from global memory a second time.
     __shared__ __align__(8) unsigned long long s_mbar[NW][3]; // a worker warp's three landing buffers: the bulk copy has arrived
+    __shared__ __align__(8) unsigned long long s_mbarKF[2];   // the reaction block / the factor of an item has arrived
     __shared__ unsigned s_pcnt[2], s_pkey[2][PCAP];
     __shared__ double s_pval[2][PCAP];
     const int tid = threadIdx.x, lane = tid & 31;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
         const int q0 = __ldg(T.rptr + si), q1 = __ldg(T.rptr + si + 1);
         for (int w = 0; w < RW; w++) {
             const int q = q0 + w;
-            const unsigned e = q < q1 ? (((unsigned)xoff(__ldg(T.rcol + q)) >> 3) | ((unsigned)q << 16)) : ((ZB >> 3) | ((unsigned)T.nnzR << 16));
+            const unsigned e = q < q1 ? (((unsigned)xoff(__ldg(T.rcol + q)) >> 3) | ((unsigned)q << 16)) : ((ZB >> 3) | ((unsigned)(T.nnzR + 1) << 16)); // value nnzR + 1: a zero behind the block's bulk copy
             sts_s32(elA + 4u * (unsigned)(si * RW + w), (int)e);
         }
     }
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
         sts_f64(xs0 + (unsigned)(k / zb) * xsBytes + ZB + 8u * (unsigned)(k % zb), 0.0);
     }
     if (tid < 3 * NW) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar[0][0]) + 8u * (unsigned)tid) : "memory");
+    if (tid < 2) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbarKF[tid])) : "memory");
     if (tid < 2) {
         s_failNF[tid] = NOFAIL;
         s_failIG[tid] = NOFAIL;
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
     };
 
     unsigned landPhase = 0; // parity bits of this warp's three landing buffers
+    const unsigned mbarK = (unsigned)__cvta_generic_to_shared(&s_mbarKF[0]), mbarF = mbarK + 8u;
     // reactions: unit warp uw keeps to row chunk rJ0 (chunks rJ0, rJ0 + NU, ... when there are more chunks than unit warps) and
     // takes the case pairs rC0, rC0 + rCStep, ... there
     const bool rSpread = NU >= nCh;
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
     for (int i = 0; i < nIt + 2; i++) {
         const unsigned buf = (unsigned)(i & 1);
         const unsigned lvB = lvm0 + buf * lvmBytes, xsB = xs0 + buf * xsBytes;
-        const unsigned cs = (unsigned)nB * 8u, ksA = lvB + 4u * cs;
+        const unsigned cs = (unsigned)nB * 8u;
         if (tid < 32) {
             // ================= solver warp: item i-1 =================
             if (i >= 1 && i <= nIt) {
@@ -239,6 +242,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                 const int nc = min(CSP, L.nLC - pass * CSP);
                 const unsigned sbuf = (unsigned)(it & 1);
                 if (tid < nc) {
+                    mbar_wait_sleep(mbarF, (unsigned)it & 1u); // the factor's bulk copy (issued one iteration ago) has landed
                     const long long t0 = DBG ? clock64() : 0;
                     const unsigned tabA = lvm0 + sbuf * lvmBytes, xA = xs0 + sbuf * xsBytes + (unsigned)tid * 24u;
                     walk_ops<true>(opsA, tabA, xA, BS);
@@ -258,6 +262,8 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                 const int c0 = pass * CSP, nc = min(CSP, L.nLC - c0);
                 const int halfC = (nc + 1) >> 1;
                 const unsigned offB = (unsigned)halfC * 24u; // slot B's case in xs
+                const unsigned ksShift = (unsigned)((reinterpret_cast<uintptr_t>(L.Ksf + (size_t)model * T.nnzR) >> 3) & 1);
+                const unsigned ksA = lvB + 4u * cs + 8u * ksShift; // the reaction block in the dead factor buffer, behind the coefficient table
                 const int nRowU = halfC * nCh;               // row-chunk pairs of a [cases][dof] output
                 const size_t rowBase = ((size_t)model * L.nLC + c0) * dof;
                 const int stepC = NW / nCh, stepJ = NW - stepC * nCh, cStart = sw / nCh, jStart = sw - cStart * nCh; // unit u = (case u / nCh, chunk u % nCh), walked without divisions
@@ -282,24 +288,18 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                         if (hx == 2 && passN == 0) prefetch_run(L.Ksf + (size_t)modelN * T.nnzR, (size_t)T.nnzR * 8, polIn);
                         if (hx == 3 && passN == 0) prefetch_run(L.sections + (size_t)modelN * nB * 3, (size_t)nB * 24, polIn);
                     }
-                    // (loads in batches: the shared-memory stores are ordered asm statements, a load behind one would wait for it)
-                    if (L.react) {
-                        for (int q0 = 0; q0 < T.nnzR; q0 += 8 * NH) {
-                            double kv[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) kv[u] = q0 + u * NH + hx < T.nnzR ? __ldcs(ksf + q0 + u * NH + hx) : 0.0;
-#pragma unroll
-                            for (int u = 0; u < 8; u++)
-                                if (q0 + u * NH + hx < T.nnzR) sts_f64(ksA + 8u * (unsigned)(q0 + u * NH + hx), kv[u]);
-                        }
-                        if (hx == 0) sts_f64(ksA + 8u * (unsigned)T.nnzR, 0.0); // what the padding of the reaction rows points at
+                    // the reaction block: one bulk copy (it starts on 16 bytes, so the block may sit one double into its buffer);
+                    // the zero that the padding of the reaction rows points at lies behind the copied range
+                    if (L.react && hx == 0) {
+                        bulk_load(ksA & ~15u, ksf - ksShift, (((unsigned)T.nnzR + ksShift + 1u) & ~1u) * 8u, mbarK);
+                        sts_f64(ksA + 8u * (unsigned)(T.nnzR + 1), 0.0);
                     }
                     if (DBG && hx == 0) tPh[0] += clock64() - t0;
                 }
                 const unsigned pCnt = s_pcnt[buf]; // non-zero loads on supported DOFs of this item (read before bar_tables, reset after it)
                 // ---- displacements (model.go:446-451) ----
-                if (L.disp && worker)
-                    for (int u = sw, cA = cStart, j = jStart; u < nRowU; u += NW, cA += stepC, j += stepJ) {
+                if (L.disp) // (the helper warps too: their copy of the reaction block is under way)
+                    for (int u = uw, cA = cStartU, j = jStartU; u < nRowU; u += NU, cA += stepCU, j += stepJU) {
                         if (j >= nCh) { j -= nCh; cA++; }
                         const int g0 = j * chD, nE = min(chD, dof - g0);
                         const bool hasB = cA + halfC < nc;
@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                     }
                 }
                 TICK(0);
+                if (L.react) mbar_wait_sleep(mbarK, (unsigned)i & 1u); // the reaction block has landed (every thread observes the copy itself)
                 bar_tables(); // the helpers' reaction block and the workers' coefficient table are complete; everybody has read the side list's count
                 TICK(1);
                 if (!worker && hx == 0) s_pcnt[buf] = 0; // the load stage of item i starts a new list after the next barrier
@@ -554,17 +555,7 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                 const int pass = i % cfg.s.nPass;
                 const int model = (int)blockIdx.x + (i / cfg.s.nPass) * (int)gridDim.x;
                 const int nc = min(CSP, L.nLC - pass * CSP);
-                const double2 *wf = reinterpret_cast<const double2 *>(L.Lm + (size_t)model * T.nSlots);
-                const int n2 = T.nSlots / 2;
-                for (int s0 = 0; s0 < n2; s0 += 4 * NH) {
-                    double2 v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = s0 + u * NH + hx < n2 ? __ldcs(wf + s0 + u * NH + hx) : make_double2(0.0, 0.0);
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (s0 + u * NH + hx < n2) sts_v2f64(lvB + 16u * (unsigned)(s0 + u * NH + hx), v[u].x, v[u].y);
-                }
-                if ((T.nSlots & 1) && hx == 0) sts_f64(lvB + 8u * (unsigned)(T.nSlots - 1), __ldcs(L.Lm + (size_t)model * T.nSlots + T.nSlots - 1));
+                if (hx == 0) bulk_load(lvB, L.Lm + (size_t)model * T.nSlots, (unsigned)T.nSlots * 8u, mbarF); // one bulk copy (block columns are 6 + 10 k slots: whole 16-byte pairs)
                 for (int idx = hx; idx < T.nDummy * nc; idx += NH) {
                     const int q = idx / nc, c = idx - q * nc;
                     const int r = __ldg(T.dummyPos + q);
@@ -694,7 +685,7 @@ cudaError_t launch_solve_bulk(const DevTopo &T, const StaticLaunch &L, cudaStrea
     if (const char *e = std::getenv("HDB_SOLVE_LEGACY"))
         if (atoi(e)) return cudaSuccess; // diagnostics / tests: k_solve_pipe
     auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    if (!(al16(L.loads) && al16(L.disp) && al16(L.react) && al16(L.forces))) return cudaSuccess;
+    if (!(al16(L.loads) && al16(L.disp) && al16(L.react) && al16(L.forces) && al16(L.Lm))) return cudaSuccess;
     BulkCfg cfg;
     size_t smem = 0;
     if (!solve_bulk_config(T, L.nLC, optin, cfg.s.casesPerPass, smem)) return cudaSuccess;
