@@ -1,5 +1,5 @@
-// bulk_ops.cuh — PTX wrappers shared by the bulk-copy solve kernels (k_solve_bulk, k_solve_half): bulk copies shared ->
-// global (SASS UBLKCP), L2 cache policies, proxy fence, single-lane election, named-barrier arrive / sync.
+// bulk_ops.cuh — PTX wrappers of k_solve_bulk: bulk copies shared -> global and global -> shared (SASS UBLKCP), mbarrier
+// waits, L2 cache policy, proxy fence, single-lane election.
 #pragma once
 #include "solve_ops.cuh"
 
@@ -15,13 +15,7 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first()
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ unsigned long long l2_policy_evict_last()
-{
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-// results are written once and not read again by this kernel: they should not push the prefetched inputs out of L2
+// results are written once and not read again by this kernel: evict-first keeps them from displacing the inputs in L2
 __device__ __forceinline__ void bulk_store(void *gdst, unsigned ssrc, unsigned bytes, unsigned long long pol)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(ssrc), "r"(bytes), "l"(pol) : "memory");
@@ -31,18 +25,6 @@ __device__ __forceinline__ void bulk_load(unsigned sdst, const void *gsrc, unsig
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(unsigned mbar, unsigned parity) // does not block
-{
-    unsigned done;
-    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-    return done != 0u;
-}
-__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity)
-{
-    unsigned done = 0;
-    while (!done) // try_wait suspends the thread for a while when the phase is not complete
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_sleep(unsigned mbar, unsigned parity) // try_wait may put the warp to sleep until the phase completes
 {
@@ -54,45 +36,14 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_prefetch_l2(const void *g, unsigned bytes, unsigned long long pol)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(g), "r"(bytes), "l"(pol) : "memory");
-}
 __device__ __forceinline__ void lds_v2s32(unsigned a, int &x, int &y) { asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a)); }
 __device__ __forceinline__ void sts_v2f64(unsigned a, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory"); }
-__device__ __forceinline__ double2 ldg_v2_stream(const double *p)
-{ // read once more at most: no L1 allocation
-    double2 v;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-}
 __device__ __forceinline__ bool elect_one()
 { // one lane of the (converged) warp, as a warp-uniform predicate
     unsigned pred;
     asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
     return pred != 0u;
 }
-__device__ __forceinline__ bool is_finite(double v) { return fabs(v) <= 1.7976931348623157e308; }
-
-// prefetch a run into L2 in pieces the instruction accepts (size: multiple of 16)
-__device__ __forceinline__ void prefetch_run(const void *p, size_t bytes, unsigned long long pol)
-{
-    const char *q = reinterpret_cast<const char *>(p);
-    const size_t head = (16 - (reinterpret_cast<uintptr_t>(q) & 15)) & 15;
-    if (bytes <= head + 16) return;
-    q += head;
-    bytes = (bytes - head) & ~(size_t)15;
-    while (bytes) {
-        const unsigned n = bytes > (1u << 20) ? (1u << 20) : (unsigned)bytes;
-        bulk_prefetch_l2(q, n, pol);
-        q += n;
-        bytes -= n;
-    }
-}
-
-// named barriers as producer / consumer signals: arrive does not wait, sync waits for `count` arrivals (arrive + sync)
-__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // a beam with released ends: the condensed element is dense (feBeam2d.go:58-137).  Out of line, arguments by value and
 // the result stored straight to the staging slot, so that the caller keeps no local array

@@ -1,23 +1,30 @@
 // kernels_solve_bulk.cu — k_solve_bulk: the solve / recovery step of LinearStatic (model.go:415-489) as a persistent
-// block per SM whose results leave through the bulk-copy engine (cp.async.bulk shared -> global, SASS UBLKCP).
+// block per SM whose bytes move through the bulk-copy engine (cp.async.bulk, SASS UBLKCP) wherever that is the cheaper path.
 //
 // Same three-stage pipeline over two shared-memory buffers as k_solve_pipe (kernels_static.cu): in iteration i the
-// solver warp (alone on SM sub-partition 0) runs both block substitutions of item i-1, the twelve worker warps turn
-// item i-2's solution into its three outputs and then pull item i in.  What differs is how bytes move:
-//   * every output ([cases][dof] displacements and reactions, [cases][nB][6] beam forces) is one contiguous run per
-//     item.  A worker warp builds 1536-byte chunks of it in its own staging slot with 16-byte shared stores and hands
-//     each chunk to the bulk-copy engine: no global store instruction, no partially written line, and the copy of chunk
-//     n drains while the warp computes chunk n+1 (two slots per warp, cp.async.bulk.wait_group.read);
-//   * reactions are written ONCE: R = -p + K[r,:] d (model.go:470-489) is formed in the staging slot; p is read a
-//     second time (a coalesced 16-byte load per lane; the first read, two iterations earlier, left it in L2) instead
-//     of storing -p rows with the load stage and adding K d with reductions;
-//   * the next item's load cases, factor, reaction block and sections are prefetched into L2 with one bulk prefetch
-//     each at the start of the recovery stage, so the load stage's reads do not wait for DRAM behind the stores.
-// Units of work are flat: chunk u of an output covers elements [192 u, 192 u + 192) of the item's run, (case, DOF) or
-// (case, beam) follow from a multiply-high division.  One unit = one warp = one bulk store.
+// solver warp (warp 0; it shares SM sub-partition 0 with two helper warps only) runs both block substitutions of item
+// i-1, the nine worker warps and the helpers turn item i-2's solution into its three outputs, then the workers pull item
+// i in.  384 threads at 168 registers: every loop of this kernel is kept free of spills, which cost it more than
+// anything else that was measured (a spilled value in a unit loop: 5 to 10 % of the kernel).
+//   * Outputs.  Reactions and beam forces are built as 1536-byte chunks in a warp's staging slots with 16-byte shared
+//     stores and handed to the bulk-copy engine (fence.proxy.async, one elected lane, two slots per warp so that a pair
+//     drains while the next is built); displacements go out as 16-byte streaming stores (a second path into L2).
+//   * Reactions are written ONCE: R = -p + K[r,:] d (model.go:470-489) is formed in the slot.  Non-zero loads on supported
+//     DOFs (almost always none) travel in a side list from the load stage; p is read again only if that list overflows.
+//     A warp keeps to one row chunk: its supported DOFs, their positions and reaction-row entries are read once per item
+//     and the slots need their zeros once (a unit overwrites exactly the positions the unit before it wrote).
+//   * Inputs.  The load cases arrive by bulk copies global -> shared into a ring of three buffers per worker warp (its
+//     two staging slots, idle in that stage, and a landing slot; one mbarrier each): no load instruction and no register
+//     holds data in flight, the scatter into the right-hand sides is straight-line integer code with one vote per chunk
+//     for the rare cases.  Factor and reaction block arrive by one bulk copy each, issued by a helper thread.
+//   * No L2 prefetch and no start offset between blocks: with the copies above both measured slower or neutral.
+// Units of work are flat: chunk u of an output covers elements [192 u, 192 u + 192) of the item's run (forces) or
+// (case, row chunk) pairs; a unit handles a case of the first half of the load cases and its partner from the second
+// half, so that every table entry, coefficient and address is fetched once for two chunks.
 //
 // Needs dof even and 16-byte aligned arrays (the chunks must start on 16 bytes); otherwise, or when the model does not
-// fit, launch_solve_pipe keeps k_solve_pipe / k_solve_general.
+// fit, launch_solve_pipe keeps k_solve_pipe / k_solve_general.  profiles/experiments/ has the variants that were
+// measured and dropped.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -26,7 +33,7 @@
 
 namespace hdb {
 
-constexpr int BULK_THREADS = 384;                  // warp 0 = solver, warps 4, 8, 12 idle (its sub-partition), twelve workers
+constexpr int BULK_THREADS = 384;                  // warp 0 = solver, warps 4 and 8 = helpers (its sub-partition), nine workers
 constexpr int NW = BULK_THREADS / 32 / 4 * 3;      // worker warps
 constexpr int NH_WARPS = BULK_THREADS / 32 / 4 - 1; // helper warps (the solver's sub-partition)
 constexpr int NWT = NW * 32;                       // worker threads
@@ -36,14 +43,12 @@ constexpr unsigned SLOT_BYTES = 2u * CHUNK_BYTES;  // two slots per worker warp
 constexpr unsigned NOFAIL = NO_FAIL_CASE;
 constexpr int NU = NW + NH_WARPS;                    // unit warps: workers + helpers
 constexpr int PCAP = 64;                             // non-zero loads on supported DOFs kept per item
-constexpr int NH = (BULK_THREADS / 32 / 4 - 1) * 32; // helper threads: warps 4, 8, 12
+constexpr int NH = (BULK_THREADS / 32 / 4 - 1) * 32; // helper threads: warps 4, 8
 __device__ __forceinline__ void bar_tables() { asm volatile("bar.sync 3, %0;" ::"r"(NWT + NH) : "memory"); } // workers + helpers
 
 struct BulkCfg {
     SolveCfg s;
     unsigned magicNB; // floor(2^32 / nB) + 1: q = umulhi(e, magic) is e / nB for e * nB < 2^32; 0 = divide by one
-    int prefetchL2;
-    int stagger; // cycles by which blocks 1, 2, 3 (mod 4) start later than block 0: see the kernel
     // byte offsets of the shared-memory regions from the start of dynamic shared memory, computed on the host: as kernel
     // parameters they are constant-bank operands, not registers that live through every loop
     unsigned oDt, oBb, oRp, oRl, oEl, oPm, oGm, oLand, oSlot, oLvm, oXs, lvmBytes, xsBytes, BS, ZB;
@@ -121,9 +126,9 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0); // broadcast: the compiler then knows it is warp-uniform (bulk-copy operands live in uniform registers)
     const bool worker = (warp & 3) != 0;
-    const int sw = warp - (warp >> 2) - 1;        // worker warp index 0..11
+    const int sw = warp - (warp >> 2) - 1;        // worker warp index 0..8
     const int wt = sw * 32 + lane;                // worker thread index
-    const int hx = ((warp >> 2) - 1) * 32 + lane; // helper thread index (warps 4, 8, 12)
+    const int hx = ((warp >> 2) - 1) * 32 + lane; // helper thread index (warps 4, 8)
     const int dof = T.dof, nB = T.nB, CSP = cfg.s.casesPerPass, RW = T.rWidth, nCh = T.rNCh, chD = T.rChunk;
     const unsigned smA = (unsigned)__cvta_generic_to_shared(smem_d);
     const unsigned opsA = smA;
@@ -186,12 +191,6 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
     }
     __syncthreads();
 
-    // Every block does the same work per item, so without this all SMs would store at the same time (DRAM saturated with
-    // writes) and then load at the same time (DRAM mostly idle): blocks start a quarter of an iteration apart instead.
-    if (cfg.stagger > 0 && (blockIdx.x & 3)) {
-        const long long until = clock64() + (long long)(blockIdx.x & 3) * cfg.stagger;
-        while (clock64() < until) __nanosleep(200);
-    }
     const int nMy = (L.nModels - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int nIt = nMy * cfg.s.nPass;
     long long tSolve = 0, tAll = DBG ? clock64() : 0;
@@ -278,16 +277,6 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                     // The factor buffer is dead once the solve is over: it takes the reaction block K[sup, free] of the item (helpers,
                     // while the workers write the displacements) and its beam coefficients [4][nB] (workers, before the forces).
                     const double *ksf = L.Ksf + (size_t)model * T.nnzR;
-                    if ((cfg.prefetchL2 == 1 || cfg.prefetchL2 == 2) && i < nIt && hx < 4) {
-                        const unsigned long long polIn = cfg.prefetchL2 == 1 ? l2_policy_evict_last() : l2_policy_evict_first(); // the next item's inputs on their way into L2 while this stage stores
-                        const int passN = i % cfg.s.nPass;
-                        const int modelN = (int)blockIdx.x + (i / cfg.s.nPass) * (int)gridDim.x;
-                        const int ncN = min(CSP, L.nLC - passN * CSP);
-                        if (hx == 0) prefetch_run(L.loads + ((size_t)modelN * L.nLC + passN * CSP) * dof, (size_t)ncN * dof * 8, polIn);
-                        if (hx == 1 && passN == 0) prefetch_run(L.Lm + (size_t)modelN * T.nSlots, (size_t)T.nSlots * 8, polIn);
-                        if (hx == 2 && passN == 0) prefetch_run(L.Ksf + (size_t)modelN * T.nnzR, (size_t)T.nnzR * 8, polIn);
-                        if (hx == 3 && passN == 0) prefetch_run(L.sections + (size_t)modelN * nB * 3, (size_t)nB * 24, polIn);
-                    }
                     // the reaction block: one bulk copy (it starts on 16 bytes, so the block may sit one double into its buffer);
                     // the zero that the padding of the reaction rows points at lies behind the copied range
                     if (L.react && hx == 0) {
@@ -483,13 +472,6 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) k_solve_bulk(const DevTopo T,
                     }
                 }
                 TICK(2);
-                if (cfg.prefetchL2 == 3 && i < nIt && sw == 0 && lane < 2) { // late prefetch of the next item's inputs
-                    const int passN = i % cfg.s.nPass;
-                    const int modelN = (int)blockIdx.x + (i / cfg.s.nPass) * (int)gridDim.x;
-                    const int ncN = min(CSP, L.nLC - passN * CSP);
-                    if (lane == 0) prefetch_run(L.loads + ((size_t)modelN * L.nLC + passN * CSP) * dof, (size_t)ncN * dof * 8, l2_policy_evict_last());
-                    if (lane == 1 && passN == 0) prefetch_run(L.Lm + (size_t)modelN * T.nSlots, (size_t)T.nSlots * 8, l2_policy_evict_last());
-                }
                 // ---- beam end forces s = k (T Zo), model.go:455-468: lane = (case, beam) item of the first half of the cases
                 //      and the same beam in the second half, 48 bytes each ----
                 if (L.forces) {
@@ -717,11 +699,6 @@ cudaError_t launch_solve_bulk(const DevTopo &T, const StaticLaunch &L, cudaStrea
     }
     cfg.magicNB = T.nB > 1 ? (unsigned)((1ull << 32) / (unsigned)T.nB) + 1u : 0u;
     cfg.magicCh = T.rNCh > 1 ? (unsigned)((1ull << 32) / (unsigned)T.rNCh) + 1u : 0u;
-    cfg.prefetchL2 = 1;
-    if (const char *e = std::getenv("HDB_BULK_PREFETCH")) cfg.prefetchL2 = atoi(e);
-    cfg.stagger = 8000;
-    if (const char *e = std::getenv("HDB_BULK_STAGGER")) cfg.stagger = atoi(e);
-    if (L.nModels < 4 * nSM) cfg.stagger = 0; // a few items per block: the delay would not pay
     cfg.dbg = 0;
     if (const char *e = std::getenv("HDB_BULK_DBG")) cfg.dbg = atoi(e);
     auto kern = L.dbgClocks ? k_solve_bulk<true> : k_solve_bulk<false>;
