@@ -578,7 +578,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_solve_pipe) ----
+    # ---- roofline of the dominant kernel (k_solve_bulk) ----
     peaks, peak_src = measured_peaks()
     sub = int(os.environ.get("HDB_SUB_BATCH", "8192"))
     n_launch = args.steps * ((M + sub - 1) // sub)
