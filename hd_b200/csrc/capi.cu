@@ -753,19 +753,17 @@ static void debug_report_clocks(hdb_topology *t, int nModels)
         for (int k = 0; k < 24; k++) ph[k] += (double)d[8 + k];
     }
     if (models <= 0) return;
-    std::fprintf(stderr, "[hdb] k_solve_pipe cycles/model (last launch, %d blocks): block %.0f | solver warp %.0f | streaming warp 1:\n", n,
+    std::fprintf(stderr, "[hdb] solve kernel cycles/model (last launch, %d blocks): block %.0f | solver warp %.0f | worker warp 1:\n", n,
                  blk / models, sol / models);
     static const char *namesPipe[11] = {"Ksf/section loads issued", "-", "disp + Ksf, coefficients -> smem", "(barrier)", "react", "forces", "(barrier)", "factor gather issue",
                                         "load cases", "(barrier)", "status"};
-    static const char *namesBulk[11] = {"coefficients + Ksf -> smem", "(barrier)", "react", "forces", "disp", "(barrier)", "load cases + factor", "(barrier)", "-", "-", "-"};
+    static const char *namesBulk[11] = {"displacements + coefficient table", "(reaction block has landed)", "reactions", "beam forces", "(last copies read)", "(barrier)", "load cases", "(barrier)", "-", "-", "-"};
     const char *leg = std::getenv("HDB_SOLVE_LEGACY");
     const char **names = (leg && atoi(leg)) ? namesPipe : namesBulk;
     std::fprintf(stderr, "[hdb]  ");
     for (int k = 0; k < 11; k++) std::fprintf(stderr, " %s %.0f |", names[k], ph[k] / models);
     std::fprintf(stderr, "\n");
-    if (!(leg && atoi(leg)))
-        std::fprintf(stderr, "[hdb]   disp units: loads %.0f | wait slots %.0f | stores to slot %.0f | fence + issue %.0f || react units: items %.0f | wait slots %.0f | zero + stores %.0f | fence + issue %.0f || helper tables %.0f\n",
-                     ph[8] / models, ph[9] / models, ph[10] / models, ph[11] / models, ph[12] / models, ph[13] / models, ph[14] / models, ph[15] / models, ph[16] / models);
+    if (!(leg && atoi(leg))) std::fprintf(stderr, "[hdb]   helper warp: bulk copy of the reaction block issued after %.0f\n", ph[16] / models);
 }
 
 int hdb_static_batch_dev(hdb_topology *t, int32_t nModels, const double *sections, int32_t nLC, const double *loads,
